@@ -1,0 +1,151 @@
+/*
+ * hypo_b200.h — C ABI of the B200-native POA-consensus hot path of HyPo.
+ *
+ * This is the drop-in boundary for ONE path of the reference:
+ *     hypo::Window::generate_consensus(engine_idx)        reference src/Window.cpp:44-61
+ *       -> generate_consensus_short / _long / curate      reference src/Window.cpp:87-254
+ *       -> spoa::AlignmentEngine::align (SISD, linear)     reference external/spoa/src/sisd_alignment_engine.cpp:246-439
+ *       -> spoa::Graph::add_alignment / topological_sort   reference external/spoa/src/graph.cpp:154-353
+ *       -> spoa::Graph::generate_consensus{,_custom}       reference external/spoa/src/graph.cpp:467-476,533-568,610-705
+ * as it is driven by the "Polish with arms" block of Hypo::polish
+ * (reference src/Hypo.cpp:236-248).  Everything else in HyPo stays host code.
+ *
+ * Plain C, plain pointers and sizes; no C++/torch types cross this boundary.
+ * All entry points return 0 on success and a non-zero HYPO_E_* code on
+ * failure; hypo_gpu_last_error() then returns a human-readable message
+ * (the reference convention is fprintf(stderr,"[Hypo::X] Error: ...")+exit(1),
+ * which the host wrapper reproduces around these calls).
+ *
+ * There is NO CPU fallback behind this API: if no CUDA device is usable the
+ * calls fail loudly.
+ */
+#ifndef HYPO_B200_H
+#define HYPO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYPO_B200_ABI_VERSION 1
+
+/* Window types — hypo::WindowType, reference include/Window.hpp:35-38 */
+#define HYPO_WINDOW_SHORT 0u
+#define HYPO_WINDOW_LONG  1u
+
+/* Error codes */
+#define HYPO_OK            0
+#define HYPO_E_NOT_INIT    1   /* hypo_gpu_init was not called                         */
+#define HYPO_E_CUDA        2   /* a CUDA runtime call failed (no device, OOM, ...)     */
+#define HYPO_E_ARG         3   /* malformed descriptors / offsets out of range         */
+#define HYPO_E_OUT_CAP     4   /* output buffer too small (see hypo_gpu_out_bound)     */
+#define HYPO_E_SCORES      5   /* gap penalty > 0 (spoa rejects it too,
+                                  reference external/spoa/src/alignment_engine.cpp:42-49) */
+#define HYPO_E_CAPACITY    6   /* a window exceeds every device capacity tier          */
+
+/*
+ * One weak-region window == one hypo::Window (reference include/Window.hpp:122-135).
+ *
+ *  - draft: the PackedSeq<4> bytes of Window::_draft verbatim: 2 bases/byte,
+ *    base i in the HIGH nibble of byte i>>1 when i is even, LOW nibble when odd;
+ *    nibble codes A0 C1 G2 T3, anything >=4 unpacks to 'N'
+ *    (reference src/PackedSeq.cpp:45-48, include/PackedSeq.hpp:54-72).
+ *  - arms [first_arm, first_arm + n_internal + n_pre + n_suf) of the arm table,
+ *    in container order: _internal_arms, then _pre_arms, then _suf_arms
+ *    (reference include/Window.hpp:131-133).  The device applies the
+ *    reverse-prefix-order rule of generate_consensus_short itself.
+ *  - n_internal/n_pre/n_suf are both the counters _num_internal/_num_pre/_num_suf
+ *    and the vector sizes (they are always equal in the reference,
+ *    include/Window.hpp:66-118); zero-length arms are allowed and are skipped
+ *    exactly like the reference skips them (src/Window.cpp:103,114,125,182).
+ *  - n_empty is Window::_num_empty.
+ */
+typedef struct HypoWindowDesc {
+    uint64_t draft_off;    /* byte offset of the packed draft inside `packed`      */
+    uint64_t first_arm;    /* index of this window's first arm in the arm table    */
+    uint32_t draft_len;    /* draft length in bases (Window::get_window_len)       */
+    uint32_t n_internal;
+    uint32_t n_pre;
+    uint32_t n_suf;
+    uint32_t n_empty;
+    uint32_t wtype;        /* HYPO_WINDOW_SHORT / HYPO_WINDOW_LONG                 */
+} HypoWindowDesc;          /* 40 bytes */
+
+/*
+ * One arm == one PackedSeq<2> (reference include/PackedSeq.hpp:152-154):
+ * 4 bases/byte, base i in bits (6 - 2*(i&3)) of byte i>>2, codes A0 C1 G2 T3
+ * (reference src/PackedSeq.cpp:45, include/globalDefs.hpp:158-178).
+ */
+typedef struct HypoArmDesc {
+    uint64_t off;          /* byte offset of the packed arm inside `packed`        */
+    uint32_t len;          /* arm length in bases (PackedSeq::get_seq_size)        */
+    uint32_t reserved;     /* must be 0                                            */
+} HypoArmDesc;             /* 16 bytes */
+
+/*
+ * Replaces hypo::Window::prepare_for_poa(const ScoreParams&, num_threads)
+ * (reference src/Window.cpp:31-42).  scores = {sr_match, sr_mismatch, sr_gap,
+ * lr_match, lr_mismatch, lr_gap} == hypo::ScoreParams (reference
+ * include/globalDefs.hpp:58-66).  device = CUDA ordinal to run on (one process
+ * per GPU; multi-GPU sharding happens above this ABI).
+ * May be called again to change scores/device.
+ */
+int hypo_gpu_init(const int8_t scores[6], int device);
+
+/*
+ * Upper bound of the consensus bytes a batch can produce (used to size `out`):
+ * sum over windows of max(draft_len, sum(arm_len + 2) + draft_len + 2).
+ */
+uint64_t hypo_gpu_out_bound(const HypoWindowDesc* win, uint64_t n_win,
+                            const HypoArmDesc* arms, uint64_t n_arms);
+
+/*
+ * Replaces the OpenMP loop over Contig::generate_consensus(w, tid) ->
+ * Window::generate_consensus(tid) (reference src/Hypo.cpp:238-247,
+ * include/Contig.hpp:119) for a whole batch of windows.
+ *
+ * All pointers are HOST pointers (pinned memory makes the copies faster but is
+ * not required).  On success, the consensus of window w — byte-identical to
+ * what Window::get_consensus() returns in the reference's default (SISD) build —
+ * is out[out_off[w] .. out_off[w+1]) (ASCII ACGTN, no terminator).
+ * out_off must hold n_win+1 entries.  Nothing is retained after return.
+ */
+int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win,
+                             const HypoArmDesc* arms, uint64_t n_arms,
+                             const uint8_t* packed, uint64_t packed_bytes,
+                             char* out, uint64_t out_cap, uint64_t* out_off);
+
+/*
+ * Same computation with every buffer already resident in device memory on the
+ * device given to hypo_gpu_init (d_* are device pointers; `stream` is a
+ * cudaStream_t passed as void*, NULL = default stream).  The call is
+ * asynchronous with respect to the host except for internal tier bookkeeping;
+ * results are valid after the stream is synchronised.
+ *   d_out_len[w]  = consensus length of window w
+ *   d_out         = consensus bytes, window w at d_out + d_out_pos[w] where
+ *                   d_out_pos is caller-provided (n_win entries, e.g. an
+ *                   exclusive scan of per-window bounds).
+ */
+int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
+                                    const HypoArmDesc* d_arms, uint64_t n_arms,
+                                    const uint8_t* d_packed, uint64_t packed_bytes,
+                                    char* d_out, const uint64_t* d_out_pos,
+                                    uint32_t* d_out_len, void* stream);
+
+/* Number of kernel launches issued by this library since hypo_gpu_init. */
+uint64_t hypo_gpu_launch_count(void);
+
+/* Thread-local message describing the last failure ("" if none). */
+const char* hypo_gpu_last_error(void);
+
+/* Releases device memory and streams. */
+void hypo_gpu_shutdown(void);
+
+int hypo_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPO_B200_H */

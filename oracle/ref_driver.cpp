@@ -1,0 +1,188 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called by the product path.
+//
+// Thin driver around the UNMODIFIED reference implementation of the hot path.
+// It is compiled by oracle/Makefile straight from the sources under
+// /root/reference (hypo::Window + hypo::PackedSeq + the adapted spoa fork) with
+// the reference's default flags (-O3, no -march  =>  spoa's SISD engine, the
+// parity oracle) into oracle/_ref/libhypo_ref.so.
+// No reference source is copied into this repository.
+//
+// It speaks the same batch layout as include/hypo_b200.h so that tests can
+// hand the very same buffers to the reference, to the C restatement
+// (oracle/poa_oracle.c) and to the CUDA library.
+//
+// Reference call sequence reproduced here (reference src/Hypo.cpp:236-248):
+//   Window::prepare_for_poa(score_params, threads);
+//   #pragma omp parallel for schedule(static,1)
+//   for w: window[w]->generate_consensus(omp_get_thread_num());
+#include <omp.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+// The engines live in private static vectors that prepare_for_poa only ever
+// appends to (reference src/Window.cpp:31-42).  To be able to switch score
+// parameters between calls inside one test process the driver needs to clear
+// them; the access specifier is lifted for this translation unit only.
+// Everything Window.hpp includes is pulled in first (include guards), so the
+// define only affects class hypo::Window itself.
+#include "spoa/spoa.hpp"
+#include "globalDefs.hpp"
+#include "PackedSeq.hpp"
+#include "Filter.hpp"
+#define private public
+#include "Window.hpp"
+#undef private
+
+#include "../include/hypo_b200.h"
+
+namespace {
+
+const char kNib[16] = {'A', 'C', 'G', 'T', 'N', 'N', 'N', 'N',
+                       'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N'};
+
+std::string unpack2(const uint8_t* p, uint32_t len) {
+    std::string s(len, 'A');
+    for (uint32_t i = 0; i < len; ++i) s[i] = "ACGT"[(p[i >> 2] >> (6 - 2 * (i & 3))) & 3];
+    return s;
+}
+
+std::string unpack4(const uint8_t* p, uint32_t len) {
+    std::string s(len, 'A');
+    for (uint32_t i = 0; i < len; ++i) s[i] = kNib[(p[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
+    return s;
+}
+
+int8_t g_scores[6] = {0, 0, 0, 0, 0, 0};
+int g_threads = 0;
+
+void ensure_engines(const int8_t scores[6], int threads) {
+    if (g_threads >= threads && std::memcmp(scores, g_scores, 6) == 0) return;
+    hypo::Window::_alignment_engines.clear();
+    hypo::Window::_alignment_engines_long.clear();
+    hypo::ScoreParams sp;
+    sp.sr_match_score = scores[0];
+    sp.sr_misMatch_score = scores[1];
+    sp.sr_gap_penalty = scores[2];
+    sp.lr_match_score = scores[3];
+    sp.lr_misMatch_score = scores[4];
+    sp.lr_gap_penalty = scores[5];
+    hypo::Window::prepare_for_poa(sp, (hypo::UINT32)threads);
+    std::memcpy(g_scores, scores, 6);
+    g_threads = threads;
+}
+
+}  // namespace
+
+extern "C" {
+
+// n_threads <= 0: omp_get_max_threads().  schedule: 0 = schedule(static,1) as
+// shipped (reference src/Hypo.cpp:240), 1 = schedule(dynamic,1).
+// arm_accepted (nullable, n_arms bytes): 1 if Window::add_* kept the arm (LONG
+// windows run every arm through hypo::Filter::is_good at insert time, reference
+// include/Window.hpp:66-101, which is outside the hot path).
+// seconds (nullable): wall time of the consensus loop only.
+int hypo_ref_consensus_batch(const int8_t scores[6], const HypoWindowDesc* win, uint64_t n_win,
+                             const HypoArmDesc* arms, uint64_t n_arms, const uint8_t* packed,
+                             uint64_t packed_bytes, char* out, uint64_t out_cap,
+                             uint64_t* out_off, uint8_t* arm_accepted, int n_threads,
+                             int schedule, double* seconds) {
+    (void)n_arms;
+    (void)packed_bytes;
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    ensure_engines(scores, n_threads);
+
+    std::vector<std::unique_ptr<hypo::Window>> windows(n_win);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        hypo::PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        auto wt = d.wtype == HYPO_WINDOW_LONG ? hypo::WindowType::LONG : hypo::WindowType::SHORT;
+        windows[w].reset(new hypo::Window(draft, 0, d.draft_len, wt));
+        hypo::Window& W = *windows[w];
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) {
+            auto before = W._internal_arms.size();
+            W.add_internal(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+            if (arm_accepted) arm_accepted[a] = W._internal_arms.size() != before;
+        }
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) {
+            auto before = W._pre_arms.size();
+            W.add_prefix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+            if (arm_accepted) arm_accepted[a] = W._pre_arms.size() != before;
+        }
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) {
+            auto before = W._suf_arms.size();
+            W.add_suffix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+            if (arm_accepted) arm_accepted[a] = W._suf_arms.size() != before;
+        }
+        for (uint32_t i = 0; i < d.n_empty; ++i) W.add_empty();
+    }
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (schedule == 0) {
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+        for (uint64_t w = 0; w < n_win; ++w) windows[w]->generate_consensus(omp_get_thread_num());
+    } else {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+        for (uint64_t w = 0; w < n_win; ++w) windows[w]->generate_consensus(omp_get_thread_num());
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+
+    uint64_t pos = 0;
+    for (uint64_t w = 0; w < n_win; ++w) {
+        out_off[w] = pos;
+        std::string c = windows[w]->get_consensus();
+        if (pos + c.size() > out_cap) return HYPO_E_OUT_CAP;
+        std::memcpy(out + pos, c.data(), c.size());
+        pos += c.size();
+    }
+    out_off[n_win] = pos;
+    return HYPO_OK;
+}
+
+// Raw spoa entry used to pin the oracle on the reference's own known-answer test
+// SpoaAlignmentTest.GlobalConsensus (reference external/spoa/test/spoa_test.cpp:220-239):
+// kNW, linear gaps, sequences added in order with weight 1 per base,
+// consensus = Graph::generate_consensus().
+// seqs: concatenated ASCII sequences; seq_off: n_seq+1 offsets.
+// align_type: 0 kNW, 1 kLOV, 2 kROV.
+int hypo_ref_spoa_consensus(int8_t m, int8_t n, int8_t g, const char* seqs,
+                            const uint64_t* seq_off, uint32_t n_seq, const uint8_t* align_type,
+                            char* out, uint64_t out_cap, uint64_t* out_len) {
+    auto engine = spoa::createAlignmentEngine(spoa::AlignmentType::kNW, m, n, g);
+    auto graph = spoa::createGraph();
+    for (uint32_t i = 0; i < n_seq; ++i) {
+        std::string s(seqs + seq_off[i], seqs + seq_off[i + 1]);
+        auto t = spoa::AlignmentType::kNW;
+        if (align_type && align_type[i] == 1) t = spoa::AlignmentType::kLOV;
+        if (align_type && align_type[i] == 2) t = spoa::AlignmentType::kROV;
+        engine->changeAlignType(t);
+        auto alignment = engine->align(s, graph);
+        graph->add_alignment(alignment, s);
+    }
+    std::string c = graph->generate_consensus();
+    if (c.size() > out_cap) return HYPO_E_OUT_CAP;
+    std::memcpy(out, c.data(), c.size());
+    *out_len = c.size();
+    return HYPO_OK;
+}
+
+int hypo_ref_max_threads(void) { return omp_get_max_threads(); }
+
+// 1 if this build of the reference selected spoa's SIMD engine (built with
+// -march=native), 0 for the SISD engine (default flags; the parity oracle).
+int hypo_ref_is_simd(void) {
+#if defined(__AVX2__) || defined(__SSE4_1__)
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+}  // extern "C"

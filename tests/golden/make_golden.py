@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory.  Runs ONLY in the authoring container
+(needs /root/reference and oracle/_ref/libhypo_ref.so); the fixtures are committed because
+neither travels to the GPU box.
+
+  spoa_global_consensus.json.gz
+      Inputs + expected output of the reference's own known-answer test
+      SpoaAlignmentTest.GlobalConsensus (reference external/spoa/test/spoa_test.cpp:220-239):
+      the 55 reads of external/spoa/test/data/sample.fastq, kNW, linear 5/-4/-8, and the
+      469-character consensus the test asserts.  The expected string is parsed out of the
+      test source at generation time and cross-checked against the compiled reference.
+
+  windows.json.gz
+      Windows of every kind (internal / draft-backbone / prefix-heavy / suffix-heavy / mixed /
+      N-in-draft / LONG two-round + curate / alternative scores / hand-written edge cases) with
+      the consensus produced by the compiled, UNMODIFIED reference (default flags => SISD).
+      LONG windows only contain the arms the reference's insert-time Filter accepted.
+
+Usage:  make -C oracle ref && python tests/golden/make_golden.py
+"""
+import gzip
+import json
+import os
+import re
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from hypo_b200.batch import WINDOW_LONG, build_batch  # noqa: E402
+from hypo_b200.synth import edge_case_windows, random_window  # noqa: E402
+from tests.oracle_util import DEFAULT_SCORES, drop_rejected_arms, ref_consensus, ref_spoa  # noqa: E402
+
+REF = "/root/reference/external/spoa/test"
+GENERATOR_VERSION = 1
+
+
+def spoa_fixture():
+    lines = open(os.path.join(REF, "data", "sample.fastq")).read().split("\n")
+    seqs = [lines[i + 1] for i in range(0, len(lines) - 3, 4) if lines[i].startswith("@")]
+    src = open(os.path.join(REF, "spoa_test.cpp")).read()
+    body = src[src.index("TEST_F(SpoaAlignmentTest, GlobalConsensus)"):]
+    body = body[: body.index("EXPECT_TRUE")]
+    assert "5, -4, -8, -8, -8, -8" in body and "kNW" in body
+    expected = "".join(re.findall(r'"([ACGT]+)"', body[body.index("valid_result"):]))
+    got = ref_spoa(seqs, 5, -4, -8)
+    assert got == expected, "compiled reference disagrees with its own test?"
+    return {"source": "reference external/spoa/test/spoa_test.cpp:220-239 + test/data/sample.fastq",
+            "m": 5, "n": -4, "g": -8, "seqs": seqs, "expected": expected}
+
+
+def window_fixture():
+    rng = np.random.default_rng(20261017)
+    groups = []
+
+    def add(name, specs, scores=DEFAULT_SCORES):
+        batch = build_batch(specs)
+        cons, acc, _ = ref_consensus(batch, scores)
+        if not acc.all():
+            batch = drop_rejected_arms(batch, acc)
+            cons, acc, _ = ref_consensus(batch, scores)
+            assert acc.all()
+        wins = []
+        for w in range(batch.n_win):
+            s = batch.spec(w)
+            wins.append({"draft": s.draft, "internal": list(s.internal), "pre": list(s.pre),
+                         "suf": list(s.suf), "n_empty": s.n_empty, "wtype": s.wtype,
+                         "consensus": cons[w]})
+        groups.append({"name": name, "scores": list(scores), "windows": wins})
+
+    add("edge_cases", edge_case_windows())
+    for kind in ("internal", "backbone", "prefix", "suffix", "mixed"):
+        specs = [random_window(rng, length=120, n_arms=30, kind=kind) for _ in range(4)]
+        specs += [random_window(rng, length=int(rng.integers(5, 70)), n_arms=int(rng.integers(3, 25)),
+                                kind=kind, err=float(rng.choice([0.01, 0.05, 0.15]))) for _ in range(28)]
+        add(kind, specs)
+    add("n_in_draft", [random_window(rng, length=40, n_arms=8, kind="backbone", draft_n=0.1) for _ in range(12)])
+    add("long", [random_window(rng, length=int(rng.integers(120, 400)), n_arms=int(rng.integers(4, 16)),
+                               kind=str(rng.choice(["internal", "mixed", "prefix"])), wtype=WINDOW_LONG,
+                               err=float(rng.choice([0.01, 0.05]))) for _ in range(16)])
+    add("alt_scores", [random_window(rng, length=40, n_arms=10, kind="mixed", err=0.1) for _ in range(16)],
+        scores=(2, -3, -2, 1, -1, -1))
+    add("alt_scores_long", [random_window(rng, length=150, n_arms=8, kind="mixed", err=0.05, wtype=WINDOW_LONG)
+                            for _ in range(8)], scores=(1, -1, -1, 2, -2, -3))
+    return {"generator_version": GENERATOR_VERSION, "oracle": "oracle/_ref/libhypo_ref.so (SISD)",
+            "groups": groups}
+
+
+def dump(name, obj):
+    with gzip.GzipFile(os.path.join(HERE, name), "wb", mtime=0) as f:
+        f.write(json.dumps(obj, separators=(",", ":")).encode())
+
+
+if __name__ == "__main__":
+    dump("spoa_global_consensus.json.gz", spoa_fixture())
+    wf = window_fixture()
+    dump("windows.json.gz", wf)
+    print("windows:", sum(len(g["windows"]) for g in wf["groups"]))

@@ -1,0 +1,86 @@
+"""Pins the CPU restatement (oracle/poa_oracle.c) — the checker every GPU parity test uses —
+against (1) the reference's own known-answer test, (2) golden vectors produced by the compiled
+unmodified reference, (3) the compiled reference itself when oracle/_ref exists."""
+import numpy as np
+import pytest
+
+from hypo_b200.batch import WINDOW_LONG, build_batch
+from hypo_b200.synth import edge_case_windows, random_batch
+from tests.golden_util import group_batch
+from tests.oracle_util import (DEFAULT_SCORES, drop_rejected_arms, oracle_consensus, oracle_spoa,
+                               ref_consensus, ref_lib, ref_spoa)
+
+
+def test_spoa_global_consensus_known_answer(golden_spoa):
+    """reference external/spoa/test/spoa_test.cpp:220-239 (kNW, 5/-4/-8, 55 reads)."""
+    g = golden_spoa
+    assert len(g["seqs"]) == 55 and len(g["expected"]) == 469
+    assert oracle_spoa(g["seqs"], g["m"], g["n"], g["g"]) == g["expected"]
+
+
+def test_golden_windows(golden_windows):
+    total = 0
+    for group in golden_windows["groups"]:
+        batch, expected = group_batch(group)
+        got, _ = oracle_consensus(batch, tuple(group["scores"]))
+        assert got == expected, group["name"]
+        total += len(expected)
+    assert total >= 200
+
+
+def test_thread_count_independent():
+    b = random_batch(11, 64, kind="mixed", length=50, n_arms=12)
+    a, _ = oracle_consensus(b, threads=1)
+    c, _ = oracle_consensus(b, threads=4)
+    assert a == c
+
+
+def test_gap_must_be_non_positive():
+    b = random_batch(12, 2)
+    with pytest.raises(RuntimeError):
+        oracle_consensus(b, scores=(5, -4, 8, 3, -5, -4))
+
+
+needs_ref = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built (no /root/reference)")
+
+
+@needs_ref
+def test_reference_agrees_with_its_own_fixture(golden_spoa):
+    g = golden_spoa
+    assert ref_spoa(g["seqs"], g["m"], g["n"], g["g"]) == g["expected"]
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["internal", "backbone", "prefix", "suffix", "mixed"])
+def test_oracle_vs_compiled_reference_short(kind):
+    for seed, kw in ((100, dict(length=120, n_arms=30)), (101, dict(length=35, n_arms=14, err=0.08)),
+                     (102, dict(length=9, n_arms=25, err=0.03))):
+        b = random_batch(seed, 60, kind=kind, **kw)
+        r, acc, _ = ref_consensus(b)
+        assert acc.all()
+        o, _ = oracle_consensus(b)
+        assert r == o
+
+
+@needs_ref
+def test_oracle_vs_compiled_reference_long_and_edges():
+    for b in (build_batch(edge_case_windows()),
+              random_batch(103, 40, kind="mixed", wtype=WINDOW_LONG, length=220, n_arms=14),
+              random_batch(104, 30, kind="internal", wtype=WINDOW_LONG, length=400, n_arms=10, err=0.03)):
+        r, acc, _ = ref_consensus(b)
+        if not acc.all():
+            b = drop_rejected_arms(b, acc)
+            r, acc, _ = ref_consensus(b)
+        o, _ = oracle_consensus(b)
+        assert r == o
+
+
+@needs_ref
+def test_oracle_vs_compiled_reference_mixed_alignment_types():
+    rng = np.random.default_rng(5)
+    from hypo_b200.synth import mutate
+    for _ in range(30):
+        truth = "".join("ACGT"[i] for i in rng.integers(0, 4, size=60))
+        seqs = [mutate(rng, truth, 0.05, 0.05, 0.05) or "A" for _ in range(10)]
+        types = [0] + [int(x) for x in rng.integers(0, 3, size=9)]
+        assert oracle_spoa(seqs, 5, -4, -8, types) == ref_spoa(seqs, 5, -4, -8, types)
