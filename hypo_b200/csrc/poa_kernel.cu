@@ -1,0 +1,856 @@
+// poa_kernel.cu — sm_100a kernels for the POA-consensus hot path.  See poa_kernel.cuh for
+// the overview and DESIGN.md for the data layout and the roofline accounting.
+#include "poa_kernel.cuh"
+
+namespace hypo_b200 {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------
+// Per-warp state
+// ------------------------------------------------------------------------------------------
+struct Graph {
+    uint8_t* letter;      // node -> letter code (0..6 = A C G T N J O)
+    uint16_t* in_head;    // node -> first in-edge (insertion order), kNone if none
+    uint16_t* in_tail;
+    uint16_t* out_deg;    // node -> number of out-edges (only "== 0" is ever asked)
+    uint16_t* al_blk;     // node -> block in al_pool holding its aligned_nodes_ids_, kNone
+    uint8_t* al_cnt;      // node -> number of aligned nodes
+    uint8_t* mark;        // toposort scratch
+    uint16_t* n2r;        // node -> rank
+    uint16_t* r2n;        // rank -> node
+    uint16_t* e_src;
+    uint16_t* e_dst;
+    uint16_t* e_w;        // Edge::total_weight_ (2 per traversal)
+    uint16_t* e_next;     // next in-edge of the same destination
+    uint16_t* al_pool;
+    uint16_t* stack;
+    uint8_t* seq;         // current sequence, letter codes
+    uint16_t* cur;        // per sequence position: aligned node / resolved node
+    int16_t* prof;        // [code][column] (match ? m : n) - g
+    int32_t* score;       // epilogue
+    uint16_t* pred;
+    uint16_t* cons;
+    int n_nodes, n_edges, n_al, n_seq;
+};
+
+__device__ __forceinline__ Graph make_graph(uint8_t* base, const ArenaLayout& L) {
+    Graph g;
+    g.letter = base + L.letter;
+    g.in_head = (uint16_t*)(base + L.in_head);
+    g.in_tail = (uint16_t*)(base + L.in_tail);
+    g.out_deg = (uint16_t*)(base + L.out_deg);
+    g.al_blk = (uint16_t*)(base + L.al_blk);
+    g.al_cnt = base + L.al_cnt;
+    g.mark = base + L.mark;
+    g.n2r = (uint16_t*)(base + L.n2r);
+    g.r2n = (uint16_t*)(base + L.r2n);
+    g.e_src = (uint16_t*)(base + L.e_src);
+    g.e_dst = (uint16_t*)(base + L.e_dst);
+    g.e_w = (uint16_t*)(base + L.e_w);
+    g.e_next = (uint16_t*)(base + L.e_next);
+    g.al_pool = (uint16_t*)(base + L.al_pool);
+    g.stack = (uint16_t*)(base + L.stack);
+    g.seq = base + L.seq;
+    g.cur = (uint16_t*)(base + L.cur);
+    g.prof = (int16_t*)(base + L.prof);
+    g.score = (int32_t*)(base + L.score);
+    g.pred = (uint16_t*)(base + L.pred);
+    g.cons = (uint16_t*)(base + L.cons);
+    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+    return g;
+}
+
+struct Scores {
+    int m, n, g;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ------------------------------------------------------------------------------------------
+// Sequence decode (PackedSeq<2>/<4>::unpack, reference src/PackedSeq.cpp:231-262 with the bit
+// layouts of :45,:48) straight into letter codes, plus the J/O markers of SHORT windows
+// (reference include/Window.hpp:30-33, src/Window.cpp:98,105,116,127).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode2(const uint8_t* __restrict__ src, int len, uint8_t* dst) {
+    for (int p = lane_id(); p < len; p += 32) dst[p] = (src[p >> 2] >> (6 - 2 * (p & 3))) & 3;
+}
+__device__ __forceinline__ void decode4(const uint8_t* __restrict__ src, int len, uint8_t* dst) {
+    for (int p = lane_id(); p < len; p += 32) {
+        int v = (src[p >> 1] >> ((p & 1) ? 0 : 4)) & 15;
+        dst[p] = v > 4 ? 4 : v;
+    }
+}
+
+// Query profile (reference sisd_alignment_engine.cpp:101-108), g-normalised:
+// prof[c][j] = (decoder(c) == seq[j-1] ? m : n) - g for 1 <= j <= len, mismatch for the
+// padding columns, 0 for column 0 (its diagonal input is -inf anyway).
+__device__ __forceinline__ void build_profile(const Graph& g, int len, int cols, Scores sc) {
+    const int mm = sc.m - sc.g, nn = sc.n - sc.g;
+    for (int j = lane_id(); j < cols; j += 32) {
+        int letter = (j >= 1 && j <= len) ? g.seq[j - 1] : -1;
+#pragma unroll
+        for (int c = 0; c < kNumCodes; ++c)
+            g.prof[c * cols + j] = (int16_t)(j == 0 ? 0 : (letter == c ? mm : nn));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DP fill (reference sisd_alignment_engine.cpp:263-342, initialisation :158-159,197-211,
+// 229-239).  Lane l owns columns [4l, 4l+4) of each 128-column tile as two s16x2 registers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) {
+    return (uint32_t)(lo & 0xffff) | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+// x = max(x, diag + prof, vert + g) for one predecessor row.
+__device__ __forceinline__ void relax(uint32_t (&x)[kNR], const uint32_t (&p)[kNR], uint32_t left,
+                                      const uint32_t (&pf)[kNR], uint32_t g2) {
+    uint32_t prevreg = left;   // (.., pred[c0-1]) in the HIGH half
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        uint32_t d = __byte_perm(prevreg, p[r], 0x5432);   // (pred[j-1] for lo, for hi)
+        x[r] = __viaddmax_s16x2(d, pf[r], x[r]);
+        x[r] = __viaddmax_s16x2(p[r], g2, x[r]);
+        prevreg = p[r];
+    }
+}
+
+// In-lane inclusive prefix max over the 2*kNR columns, then warp exclusive prefix max.
+// carry = prefix max of everything left of this tile (tile > 0) or kNegInf.
+// Returns the tile's total (for the next tile's carry).
+__device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry) {
+    int run = kNegInf;
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        uint32_t t = __byte_perm(x[r], kNegInf2, 0x1054);          // (lo: -inf, hi: x.lo)
+        x[r] = __vimax3_s16x2(x[r], t, pack2(run, run));
+        run = hi16(x[r]);
+    }
+    int tot = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(kFull, tot, d);
+        if (lane_id() >= d) tot = max(tot, y);
+    }
+    int excl = __shfl_up_sync(kFull, tot, 1);
+    if (lane_id() == 0) excl = kNegInf;
+    excl = max(excl, carry);
+    uint32_t cb = pack2(excl, excl);
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
+    return max(__shfl_sync(kFull, tot, 31), carry);
+}
+
+struct EndCell {
+    int row;   // 0 if no candidate (reference clamps max_i=-1 to 0)
+    int col;
+};
+
+template <bool kOneTile>
+__device__ __forceinline__ EndCell dp_fill(const Graph& g, int16_t* __restrict__ H, int len, int tiles,
+                                           int type, Scores sc) {
+    const int lane = lane_id();
+    const int cols = tiles * kTileCols;
+    const uint32_t g2 = pack2(sc.g, sc.g);
+    const int end_tile = len / kTileCols, end_lane = (len % kTileCols) / (2 * kNR),
+              end_reg = (len % (2 * kNR)) / 2, end_hi = len & 1;
+
+    // row 0: H^[0][j] = 0
+    for (int t = 0; t < tiles; ++t)
+        *reinterpret_cast<uint2*>(H + t * kTileCols + lane * 4) = make_uint2(0u, 0u);
+
+    uint32_t prev[kNR];
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) prev[r] = 0u;
+    int prev_row = 0;
+    int best = INT_MIN, best_row = -1;
+
+    for (int rk = 0; rk < g.n_nodes; ++rk) {
+        const int v = g.r2n[rk];
+        const int code = g.letter[v];
+        const int e0 = g.in_head[v];
+        const int row = rk + 1;
+        int16_t* Hrow = H + (size_t)row * cols;
+        int carry = kNegInf;
+        int endval = 0;
+        uint32_t x[kNR];
+        for (int t = 0; t < (kOneTile ? 1 : tiles); ++t) {
+#pragma unroll
+            for (int r = 0; r < kNR; ++r) x[r] = kNegInf2;
+            uint32_t pf[kNR];
+            {
+                uint2 q = *reinterpret_cast<const uint2*>(g.prof + code * cols + t * kTileCols + lane * 4);
+                pf[0] = q.x; pf[1] = q.y;
+            }
+            if (e0 == kNone) {
+                // no predecessor: virtual row 0 (reference :300-301)
+                uint32_t p[kNR] = {0u, 0u};
+                uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
+                relax(x, p, left, pf, g2);
+            } else {
+                for (int e = e0; e != kNone; e = g.e_next[e]) {
+                    const int prow = g.n2r[g.e_src[e]] + 1;
+                    uint32_t p[kNR];
+                    if (kOneTile && prow == prev_row) {
+                        p[0] = prev[0]; p[1] = prev[1];
+                    } else {
+                        uint2 q = *reinterpret_cast<const uint2*>(H + (size_t)prow * cols + t * kTileCols + lane * 4);
+                        p[0] = q.x; p[1] = q.y;
+                    }
+                    uint32_t left = __shfl_up_sync(kFull, p[kNR - 1], 1);
+                    if (lane == 0) {
+                        if (t == 0) left = kNegInf2;
+                        else left = (uint32_t)(uint16_t)H[(size_t)prow * cols + t * kTileCols - 1] << 16;
+                    }
+                    relax(x, p, left, pf, g2);
+                }
+            }
+            // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
+            // ROV pins it to 0 (reference :229-239)
+            if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
+            carry = scan_row(x, carry);
+            *reinterpret_cast<uint2*>(Hrow + t * kTileCols + lane * 4) = make_uint2(x[0], x[1]);
+            if (t == end_tile) {
+                uint32_t w = end_reg == 0 ? x[0] : x[1];
+                endval = __shfl_sync(kFull, end_hi ? hi16(w) : lo16(w), end_lane);
+            }
+        }
+        if (kOneTile) { prev[0] = x[0]; prev[1] = x[1]; prev_row = row; }
+        else __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
+        // end cell (reference :276-288,328-340): strictly greater => lowest rank wins ties
+        const bool cand = (type == kLOV) || (g.out_deg[v] == 0);
+        if (cand && endval > best) { best = endval; best_row = row; }
+    }
+    __syncwarp();
+    EndCell ec;
+    ec.row = best_row > 0 ? best_row : 0;
+    ec.col = best_row > 0 ? len : 0;
+    return ec;
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback (reference sisd_alignment_engine.cpp:344-437).  Executed redundantly by all
+// lanes (uniform control flow, broadcast loads); lane 0 records cur[pos].
+// Preference: diagonal via in-edge 0,1,..; vertical via in-edge 0,1,..; horizontal.
+// Returns first/last aligned sequence position (-1/-1 for an alignment without any).
+// ------------------------------------------------------------------------------------------
+struct AlnSpan {
+    int first, last;
+};
+
+__device__ __forceinline__ AlnSpan traceback(const Graph& g, const int16_t* __restrict__ H, int cols,
+                                             EndCell ec, int type, Scores sc, int max_steps) {
+    const int lane = lane_id();
+    int i = ec.row, j = ec.col;
+    AlnSpan span;
+    span.first = -1; span.last = -1;
+    int hij = (int)H[(size_t)i * cols + j];
+    const int mm = sc.m - sc.g, nn = sc.n - sc.g;
+    int steps = 0;
+    while ((type == kROV ? (i != 0 && j != 0) : (i != 0 || j != 0)) && steps++ < max_steps) {
+        int ni = i, nj = j, nh = hij;
+        bool found = false;
+        if (i != 0) {
+            const int v = g.r2n[i - 1];
+            const int e0 = g.in_head[v];
+            if (j != 0) {
+                const int s = (g.letter[v] == g.seq[j - 1]) ? mm : nn;
+                if (e0 == kNone) {
+                    int h = (int)H[j - 1];
+                    if (hij == h + s) { ni = 0; nj = j - 1; nh = h; found = true; }
+                } else {
+                    for (int e = e0; e != kNone; e = g.e_next[e]) {
+                        const int pi = g.n2r[g.e_src[e]] + 1;
+                        int h = (int)H[(size_t)pi * cols + j - 1];
+                        if (hij == h + s) { ni = pi; nj = j - 1; nh = h; found = true; break; }
+                    }
+                }
+            }
+            if (!found) {
+                if (e0 == kNone) {
+                    int h = (int)H[j];
+                    if (hij == h + sc.g) { ni = 0; nj = j; nh = h; found = true; }
+                } else {
+                    for (int e = e0; e != kNone; e = g.e_next[e]) {
+                        const int pi = g.n2r[g.e_src[e]] + 1;
+                        int h = (int)H[(size_t)pi * cols + j];
+                        if (hij == h + sc.g) { ni = pi; nj = j; nh = h; found = true; break; }
+                    }
+                }
+            }
+        }
+        if (!found && j != 0) {
+            int h = (int)H[(size_t)i * cols + j - 1];
+            if (hij == h) { ni = i; nj = j - 1; nh = h; found = true; }
+        }
+        if (!found) break;   // impossible for a consistent H; never spin
+        if (nj != j) {
+            // pair (node or -1, j-1)
+            if (lane == 0) g.cur[j - 1] = (ni != i) ? g.r2n[i - 1] : kNone;
+            if (span.last < 0) span.last = j - 1;
+            span.first = j - 1;
+        }
+        i = ni; j = nj; hij = nh;
+    }
+    __syncwarp();
+    return span;
+}
+
+// ------------------------------------------------------------------------------------------
+// Graph fusion (reference graph.cpp:154-291), warp-parallel over sequence positions.
+// Returns false if a capacity was exceeded (window is abandoned and re-run in a larger tier).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void init_node(const Graph& g, int id, int code) {
+    g.letter[id] = (uint8_t)code;
+    g.in_head[id] = kNone;
+    g.in_tail[id] = kNone;
+    g.out_deg[id] = 0;
+    g.al_blk[id] = kNone;
+    g.al_cnt[id] = 0;
+}
+
+__device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len, AlnSpan span,
+                                             uint16_t* path) {
+    const int lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int first = span.first, last = span.last;
+    if (first < 0) { first = len; last = len - 1; }   // empty alignment: whole read is a chain (:174-182)
+    const int head_n = first, tail_n = len - 1 - last;
+    const int base = g.n_nodes;
+    if (base + head_n + tail_n > caps.ncap) return false;
+
+    // head chain [0, first) and tail chain (last, len): fresh nodes, allocated FIRST (:194-200)
+    for (int p = lane; p < len; p += 32) {
+        int id = -1;
+        if (p < first) id = base + p;
+        else if (p > last) id = base + head_n + (p - last - 1);
+        if (id >= 0) {
+            init_node(g, id, g.seq[p]);
+            g.cur[p] = (uint16_t)id;
+        }
+    }
+    int n_nodes = base + head_n + tail_n;
+    int n_al = g.n_al;
+    __syncwarp();
+
+    // aligned part [first, last]: reuse / clique lookup / new node (:206-245)
+    for (int p0 = first; p0 <= last; p0 += 32) {
+        const int p = p0 + lane;
+        const bool act = p <= last;
+        int x = kNone, code = 0, res = -1;
+        bool need_new = false;
+        if (act) {
+            x = g.cur[p];
+            code = g.seq[p];
+            if (x == kNone) {
+                need_new = true;
+            } else if (g.letter[x] == code) {
+                res = x;
+            } else {
+                need_new = true;
+                const int blk = g.al_blk[x];
+                if (blk != kNone) {
+                    const int cnt = g.al_cnt[x];
+                    for (int k = 0; k < cnt; ++k) {
+                        int a = g.al_pool[blk * kAlSlots + k];
+                        if (g.letter[a] == code) { res = a; need_new = false; break; }
+                    }
+                }
+            }
+        }
+        const unsigned newmask = __ballot_sync(kFull, need_new);
+        const int n_new = __popc(newmask);
+        if (n_nodes + n_new > caps.ncap) return false;
+        if (need_new) res = n_nodes + __popc(newmask & lt_mask);
+        n_nodes += n_new;
+        // aligned-list blocks: the new node needs one; so does x if it had none
+        const bool link = need_new && x != kNone;
+        const bool x_needs_blk = link && g.al_blk[x] == kNone;
+        const unsigned m1 = __ballot_sync(kFull, link);
+        const unsigned m2 = __ballot_sync(kFull, x_needs_blk);
+        if (n_al + __popc(m1) + __popc(m2) > caps.acap) return false;
+        // cannot happen (clique letters are distinct, <= 7 letters); checked uniformly anyway
+        if (__any_sync(kFull, link && g.al_cnt[x] + 1 > kAlSlots)) return false;
+        if (need_new) init_node(g, res, code);
+        if (link) {
+            const int yb = n_al + __popc(m1 & lt_mask);
+            int xb = g.al_blk[x];
+            if (x_needs_blk) {
+                xb = n_al + __popc(m1) + __popc(m2 & lt_mask);
+                g.al_blk[x] = (uint16_t)xb;
+            }
+            g.al_blk[res] = (uint16_t)yb;
+            const int cnt = g.al_cnt[x];
+            // y.list = x.list + [x]; every a in x.list gets y appended; x.list += y (:228-240)
+            for (int k = 0; k < cnt; ++k) {
+                const int a = g.al_pool[xb * kAlSlots + k];
+                g.al_pool[yb * kAlSlots + k] = (uint16_t)a;
+                const int ab = g.al_blk[a];
+                const int ac = g.al_cnt[a];
+                g.al_pool[ab * kAlSlots + ac] = (uint16_t)res;
+                g.al_cnt[a] = (uint8_t)(ac + 1);
+            }
+            g.al_pool[yb * kAlSlots + cnt] = (uint16_t)x;
+            g.al_cnt[res] = (uint8_t)(cnt + 1);
+            g.al_pool[xb * kAlSlots + cnt] = (uint16_t)res;
+            g.al_cnt[x] = (uint8_t)(cnt + 1);
+        }
+        n_al += __popc(m1) + __popc(m2);
+        if (act) g.cur[p] = (uint16_t)res;
+        __syncwarp();
+    }
+    g.n_nodes = n_nodes;
+    g.n_al = n_al;
+
+    // edges (cur[p-1] -> cur[p]), weight 1+1 per traversal (:99-115,251-265,283-288)
+    int n_edges = g.n_edges;
+    for (int p0 = 0; p0 < len; p0 += 32) {
+        const int p = p0 + lane;
+        bool need_edge = false;
+        int src = 0, dst = 0;
+        if (p < len) {
+            dst = g.cur[p];
+            if (path) path[p] = (uint16_t)dst;
+            if (p >= 1) {
+                src = g.cur[p - 1];
+                need_edge = true;
+                for (int e = g.in_head[dst]; e != kNone; e = g.e_next[e]) {
+                    if (g.e_src[e] == src) {
+                        g.e_w[e] = (uint16_t)(g.e_w[e] + 2);
+                        need_edge = false;
+                        break;
+                    }
+                }
+            }
+        }
+        const unsigned em = __ballot_sync(kFull, need_edge);
+        if (n_edges + __popc(em) > caps.ecap) return false;
+        if (need_edge) {
+            const int e = n_edges + __popc(em & lt_mask);
+            g.e_src[e] = (uint16_t)src;
+            g.e_dst[e] = (uint16_t)dst;
+            g.e_w[e] = 2;
+            g.e_next[e] = kNone;
+            const int t = g.in_tail[dst];
+            if (t == kNone) g.in_head[dst] = (uint16_t)e; else g.e_next[t] = (uint16_t)e;
+            g.in_tail[dst] = (uint16_t)e;
+            g.out_deg[src] = (uint16_t)(g.out_deg[src] + 1);
+        }
+        n_edges += __popc(em);
+    }
+    g.n_edges = n_edges;
+    g.n_seq += 1;
+    __syncwarp();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Topological sort (reference graph.cpp:293-353): the exact iterative DFS, because the rank
+// order it produces decides every tie (end cell, heaviest bundle, branch completion).
+// mark bits: 0-1 = node mark (0 unmarked, 1 temporary, 2 permanent), bit 2 = "do not check
+// aligned nodes" (check_aligned_nodes[id] == false).  Serial on lane 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
+    const int lane = lane_id();
+    const int n = g.n_nodes;
+    for (int i = lane; i < n; i += 32) g.mark[i] = 0;
+    __syncwarp();
+    int ok = 1;
+    if (lane == 0) {
+        int nr = 0, sp = 0;
+        for (int i = 0; i < n && ok; ++i) {
+            if ((g.mark[i] & 3) != 0) continue;
+            g.stack[sp++] = (uint16_t)i;
+            while (sp != 0) {
+                const int v = g.stack[sp - 1];
+                bool valid = true;
+                const int mv = g.mark[v];
+                if ((mv & 3) != 2) {
+                    for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+                        const int s = g.e_src[e];
+                        if ((g.mark[s] & 3) != 2) {
+                            if (sp >= caps.scap) { ok = 0; break; }
+                            g.stack[sp++] = (uint16_t)s;
+                            valid = false;
+                        }
+                    }
+                    if (!ok) break;
+                    const bool check = (mv & 4) == 0;
+                    const int cnt = g.al_cnt[v];
+                    const int blk = g.al_blk[v];
+                    if (check) {
+                        for (int k = 0; k < cnt; ++k) {
+                            const int a = g.al_pool[blk * kAlSlots + k];
+                            const int ma = g.mark[a];
+                            if ((ma & 3) != 2) {
+                                if (sp >= caps.scap) { ok = 0; break; }
+                                g.stack[sp++] = (uint16_t)a;
+                                g.mark[a] = (uint8_t)(ma | 4);
+                                valid = false;
+                            }
+                        }
+                        if (!ok) break;
+                    }
+                    if (valid) {
+                        g.mark[v] = (uint8_t)((mv & 4) | 2);
+                        if (check) {
+                            g.r2n[nr++] = (uint16_t)v;
+                            for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * kAlSlots + k];
+                        }
+                    } else {
+                        g.mark[v] = (uint8_t)((mv & 4) | 1);
+                    }
+                }
+                if (valid) --sp;
+            }
+        }
+    }
+    ok = __shfl_sync(kFull, ok, 0);
+    __syncwarp();
+    if (!ok) return false;
+    for (int r = lane; r < n; r += 32) g.n2r[g.r2n[r]] = (uint16_t)r;
+    __syncwarp();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Heaviest bundle + branch completion (reference graph.cpp:610-705).  Serial on lane 0.
+// Returns the consensus length; nodes in g.cons[0..len).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
+    const int n = g.n_nodes;
+    const int node = g.r2n[rank];
+    for (int e = 0; e < g.n_edges; ++e) {
+        if (g.e_src[e] != node) continue;
+        for (int o = g.in_head[g.e_dst[e]]; o != kNone; o = g.e_next[o])
+            if (g.e_src[o] != node) g.score[g.e_src[o]] = -1;
+    }
+    int max_score = 0, max_id = 0;
+    for (int r = rank + 1; r < n; ++r) {
+        const int v = g.r2n[r];
+        int sv = -1, pv = kNone;
+        for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+            const int s = g.e_src[e];
+            const int ss = g.score[s];
+            if (ss == -1) continue;
+            const int w = g.e_w[e];
+            if (sv < w || (sv == w && g.score[pv] <= ss)) { sv = w; pv = s; }
+        }
+        if (pv != kNone) sv += g.score[pv];
+        g.score[v] = sv;
+        g.pred[v] = (uint16_t)pv;
+        if (max_score < sv) { max_score = sv; max_id = v; }
+    }
+    return max_id;
+}
+
+__device__ __forceinline__ int heaviest_bundle(const Graph& g) {
+    const int lane = lane_id();
+    const int n = g.n_nodes;
+    int len = 0;
+    if (lane == 0) {
+        int best = 0;
+        for (int i = 0; i < n; ++i) g.score[i] = -1;
+        for (int r = 0; r < n; ++r) {
+            const int v = g.r2n[r];
+            int sv = -1, pv = kNone;
+            for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+                const int s = g.e_src[e];
+                const int w = g.e_w[e];
+                if (sv < w || (sv == w && g.score[pv] <= g.score[s])) { sv = w; pv = s; }
+            }
+            if (pv != kNone) sv += g.score[pv];
+            g.score[v] = sv;
+            g.pred[v] = (uint16_t)pv;
+            if (g.score[best] < sv) best = v;
+        }
+        int guard = 0;
+        while (g.out_deg[best] != 0 && guard++ <= n) best = branch_completion(g, g.n2r[best]);
+        // backtrack (reversed in place afterwards)
+        int k = 0;
+        while (g.pred[best] != kNone && k < n) { g.cons[k++] = (uint16_t)best; best = g.pred[best]; }
+        g.cons[k++] = (uint16_t)best;
+        for (int a = 0, b = k - 1; a < b; ++a, --b) {
+            uint16_t t = g.cons[a]; g.cons[a] = g.cons[b]; g.cons[b] = t;
+        }
+        len = k;
+    }
+    len = __shfl_sync(kFull, len, 0);
+    __syncwarp();
+    return len;
+}
+
+__device__ __forceinline__ char code_to_char(int c) {
+    return "ACGTNJO"[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// One full POA round: add sequences [slot list] and leave the sorted graph in g.
+// ------------------------------------------------------------------------------------------
+struct SeqSrc {
+    const uint8_t* bytes;   // packed source (nullptr => ASCII consensus in `ascii`)
+    const char* ascii;
+    int len;                // bases without markers
+    int nb;                 // 2 or 4 bits per base
+    bool head, tail;        // J / O markers
+    int type;
+};
+
+template <bool kOneTile>
+__device__ __forceinline__ bool add_sequence(Graph& g, const Params& P, const Caps& caps, int16_t* H,
+                                             const SeqSrc& s, Scores sc, uint16_t* path) {
+    const int lane = lane_id();
+    const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
+    if (len > caps.lcap) return false;
+    uint8_t* dst = g.seq + (s.head ? 1 : 0);
+    if (s.bytes) {
+        if (s.nb == 2) decode2(s.bytes, s.len, dst); else decode4(s.bytes, s.len, dst);
+    } else {
+        for (int p = lane; p < s.len; p += 32) {
+            const char c = s.ascii[p];
+            dst[p] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+        }
+    }
+    if (lane == 0) {
+        if (s.head) g.seq[0] = kCodeJ;
+        if (s.tail) g.seq[len - 1] = kCodeO;
+    }
+    __syncwarp();
+
+    AlnSpan span;
+    span.first = -1; span.last = -1;
+    if (g.n_nodes > 0) {   // reference sisd_alignment_engine.cpp:249-251
+        const int tiles = kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols;
+        const int cols = tiles * kTileCols;
+        // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
+        const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
+        if (S * (g.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
+        build_profile(g, len, cols, sc);
+        __syncwarp();
+        EndCell ec = dp_fill<kOneTile>(g, H, len, tiles, s.type, sc);
+        span = traceback(g, H, cols, ec, s.type, sc, g.n_nodes + len + 4);
+    }
+    if (!add_to_graph(g, caps, len, span, path)) return false;
+    return topo_sort(g, caps);
+}
+
+// ------------------------------------------------------------------------------------------
+// Window driver (reference src/Window.cpp:44-254)
+// ------------------------------------------------------------------------------------------
+template <bool kOneTile>
+__device__ __forceinline__ int run_short(Graph& g, const Params& P, const Caps& caps, int16_t* H,
+                                         const WinDesc& w, char* out) {
+    const int lane = lane_id();
+    const ArmDesc* a = P.arms + w.first_arm;
+    const Scores sc = {P.sr_m, P.sr_n, P.sr_g};
+    const int n_arms = w.n_internal + w.n_pre + w.n_suf;
+    // arms_added (reference :90,106,117,128)
+    bool added = false;
+    for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
+    added = __any_sync(kFull, added);
+    if (!added) return -1;   // caller copies the draft (:150-152)
+
+    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+    SeqSrc s;
+    s.ascii = nullptr;
+    if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
+        s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
+        s.head = true; s.tail = true; s.type = kNW;
+        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+    }
+    s.nb = 2;
+    for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
+        if (a[k].len == 0) continue;
+        s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
+        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+    }
+    const ArmDesc* pre = a + w.n_internal;
+    for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
+        if (pre[k].len == 0) continue;
+        s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
+        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+    }
+    const ArmDesc* suf = pre + w.n_pre;
+    for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
+        if (suf[k].len == 0) continue;
+        s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
+        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+    }
+    const int nc = heaviest_bundle(g);
+    // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
+    const int n = nc >= 2 ? nc - 2 : 0;
+    for (int p = lane; p < n; p += 32) out[p] = code_to_char(g.letter[g.cons[p + 1]]);
+    return n;
+}
+
+// LONG windows: two rounds with the lr scores, all kNW, support counts and
+// curation (reference src/Window.cpp:156-254, graph.cpp:371-388,533-568).
+template <bool kOneTile>
+__device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& caps, int16_t* H,
+                                        const WinDesc& w, char* out, uint16_t* paths, uint64_t p_slot) {
+    const int lane = lane_id();
+    const ArmDesc* a = P.arms + w.first_arm;
+    const Scores sc = {P.lr_m, P.lr_n, P.lr_g};
+    const int n_arms = w.n_internal + w.n_pre + w.n_suf;
+    bool added = false;
+    for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
+    added = __any_sync(kFull, added);
+    if (!added) return -1;
+    // (UINT)std::floor(_num_internal * _cThresh), float _cThresh = 0.4 (reference :28,245)
+    const uint32_t thres = (uint32_t)floorf(__fmul_rn((float)w.n_internal, 0.4f));
+
+    // path slot: [0, n_arms+2) 32-bit start offsets (as two u16 each), then node ids
+    uint32_t* pstart = reinterpret_cast<uint32_t*>(paths);
+    uint16_t* pnodes = paths + 2 * (n_arms + 2);
+    const uint64_t pcap = p_slot - 2 * (n_arms + 2);
+
+    int n_cons = 0;
+    for (int round = 0; round < 2; ++round) {
+        g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+        uint32_t used = 0;
+        SeqSrc s;
+        s.head = false; s.tail = false; s.type = kNW;
+        auto add = [&](const SeqSrc& q) -> bool {
+            if (used + (uint32_t)q.len > pcap) return false;
+            if (lane == 0) pstart[g.n_seq] = used;
+            const bool ok = add_sequence<kOneTile>(g, P, caps, H, q, sc, pnodes + used);
+            used += q.len;
+            return ok;
+        };
+        if (round == 0) {   // :174-179
+            s.bytes = P.packed + w.draft_off; s.ascii = nullptr; s.len = w.draft_len; s.nb = 4;
+            if (!add(s)) return -2;
+        } else if (n_cons > 0) {   // :167-172
+            s.bytes = nullptr; s.ascii = out; s.len = n_cons; s.nb = 0;
+            if (!add(s)) return -2;
+        }
+        s.ascii = nullptr; s.nb = 2;
+        for (int k = 0; k < n_arms; ++k) {   // :180-207 (container order, engine stays kNW)
+            if (a[k].len == 0) continue;
+            s.bytes = P.packed + a[k].off; s.len = a[k].len;
+            if (!add(s)) return -2;
+        }
+        if (lane == 0) pstart[g.n_seq] = used;
+        __syncwarp();
+
+        const int nc = heaviest_bundle(g);
+        // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
+        uint16_t* msa = g.n2r;
+        if (lane == 0) {
+            int id = 0;
+            for (int i = 0; i < g.n_nodes; ++i) {
+                const int v = g.r2n[i];
+                msa[v] = (uint16_t)id;
+                const int cnt = g.al_cnt[v];
+                for (int k = 0; k < cnt; ++k) msa[g.r2n[++i]] = (uint16_t)id;
+                ++id;
+            }
+        }
+        // support counts (graph.cpp:542-564) -> reuse score (free after the bundle)
+        uint32_t* sup = reinterpret_cast<uint32_t*>(g.score);
+        __syncwarp();
+        for (int c = lane; c < nc; c += 32) sup[c] = 0;
+        __syncwarp();
+        for (int q = lane; q < g.n_seq; q += 32) {
+            const uint32_t b = pstart[q], e = pstart[q + 1];
+            int c = 0;
+            for (uint32_t k = b; k < e; ++k) {
+                const int v = pnodes[k];
+                const int mv = msa[v];
+                while (c < nc && msa[g.cons[c]] < mv) ++c;
+                if (c >= nc) break;
+                if (msa[g.cons[c]] == mv && g.letter[v] == g.letter[g.cons[c]]) atomicAdd(&sup[c], 1u);
+            }
+        }
+        __syncwarp();
+        // curate (src/Window.cpp:239-254): ordered compaction
+        int kept = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + lane;
+            const bool keep = c < nc && sup[c] >= thres;
+            const unsigned km = __ballot_sync(kFull, keep);
+            if (keep) out[kept + __popc(km & ((1u << lane) - 1u))] = code_to_char(g.letter[g.cons[c]]);
+            kept += __popc(km);
+        }
+        n_cons = kept;
+        __syncwarp();
+        __threadfence_block();
+    }
+    return n_cons;
+}
+
+template <bool kSmem, bool kOneTile>
+__global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = lane_id();
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int gwarp = blockIdx.x * warps_per_cta + warp_in_cta;
+    const Caps caps = P.caps;
+    const ArenaLayout L = arena_layout(caps);
+    uint8_t* arena = kSmem ? (smem + (size_t)warp_in_cta * L.total) : (P.gws + (size_t)gwarp * P.g_slot);
+    Graph g = make_graph(arena, L);
+    int16_t* H = P.H + (size_t)gwarp * P.h_slot;
+    uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
+
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(P.queue, 1u);
+        wi = __shfl_sync(kFull, wi, 0);
+        if (wi >= P.n_work) break;
+        const uint32_t widx = P.work ? P.work[wi] : wi;
+        const WinDesc w = P.win[widx];
+        char* out = P.out + P.out_pos[widx];
+        const uint32_t n = w.n_internal + w.n_pre + w.n_suf;
+        int res;
+        if (w.n_empty > n) {
+            res = 0;   // reference src/Window.cpp:47-49
+        } else if (n >= 2) {
+            if (w.wtype == 0) res = run_short<kOneTile>(g, P, caps, H, w, out);
+            else if (paths) res = run_long<kOneTile>(g, P, caps, H, w, out, paths, P.p_slot);
+            else res = -2;
+        } else {
+            res = -1;
+        }
+        if (res == -1) {   // draft copy (reference :58-60,150-152,233-235)
+            const uint8_t* src = P.packed + w.draft_off;
+            for (int p = lane; p < (int)w.draft_len; p += 32) {
+                int v = (src[p >> 1] >> ((p & 1) ? 0 : 4)) & 15;
+                out[p] = code_to_char(v > 4 ? 4 : v);
+            }
+            res = (int)w.draft_len;
+        }
+        if (lane == 0) {
+            if (res == -2) {
+                const uint32_t k = atomicAdd(P.overflow, 1u);
+                P.overflow[1 + k] = widx;
+            } else {
+                P.out_len[widx] = (uint32_t)res;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Host-side launcher
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, int blocks, int warps_per_block,
+                       size_t smem_bytes, cudaStream_t stream) {
+    void (*k)(const Params) = nullptr;
+    if (smem_graph) k = one_tile ? poa_kernel<true, true> : poa_kernel<true, false>;
+    else k = one_tile ? poa_kernel<false, true> : poa_kernel<false, false>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace hypo_b200

@@ -1,0 +1,127 @@
+// poa_kernel.cuh — device side of the B200-native POA-consensus path.
+//
+// One warp owns one weak-region window at a time and runs the whole of
+// hypo::Window::generate_consensus for it (reference src/Window.cpp:44-254):
+// for every read segment ("arm") in the reference's order it
+//   1. decodes the 2-bit PackedSeq bytes and builds the query profile,
+//   2. fills the sequence-to-graph DP (spoa SISD linear-gap semantics,
+//      reference external/spoa/src/sisd_alignment_engine.cpp:263-342),
+//   3. walks the equality-driven traceback (:344-437),
+//   4. fuses the alignment into the DAG (reference external/spoa/src/graph.cpp:154-271),
+//   5. re-derives spoa's exact DFS topological order (:293-353),
+// and finally extracts the heaviest-bundle consensus (:610-705), for LONG windows
+// with the per-column support counts + curation (:533-568, src/Window.cpp:239-254).
+//
+// Data placement:
+//   * the growing DAG (SoA, 16-bit indices) lives in shared memory (tier S) or in a
+//     global workspace (tier L, for windows that overflow the shared-memory capacities);
+//   * the DP matrix lives in global memory and is sized to stay L2-resident; every warp
+//     keeps the previous row in registers so the common pred == previous-rank case never
+//     touches memory; rows are written once, coalesced, 8 bytes per lane;
+//   * cells are 16-bit, two per register, updated with the sm_100 DPX instructions
+//     (VIADDMNMX.S16x2 / VIMNMX3.S16x2); the horizontal gap pass is a warp-shuffle
+//     prefix-max (the matrix is stored g-normalised, H^[i][j] = H[i][j] - j*g, which
+//     turns the max-plus scan into a plain prefix max and leaves every equality test of
+//     the traceback unchanged).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hypo_b200 {
+
+// ---- ABI structs (must match include/hypo_b200.h) --------------------------------------
+struct WinDesc {
+    uint64_t draft_off, first_arm;
+    uint32_t draft_len, n_internal, n_pre, n_suf, n_empty, wtype;
+};
+struct ArmDesc {
+    uint64_t off;
+    uint32_t len, reserved;
+};
+static_assert(sizeof(WinDesc) == 40 && sizeof(ArmDesc) == 16, "ABI layout");
+
+// ---- constants ---------------------------------------------------------------------------
+constexpr int kNR = 2;                       // packed registers per lane per tile
+constexpr int kTileCols = 32 * 2 * kNR;      // 128 DP columns per tile
+constexpr uint16_t kNone = 0xFFFF;
+constexpr int kNegInf = -30000;              // "minus infinity" that survives one int16 add
+constexpr uint32_t kNegInf2 = 0x8AD08AD0u;   // (kNegInf, kNegInf) packed
+constexpr int kAlSlots = 6;                  // clique <= 7 letters (J O A C G T N) => <= 6 peers
+constexpr int kNumCodes = 7;                 // A C G T N J O
+constexpr int kCodeJ = 5, kCodeO = 6;
+constexpr int kMaxH16 = 29000;               // int16 safety bound for |H^|
+
+enum AlignType { kNW = 0, kLOV = 1, kROV = 2 };
+
+// Capacities of one tier (one kernel launch).
+struct Caps {
+    int ncap;      // nodes
+    int ecap;      // edges
+    int acap;      // aligned-list blocks (one per node that is member of a clique)
+    int scap;      // DFS stack entries
+    int lcap;      // sequence length incl. markers
+    int tiles;     // ceil((lcap+1)/kTileCols)
+};
+
+struct Params {
+    const WinDesc* win;
+    const ArmDesc* arms;
+    const uint8_t* packed;
+    const uint32_t* work;        // window ids to process in this launch (nullptr = identity)
+    uint32_t n_work;
+    uint32_t* queue;             // [0] = next work index (atomic)
+    char* out;                   // consensus bytes
+    const uint64_t* out_pos;     // where window w writes
+    uint32_t* out_len;           // consensus length of window w
+    uint32_t* overflow;          // [0] = count, [1..] = window ids that exceeded this tier
+    int16_t* H;                  // DP workspace, one slot per warp
+    uint64_t h_slot;             // elements per slot
+    uint8_t* gws;                // tier L: graph workspace, one slot per warp
+    uint64_t g_slot;             // bytes per slot
+    uint16_t* paths;             // LONG: per-warp node paths, one slot per warp
+    uint64_t p_slot;             // elements per slot
+    Caps caps;
+    int sr_m, sr_n, sr_g, lr_m, lr_n, lr_g;
+};
+
+// Bytes of graph arena one warp needs for the given capacities.
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+struct ArenaLayout {
+    uint32_t letter, in_head, in_tail, out_deg, al_blk, al_cnt, mark, n2r, r2n;
+    uint32_t e_src, e_dst, e_w, e_next, al_pool, stack, seq, cur, prof, total;
+    // epilogue scratch, aliased over [stack, seq, cur, prof] which are dead by then
+    uint32_t score, pred, cons;
+};
+
+__host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
+    ArenaLayout L;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) { uint32_t r = o; o = align16(o + bytes); return r; };
+    L.letter = take(c.ncap);
+    L.in_head = take(2u * c.ncap);
+    L.in_tail = take(2u * c.ncap);
+    L.out_deg = take(2u * c.ncap);
+    L.al_blk = take(2u * c.ncap);
+    L.al_cnt = take(c.ncap);
+    L.mark = take(c.ncap);
+    L.n2r = take(2u * c.ncap);
+    L.r2n = take(2u * c.ncap);
+    L.e_src = take(2u * c.ecap);
+    L.e_dst = take(2u * c.ecap);
+    L.e_w = take(2u * c.ecap);
+    L.e_next = take(2u * c.ecap);
+    L.al_pool = take(2u * kAlSlots * c.acap);
+    L.stack = take(2u * c.scap);
+    L.seq = take(c.lcap + 1);
+    L.cur = take(2u * (c.lcap + 1));
+    L.prof = take(2u * kNumCodes * c.tiles * kTileCols);
+    L.score = L.stack;
+    L.pred = L.score + align16(4u * c.ncap);
+    L.cons = L.pred + align16(2u * c.ncap);
+    uint32_t end = L.cons + align16(2u * c.ncap);
+    L.total = o > end ? o : end;
+    return L;
+}
+
+}  // namespace hypo_b200

@@ -1,0 +1,116 @@
+"""ctypes binding of the C ABI in include/hypo_b200.h (hypo_b200/libhypo_b200.so).
+
+This is the only way the Python host layer reaches the device.  There is no CPU fallback:
+if the shared library is missing or no CUDA device is usable, every call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .batch import WindowBatch, split_consensus
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhypo_b200.so")
+
+ABI_SYMBOLS = (
+    "hypo_gpu_init",
+    "hypo_gpu_out_bound",
+    "hypo_gpu_consensus_batch",
+    "hypo_gpu_consensus_batch_device",
+    "hypo_gpu_launch_count",
+    "hypo_gpu_last_error",
+    "hypo_gpu_shutdown",
+    "hypo_gpu_abi_version",
+)
+
+
+class HypoGpuError(RuntimeError):
+    """Raised for every non-zero return of the C ABI; mirrors the reference's
+    `fprintf(stderr, "[Hypo::X] Error: ...")` + exit(1) convention with an exception."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[Hypo::GPU] Error: {msg} (code {code})")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HypoGpuError(
+                -1,
+                f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a); there is no CPU fallback",
+            )
+        L = C.CDLL(LIB_PATH)
+        L.hypo_gpu_init.restype = C.c_int
+        L.hypo_gpu_init.argtypes = [C.POINTER(C.c_int8), C.c_int]
+        L.hypo_gpu_out_bound.restype = C.c_uint64
+        L.hypo_gpu_out_bound.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.hypo_gpu_consensus_batch.restype = C.c_int
+        L.hypo_gpu_consensus_batch.argtypes = [
+            C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+            C.c_void_p, C.c_uint64, C.c_void_p]
+        L.hypo_gpu_consensus_batch_device.restype = C.c_int
+        L.hypo_gpu_consensus_batch_device.argtypes = [
+            C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hypo_gpu_launch_count.restype = C.c_uint64
+        L.hypo_gpu_last_error.restype = C.c_char_p
+        L.hypo_gpu_shutdown.restype = None
+        L.hypo_gpu_abi_version.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise HypoGpuError(rc, lib().hypo_gpu_last_error().decode(errors="replace"))
+
+
+def init(scores: Sequence[int] = (5, -4, -8, 3, -5, -4), device: int = 0) -> None:
+    """Window::prepare_for_poa (reference src/Window.cpp:31-42): fix the score parameters."""
+    sc = (C.c_int8 * 6)(*[int(x) for x in scores])
+    _check(lib().hypo_gpu_init(sc, int(device)))
+
+
+def shutdown() -> None:
+    lib().hypo_gpu_shutdown()
+
+
+def launch_count() -> int:
+    return int(lib().hypo_gpu_launch_count())
+
+
+def consensus_batch_host(batch: WindowBatch, out: Optional[np.ndarray] = None,
+                         out_off: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """hypo_gpu_consensus_batch on host buffers; returns (bytes, offsets[n_win+1])."""
+    L = lib()
+    if out is None:
+        cap = int(batch.out_bound().sum()) + 16
+        out = np.empty(cap, np.uint8)
+    if out_off is None:
+        out_off = np.zeros(batch.n_win + 1, np.uint64)
+    _check(L.hypo_gpu_consensus_batch(
+        batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data, batch.n_arms,
+        batch.packed.ctypes.data, batch.packed.size, out.ctypes.data, out.size, out_off.ctypes.data))
+    return out, out_off
+
+
+def consensus(batch: WindowBatch) -> List[str]:
+    out, off = consensus_batch_host(batch)
+    return split_consensus(out, off)
+
+
+def consensus_batch_device(d_win: int, n_win: int, d_arms: int, n_arms: int, d_packed: int,
+                           packed_bytes: int, d_out: int, d_out_pos: int, d_out_len: int,
+                           stream: int = 0) -> None:
+    """hypo_gpu_consensus_batch_device on raw device pointers (e.g. torch tensors' data_ptr())."""
+    _check(lib().hypo_gpu_consensus_batch_device(d_win, n_win, d_arms, n_arms, d_packed, packed_bytes,
+                                                 d_out, d_out_pos, d_out_len, stream))

@@ -1,0 +1,80 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol that
+include/hypo_b200.h declares, the descriptor layouts match, and the product path fails loudly
+(no CPU fallback) when no device is usable."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hypo_b200 import native
+from hypo_b200.batch import ARM_DTYPE, WIN_DTYPE, build_batch, pack2, pack4, unpack2, unpack4, WindowSpec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "hypo_b200.h")).read()
+    return sorted(set(re.findall(r"\b(hypo_gpu_\w+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    if not os.path.exists(native.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(native.LIB_PATH)
+    declared = _declared_symbols()
+    assert set(declared) == set(native.ABI_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.hypo_gpu_abi_version.restype = ctypes.c_int
+    assert lib.hypo_gpu_abi_version() == 1
+
+
+def test_descriptor_layouts_match_header():
+    assert WIN_DTYPE.itemsize == 40 and ARM_DTYPE.itemsize == 16
+    assert [WIN_DTYPE.fields[n][1] for n in ("draft_off", "first_arm", "draft_len", "n_internal", "n_pre",
+                                            "n_suf", "n_empty", "wtype")] == [0, 8, 16, 20, 24, 28, 32, 36]
+    assert [ARM_DTYPE.fields[n][1] for n in ("off", "len", "reserved")] == [0, 8, 12]
+
+
+def test_packing_matches_packedseq_layout():
+    # reference src/PackedSeq.cpp:45 — PackedSeq<2>: base i in bits 6-2*(i&3) of byte i>>2
+    assert pack2("ACGT").tolist() == [0b00011011]
+    assert pack2("TGCAT").tolist() == [0b11100100, 0b11000000]
+    # reference src/PackedSeq.cpp:48 — PackedSeq<4>: even base in the high nibble, N = 4
+    assert pack4("ANT").tolist() == [0x04, 0x30]
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 4, 5, 31, 120):
+        s = "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
+        assert unpack2(pack2(s), 0, n) == s
+        assert unpack4(pack4(s), 0, n) == s
+    with pytest.raises(ValueError):
+        pack2("ACGN")
+
+
+def test_batch_select_reindexes_arms():
+    specs = [WindowSpec("ACGT", ["AC", "ACG"], ["A"], [], 0, 0), WindowSpec("TTTT", ["TT", "TTT", "T"], [], ["TTTT"], 1, 0),
+             WindowSpec("GG", [], [], [], 0, 0)]
+    b = build_batch(specs)
+    sub = b.select(np.array([1, 2]))
+    assert sub.n_win == 2 and sub.n_arms == 4
+    assert sub.spec(0).internal == ["TT", "TTT", "T"] and sub.spec(0).suf == ["TTTT"] and sub.spec(0).n_empty == 1
+    assert sub.spec(1).draft == "GG"
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must raise, not silently compute on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(native.HypoGpuError):
+        native.init((5, -4, -8, 3, -5, -4), 0)
+    b = build_batch([WindowSpec("ACGT", ["ACGT", "ACGT"], [], [], 0, 0)])
+    with pytest.raises(native.HypoGpuError):
+        native.consensus(b)
