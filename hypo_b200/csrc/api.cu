@@ -91,6 +91,10 @@ struct Ctx {
     DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
     DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp;
     void* pinned_ctrl = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
+    uint32_t poa_launches = 0;
+    uint32_t tier_windows[8] = {0};
 } g;
 
 std::mutex g_mu;
@@ -210,8 +214,8 @@ struct Tier {
 //     16 warps/SM.  T1: anything up to 1023 columns with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 const Tier kTiers[] = {
-    {true, true, false, false, 320, 576, 64, 320, 127, 8, 2},
-    {true, false, true, false, 1536, 3072, 256, 1536, 1023, 4, 1},
+    {true, true, false, false, 320, 576, 128, 320, 127, 8, 2},
+    {true, false, true, false, 1536, 3072, 512, 1536, 1023, 4, 1},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1},
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1},
 };
@@ -228,6 +232,9 @@ int check_scores(const int8_t s[6]) {
 int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t n_arms,
                const uint8_t* d_packed, uint64_t packed_bytes, char* d_out, const uint64_t* d_out_pos,
                uint32_t* d_out_len, const WinStat* d_stats, cudaStream_t stream) {
+    g.poa_ms = 0.f;
+    g.poa_launches = 0;
+    memset(g.tier_windows, 0, sizeof(g.tier_windows));
     if (n_win == 0) return HYPO_OK;
     if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
     // control block: [0..kNumTiers) TierMax, then queue counters
@@ -341,10 +348,19 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         P.caps = caps;
         P.sr_m = g.scores[0]; P.sr_n = g.scores[1]; P.sr_g = g.scores[2];
         P.lr_m = g.scores[3]; P.lr_n = g.scores[4]; P.lr_g = g.scores[5];
+        CUDA_TRY(cudaEventRecord(g.ev0, stream));
         CUDA_TRY(launch_poa(P, T.smem_graph, T.one_tile, blocks, wpb, smem, stream));
+        CUDA_TRY(cudaEventRecord(g.ev1, stream));
         ++g.launches;
         CUDA_TRY(cudaMemcpyAsync(h_ovf_count, d_over, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+            g.poa_ms += ms;
+            g.poa_launches += 1;
+            g.tier_windows[t] += n_work;
+        }
         carry = *h_ovf_count;
         ovf_buf ^= 1;
     }
@@ -400,6 +416,8 @@ int hypo_gpu_init(const int8_t scores[6], int device) {
                     prop.major, prop.minor);
     if (!g.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     if (!g.pinned_ctrl) CUDA_TRY(cudaHostAlloc(&g.pinned_ctrl, 4096, cudaHostAllocDefault));
+    if (!g.ev0) CUDA_TRY(cudaEventCreate(&g.ev0));
+    if (!g.ev1) CUDA_TRY(cudaEventCreate(&g.ev1));
     g.device = device;
     g.sms = prop.multiProcessorCount;
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -507,6 +525,43 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     return HYPO_OK;
 }
 
+int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, const uint32_t* d_out_len,
+                            uint64_t n_win, char* d_compact, uint64_t compact_cap, uint64_t* d_off,
+                            uint64_t* total, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err.clear();
+    if (!g.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    CUDA_TRY(cudaSetDevice(g.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    if (n_win == 0) { if (total) *total = 0; return HYPO_OK; }
+    CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
+    uint64_t* d_len64 = (uint64_t*)g.out_off.p;
+    const int tb = 256;
+    widen_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, s>>>(d_out_len, d_len64, n_win);
+    CUDA_TRY(cudaMemsetAsync(d_len64 + n_win, 0, sizeof(uint64_t), s));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len64, d_off, n_win + 1, s));
+    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
+    uint64_t* h64 = (uint64_t*)((char*)g.pinned_ctrl + 3072);
+    CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (total) *total = *h64;
+    if (*h64 > compact_cap) return fail(HYPO_E_OUT_CAP, "compact output needs %llu bytes, capacity is %llu",
+                                        (unsigned long long)*h64, (unsigned long long)compact_cap);
+    gather_kernel<<<(unsigned)((n_win * 32 + tb - 1) / tb), tb, 0, s>>>(d_scratch, d_out_pos, d_out_len, d_off, d_compact, n_win);
+    g.launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return HYPO_OK;
+}
+
+int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[4]) {
+    if (poa_kernel_ms) *poa_kernel_ms = g.poa_ms;
+    if (poa_launches) *poa_launches = g.poa_launches;
+    if (tier_windows) for (int t = 0; t < 4; ++t) tier_windows[t] = g.tier_windows[t];
+    return HYPO_OK;
+}
+
 void hypo_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.init && !g.stream) return;
@@ -518,6 +573,9 @@ void hypo_gpu_shutdown(void) {
     g.pinned_ctrl = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
+    if (g.ev0) cudaEventDestroy(g.ev0);
+    if (g.ev1) cudaEventDestroy(g.ev1);
+    g.ev0 = g.ev1 = nullptr;
     g.init = false;
 }
 

@@ -12,24 +12,27 @@ constexpr unsigned kFull = 0xffffffffu;
 // Per-warp state
 // ------------------------------------------------------------------------------------------
 struct Graph {
-    uint8_t* letter;      // node -> letter code (0..6 = A C G T N J O)
-    uint16_t* in_head;    // node -> first in-edge (insertion order), kNone if none
-    uint16_t* in_tail;
-    uint16_t* out_deg;    // node -> number of out-edges (only "== 0" is ever asked)
-    uint16_t* al_blk;     // node -> block in al_pool holding its aligned_nodes_ids_, kNone
+    uint8_t* ninfo;       // node -> letter code (bits 0-2: A C G T N J O) | has out-edge (bit 3)
     uint8_t* al_cnt;      // node -> number of aligned nodes
-    uint8_t* mark;        // toposort scratch
+    uint8_t* in_deg;      // node -> in-degree
+    uint16_t* in_head;    // node -> first in-edge (insertion order), kNone if none
+    uint16_t* al_blk;     // node -> block in al_pool holding its aligned_nodes_ids_, kNone
     uint16_t* n2r;        // node -> rank
     uint16_t* r2n;        // rank -> node
     uint16_t* e_src;
-    uint16_t* e_dst;
     uint16_t* e_w;        // Edge::total_weight_ (2 per traversal)
     uint16_t* e_next;     // next in-edge of the same destination
     uint16_t* al_pool;
+    uint16_t* pstart;     // rank -> offset into prows (CSR)
+    uint8_t* rcode;       // rank -> letter code | sink (bit 3)
+    uint16_t* prows;      // predecessor DP rows, in-edge order
+    uint16_t* fp;         // DP row -> first predecessor row
     uint16_t* stack;
     uint8_t* seq;         // current sequence, letter codes
     uint16_t* cur;        // per sequence position: aligned node / resolved node
     int16_t* prof;        // [code][column] (match ? m : n) - g
+    uint8_t* mark;        // toposort scratch
+    uint16_t* lists;      // toposort scratch: per-lane emission lists
     int32_t* score;       // epilogue
     uint16_t* pred;
     uint16_t* cons;
@@ -38,24 +41,27 @@ struct Graph {
 
 __device__ __forceinline__ Graph make_graph(uint8_t* base, const ArenaLayout& L) {
     Graph g;
-    g.letter = base + L.letter;
-    g.in_head = (uint16_t*)(base + L.in_head);
-    g.in_tail = (uint16_t*)(base + L.in_tail);
-    g.out_deg = (uint16_t*)(base + L.out_deg);
-    g.al_blk = (uint16_t*)(base + L.al_blk);
+    g.ninfo = base + L.ninfo;
     g.al_cnt = base + L.al_cnt;
-    g.mark = base + L.mark;
+    g.in_deg = base + L.in_deg;
+    g.in_head = (uint16_t*)(base + L.in_head);
+    g.al_blk = (uint16_t*)(base + L.al_blk);
     g.n2r = (uint16_t*)(base + L.n2r);
     g.r2n = (uint16_t*)(base + L.r2n);
     g.e_src = (uint16_t*)(base + L.e_src);
-    g.e_dst = (uint16_t*)(base + L.e_dst);
     g.e_w = (uint16_t*)(base + L.e_w);
     g.e_next = (uint16_t*)(base + L.e_next);
     g.al_pool = (uint16_t*)(base + L.al_pool);
+    g.pstart = (uint16_t*)(base + L.pstart);
+    g.rcode = base + L.rcode;
+    g.prows = (uint16_t*)(base + L.prows);
+    g.fp = (uint16_t*)(base + L.fp);
     g.stack = (uint16_t*)(base + L.stack);
     g.seq = base + L.seq;
     g.cur = (uint16_t*)(base + L.cur);
     g.prof = (int16_t*)(base + L.prof);
+    g.mark = base + L.mark;
+    g.lists = (uint16_t*)(base + L.lists);
     g.score = (int32_t*)(base + L.score);
     g.pred = (uint16_t*)(base + L.pred);
     g.cons = (uint16_t*)(base + L.cons);
@@ -101,16 +107,13 @@ __device__ __forceinline__ void build_profile(const Graph& g, int len, int cols,
 // DP fill (reference sisd_alignment_engine.cpp:263-342, initialisation :158-159,197-211,
 // 229-239).  Lane l owns columns [4l, 4l+4) of each 128-column tile as two s16x2 registers.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack2(int lo, int hi) {
-    return (uint32_t)(lo & 0xffff) | ((uint32_t)hi << 16);
-}
-__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
-__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+__device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
 
 // x = max(x, diag + prof, vert + g) for one predecessor row.
 __device__ __forceinline__ void relax(uint32_t (&x)[kNR], const uint32_t (&p)[kNR], uint32_t left,
                                       const uint32_t (&pf)[kNR], uint32_t g2) {
-    uint32_t prevreg = left;   // (.., pred[c0-1]) in the HIGH half
+    uint32_t prevreg = left;   // pred[c0-1] in the HIGH half
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
         uint32_t d = __byte_perm(prevreg, p[r], 0x5432);   // (pred[j-1] for lo, for hi)
@@ -120,29 +123,31 @@ __device__ __forceinline__ void relax(uint32_t (&x)[kNR], const uint32_t (&p)[kN
     }
 }
 
-// In-lane inclusive prefix max over the 2*kNR columns, then warp exclusive prefix max.
-// carry = prefix max of everything left of this tile (tile > 0) or kNegInf.
-// Returns the tile's total (for the next tile's carry).
-__device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry) {
-    int run = kNegInf;
+// Horizontal pass: H^[i][j] = max(H^[i][j], H^[i][j-1]) == inclusive prefix max over columns.
+// In-lane over the 2*kNR columns, then a warp scan of the lane totals.
+// carry = prefix max of everything left of this tile (tile > 0) or kNegInf; returns the new carry.
+template <bool kOneTile>
+__device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry, int lane) {
+    uint32_t runb = kNegInf2;   // running max broadcast to both halves
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
         uint32_t t = __byte_perm(x[r], kNegInf2, 0x1054);          // (lo: -inf, hi: x.lo)
-        x[r] = __vimax3_s16x2(x[r], t, pack2(run, run));
-        run = hi16(x[r]);
+        x[r] = __vimax3_s16x2(x[r], t, runb);
+        runb = __byte_perm(x[r], 0, 0x3232);                        // (x.hi, x.hi)
     }
-    int tot = run;
+    int tot = hi16(x[kNR - 1]);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         int y = __shfl_up_sync(kFull, tot, d);
-        if (lane_id() >= d) tot = max(tot, y);
+        if (lane >= d) tot = max(tot, y);
     }
     int excl = __shfl_up_sync(kFull, tot, 1);
-    if (lane_id() == 0) excl = kNegInf;
-    excl = max(excl, carry);
-    uint32_t cb = pack2(excl, excl);
+    if (lane == 0) excl = kNegInf;
+    if (!kOneTile) excl = max(excl, carry);
+    const uint32_t cb = bcast16(excl);
 #pragma unroll
     for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
+    if (kOneTile) return kNegInf;
     return max(__shfl_sync(kFull, tot, 31), carry);
 }
 
@@ -155,57 +160,55 @@ template <bool kOneTile>
 __device__ __forceinline__ EndCell dp_fill(const Graph& g, int16_t* __restrict__ H, int len, int tiles,
                                            int type, Scores sc) {
     const int lane = lane_id();
-    const int cols = tiles * kTileCols;
-    const uint32_t g2 = pack2(sc.g, sc.g);
-    const int end_tile = len / kTileCols, end_lane = (len % kTileCols) / (2 * kNR),
-              end_reg = (len % (2 * kNR)) / 2, end_hi = len & 1;
+    const int cols = kOneTile ? kTileCols : tiles * kTileCols;
+    const uint32_t g2 = bcast16(sc.g);
+    int16_t* Hl = H + lane * 4;
+    const int16_t* profl = g.prof + lane * 4;
+    const int n = g.n_nodes;
 
     // row 0: H^[0][j] = 0
-    for (int t = 0; t < tiles; ++t)
-        *reinterpret_cast<uint2*>(H + t * kTileCols + lane * 4) = make_uint2(0u, 0u);
+    for (int t = 0; t < (kOneTile ? 1 : tiles); ++t)
+        *reinterpret_cast<uint2*>(Hl + t * kTileCols) = make_uint2(0u, 0u);
 
     uint32_t prev[kNR];
 #pragma unroll
     for (int r = 0; r < kNR; ++r) prev[r] = 0u;
-    int prev_row = 0;
-    int best = INT_MIN, best_row = -1;
 
-    for (int rk = 0; rk < g.n_nodes; ++rk) {
-        const int v = g.r2n[rk];
-        const int code = g.letter[v];
-        const int e0 = g.in_head[v];
-        const int row = rk + 1;
-        int16_t* Hrow = H + (size_t)row * cols;
+    int ps = g.pstart[0];
+    for (int rk = 0; rk < n; ++rk) {
+        const int pe = g.pstart[rk + 1];
+        const int code = g.rcode[rk] & 7;
+        const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
         int carry = kNegInf;
-        int endval = 0;
         uint32_t x[kNR];
         for (int t = 0; t < (kOneTile ? 1 : tiles); ++t) {
+            const unsigned toff = (unsigned)t * kTileCols;
 #pragma unroll
             for (int r = 0; r < kNR; ++r) x[r] = kNegInf2;
             uint32_t pf[kNR];
             {
-                uint2 q = *reinterpret_cast<const uint2*>(g.prof + code * cols + t * kTileCols + lane * 4);
+                const uint2 q = *reinterpret_cast<const uint2*>(profl + (unsigned)code * (unsigned)cols + toff);
                 pf[0] = q.x; pf[1] = q.y;
             }
-            if (e0 == kNone) {
+            if (ps == pe) {
                 // no predecessor: virtual row 0 (reference :300-301)
-                uint32_t p[kNR] = {0u, 0u};
-                uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
+                const uint32_t p[kNR] = {0u, 0u};
+                const uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
                 relax(x, p, left, pf, g2);
             } else {
-                for (int e = e0; e != kNone; e = g.e_next[e]) {
-                    const int prow = g.n2r[g.e_src[e]] + 1;
+                for (int k = ps; k < pe; ++k) {
+                    const unsigned prow = g.prows[k];
                     uint32_t p[kNR];
-                    if (kOneTile && prow == prev_row) {
+                    if (kOneTile && prow == (unsigned)rk) {
                         p[0] = prev[0]; p[1] = prev[1];
                     } else {
-                        uint2 q = *reinterpret_cast<const uint2*>(H + (size_t)prow * cols + t * kTileCols + lane * 4);
+                        const uint2 q = *reinterpret_cast<const uint2*>(Hl + prow * (unsigned)cols + toff);
                         p[0] = q.x; p[1] = q.y;
                     }
                     uint32_t left = __shfl_up_sync(kFull, p[kNR - 1], 1);
                     if (lane == 0) {
-                        if (t == 0) left = kNegInf2;
-                        else left = (uint32_t)(uint16_t)H[(size_t)prow * cols + t * kTileCols - 1] << 16;
+                        if (kOneTile || t == 0) left = kNegInf2;
+                        else left = (uint32_t)(uint16_t)H[prow * (unsigned)cols + toff - 1] << 16;
                     }
                     relax(x, p, left, pf, g2);
                 }
@@ -213,31 +216,46 @@ __device__ __forceinline__ EndCell dp_fill(const Graph& g, int16_t* __restrict__
             // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
             // ROV pins it to 0 (reference :229-239)
             if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
-            carry = scan_row(x, carry);
-            *reinterpret_cast<uint2*>(Hrow + t * kTileCols + lane * 4) = make_uint2(x[0], x[1]);
-            if (t == end_tile) {
-                uint32_t w = end_reg == 0 ? x[0] : x[1];
-                endval = __shfl_sync(kFull, end_hi ? hi16(w) : lo16(w), end_lane);
-            }
+            carry = scan_row<kOneTile>(x, carry, lane);
+            *reinterpret_cast<uint2*>(Hl + rowoff + toff) = make_uint2(x[0], x[1]);
         }
-        if (kOneTile) { prev[0] = x[0]; prev[1] = x[1]; prev_row = row; }
+        if (kOneTile) { prev[0] = x[0]; prev[1] = x[1]; }
         else __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
-        // end cell (reference :276-288,328-340): strictly greater => lowest rank wins ties
-        const bool cand = (type == kLOV) || (g.out_deg[v] == 0);
-        if (cand && endval > best) { best = endval; best_row = row; }
+        ps = pe;
     }
     __syncwarp();
+
+    // end cell (reference :276-288,328-340): best last-column score over the candidate rows
+    // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
+    int best = INT_MIN, brow = 0x7fffffff;
+    for (int r = lane; r < n; r += 32) {
+        const bool cand = (type == kLOV) || (g.rcode[r] & 8);
+        if (cand) {
+            const int v = (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len];
+            if (v > best) { best = v; brow = r + 1; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const int ob = __shfl_xor_sync(kFull, best, d);
+        const int orow = __shfl_xor_sync(kFull, brow, d);
+        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+    }
     EndCell ec;
-    ec.row = best_row > 0 ? best_row : 0;
-    ec.col = best_row > 0 ? len : 0;
+    const bool any = brow != 0x7fffffff;
+    ec.row = any ? brow : 0;
+    ec.col = any ? len : 0;
     return ec;
 }
 
 // ------------------------------------------------------------------------------------------
-// Traceback (reference sisd_alignment_engine.cpp:344-437).  Executed redundantly by all
-// lanes (uniform control flow, broadcast loads); lane 0 records cur[pos].
-// Preference: diagonal via in-edge 0,1,..; vertical via in-edge 0,1,..; horizontal.
-// Returns first/last aligned sequence position (-1/-1 for an alignment without any).
+// Traceback (reference sisd_alignment_engine.cpp:344-437).
+// Preference at every cell: diagonal via in-edge 0,1,..; vertical via in-edge 0,1,..; horizontal.
+// Because "diagonal through the FIRST in-edge" is tested first, a run of such moves can be
+// verified by 32 lanes at once: the chain of first-predecessor rows is walked serially in shared
+// memory (fp[]), then lane k tests the equality for step k and the longest all-true prefix is
+// committed.  Every other move takes the serial path (uniform across lanes, broadcast loads).
+// Lane 0 / the owning lanes record cur[pos] = aligned node (kNone for a read-only column).
 // ------------------------------------------------------------------------------------------
 struct AlnSpan {
     int first, last;
@@ -249,43 +267,77 @@ __device__ __forceinline__ AlnSpan traceback(const Graph& g, const int16_t* __re
     int i = ec.row, j = ec.col;
     AlnSpan span;
     span.first = -1; span.last = -1;
-    int hij = (int)H[(size_t)i * cols + j];
+    const unsigned ucols = (unsigned)cols;
+    int hij = (int)H[(unsigned)i * ucols + (unsigned)j];
     const int mm = sc.m - sc.g, nn = sc.n - sc.g;
     int steps = 0;
     while ((type == kROV ? (i != 0 && j != 0) : (i != 0 || j != 0)) && steps++ < max_steps) {
+        if (i != 0 && j != 0) {
+            // ---- speculative diagonal run through first predecessors
+            int my_r = 0, my_rn = 0;
+            int r = i;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int rn = r != 0 ? (int)g.fp[r] : 0;
+                if (lane == k) { my_r = r; my_rn = rn; }
+                r = rn;
+            }
+            const int jj = j - lane;
+            bool ok = my_r != 0 && jj >= 1;
+            int hp = 0;
+            if (ok) {
+                const int hc = (int)H[(unsigned)my_r * ucols + (unsigned)jj];
+                hp = (int)H[(unsigned)my_rn * ucols + (unsigned)(jj - 1)];
+                const int s = ((g.rcode[my_r - 1] & 7) == g.seq[jj - 1]) ? mm : nn;
+                ok = hc == hp + s;
+            }
+            const unsigned mask = __ballot_sync(kFull, ok);
+            const int run = __ffs(~mask) - 1;   // leading all-true lanes (mask == ~0 -> -1 -> 32)
+            const int nrun = run < 0 ? 32 : run;
+            if (nrun > 0) {
+                if (lane < nrun) g.cur[jj - 1] = g.r2n[my_r - 1];
+                if (span.last < 0) span.last = j - 1;
+                span.first = j - nrun;
+                i = __shfl_sync(kFull, my_rn, nrun - 1);
+                hij = __shfl_sync(kFull, hp, nrun - 1);
+                j -= nrun;
+                steps += nrun - 1;
+                continue;
+            }
+        }
+        // ---- one general step
         int ni = i, nj = j, nh = hij;
         bool found = false;
         if (i != 0) {
-            const int v = g.r2n[i - 1];
-            const int e0 = g.in_head[v];
+            const int ps = g.pstart[i - 1], pe = g.pstart[i];
             if (j != 0) {
-                const int s = (g.letter[v] == g.seq[j - 1]) ? mm : nn;
-                if (e0 == kNone) {
-                    int h = (int)H[j - 1];
+                const int s = ((g.rcode[i - 1] & 7) == g.seq[j - 1]) ? mm : nn;
+                if (ps == pe) {
+                    const int h = (int)H[j - 1];
                     if (hij == h + s) { ni = 0; nj = j - 1; nh = h; found = true; }
                 } else {
-                    for (int e = e0; e != kNone; e = g.e_next[e]) {
-                        const int pi = g.n2r[g.e_src[e]] + 1;
-                        int h = (int)H[(size_t)pi * cols + j - 1];
+                    for (int k = ps; k < pe; ++k) {
+                        const int pi = g.prows[k];
+                        const int h = (int)H[(unsigned)pi * ucols + (unsigned)(j - 1)];
                         if (hij == h + s) { ni = pi; nj = j - 1; nh = h; found = true; break; }
                     }
                 }
             }
             if (!found) {
-                if (e0 == kNone) {
-                    int h = (int)H[j];
+                if (ps == pe) {
+                    const int h = (int)H[j];
                     if (hij == h + sc.g) { ni = 0; nj = j; nh = h; found = true; }
                 } else {
-                    for (int e = e0; e != kNone; e = g.e_next[e]) {
-                        const int pi = g.n2r[g.e_src[e]] + 1;
-                        int h = (int)H[(size_t)pi * cols + j];
+                    for (int k = ps; k < pe; ++k) {
+                        const int pi = g.prows[k];
+                        const int h = (int)H[(unsigned)pi * ucols + (unsigned)j];
                         if (hij == h + sc.g) { ni = pi; nj = j; nh = h; found = true; break; }
                     }
                 }
             }
         }
         if (!found && j != 0) {
-            int h = (int)H[(size_t)i * cols + j - 1];
+            const int h = (int)H[(unsigned)i * ucols + (unsigned)(j - 1)];
             if (hij == h) { ni = i; nj = j - 1; nh = h; found = true; }
         }
         if (!found) break;   // impossible for a consistent H; never spin
@@ -306,12 +358,11 @@ __device__ __forceinline__ AlnSpan traceback(const Graph& g, const int16_t* __re
 // Returns false if a capacity was exceeded (window is abandoned and re-run in a larger tier).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void init_node(const Graph& g, int id, int code) {
-    g.letter[id] = (uint8_t)code;
-    g.in_head[id] = kNone;
-    g.in_tail[id] = kNone;
-    g.out_deg[id] = 0;
-    g.al_blk[id] = kNone;
+    g.ninfo[id] = (uint8_t)code;
     g.al_cnt[id] = 0;
+    g.in_deg[id] = 0;
+    g.in_head[id] = kNone;
+    g.al_blk[id] = kNone;
 }
 
 __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len, AlnSpan span,
@@ -349,7 +400,7 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
             code = g.seq[p];
             if (x == kNone) {
                 need_new = true;
-            } else if (g.letter[x] == code) {
+            } else if ((g.ninfo[x] & 7) == code) {
                 res = x;
             } else {
                 need_new = true;
@@ -358,7 +409,7 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
                     const int cnt = g.al_cnt[x];
                     for (int k = 0; k < cnt; ++k) {
                         int a = g.al_pool[blk * kAlSlots + k];
-                        if (g.letter[a] == code) { res = a; need_new = false; break; }
+                        if ((g.ninfo[a] & 7) == code) { res = a; need_new = false; break; }
                     }
                 }
             }
@@ -407,12 +458,13 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
     g.n_nodes = n_nodes;
     g.n_al = n_al;
 
-    // edges (cur[p-1] -> cur[p]), weight 1+1 per traversal (:99-115,251-265,283-288)
+    // edges (cur[p-1] -> cur[p]), weight 1+1 per traversal (:99-115,251-265,283-288).  Every
+    // node of a sequence is distinct, so lanes touch disjoint in-lists / source nodes.
     int n_edges = g.n_edges;
     for (int p0 = 0; p0 < len; p0 += 32) {
         const int p = p0 + lane;
-        bool need_edge = false;
-        int src = 0, dst = 0;
+        bool need_edge = false, sat = false;
+        int src = 0, dst = 0, tail = kNone;
         if (p < len) {
             dst = g.cur[p];
             if (path) path[p] = (uint16_t)dst;
@@ -425,21 +477,21 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
                         need_edge = false;
                         break;
                     }
+                    tail = e;
                 }
+                sat = need_edge && g.in_deg[dst] >= 254;
             }
         }
         const unsigned em = __ballot_sync(kFull, need_edge);
-        if (n_edges + __popc(em) > caps.ecap) return false;
+        if (n_edges + __popc(em) > caps.ecap || __any_sync(kFull, sat)) return false;
         if (need_edge) {
             const int e = n_edges + __popc(em & lt_mask);
             g.e_src[e] = (uint16_t)src;
-            g.e_dst[e] = (uint16_t)dst;
             g.e_w[e] = 2;
             g.e_next[e] = kNone;
-            const int t = g.in_tail[dst];
-            if (t == kNone) g.in_head[dst] = (uint16_t)e; else g.e_next[t] = (uint16_t)e;
-            g.in_tail[dst] = (uint16_t)e;
-            g.out_deg[src] = (uint16_t)(g.out_deg[src] + 1);
+            if (tail == kNone) g.in_head[dst] = (uint16_t)e; else g.e_next[tail] = (uint16_t)e;
+            g.in_deg[dst] = (uint8_t)(g.in_deg[dst] + 1);
+            g.ninfo[src] = (uint8_t)(g.ninfo[src] | 8);
         }
         n_edges += __popc(em);
     }
@@ -450,72 +502,265 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
 }
 
 // ------------------------------------------------------------------------------------------
-// Topological sort (reference graph.cpp:293-353): the exact iterative DFS, because the rank
-// order it produces decides every tie (end cell, heaviest bundle, branch completion).
+// Topological sort (reference graph.cpp:293-353).  The rank order spoa's iterative DFS produces
+// decides every tie (end cell, heaviest bundle, branch completion), so it is reproduced exactly.
+//
+// The DFS's outer loop visits node ids in ascending order.  The warp processes 32 consecutive ids
+// per round: lane l replays, on its own, what the DFS would do when its outer loop reaches node
+// i0+l — assuming the lanes below it have already emitted — with a bounded recursion
+// (bulk_visit) that follows the reference's exploration order: aligned nodes last-to-first (only
+// their sources: their check_aligned flag is cleared), then the node's own not-yet-emitted
+// sources last-to-first, then the node followed by its aligned nodes.  Nodes a lane would emit
+// besides its own ("extras") are announced in a claim table; a lane may rely on extras announced
+// by LOWER lanes (second/third pass), any extra announced twice or any lane that cannot decide
+// within its bounds cuts the round there, and that one node is handled by the serial DFS
+// (dfs_from) — identical to the reference loop — before the next round starts behind it.
+// oracle/poa_oracle.c carries a sequential simulation of this scheme that is checked against
+// the plain DFS on every sort when POA_ORACLE_CHECK_BULK is set.
+//
 // mark bits: 0-1 = node mark (0 unmarked, 1 temporary, 2 permanent), bit 2 = "do not check
-// aligned nodes" (check_aligned_nodes[id] == false).  Serial on lane 0.
+// aligned nodes" (check_aligned_nodes[id] == false).
 // ------------------------------------------------------------------------------------------
+constexpr int kBulkDepth = 4;
+constexpr int kBulkMaxExtra = kBulkList - 2;   // list[0] = count, then <= 1 + kBulkMaxExtra nodes
+
+struct BulkCtx {
+    // raw views (a copy, so that the warp's Graph itself can stay in registers)
+    const uint8_t* mark;
+    const uint8_t* al_cnt;
+    const uint16_t* claim;
+    const uint16_t* in_head;
+    const uint16_t* e_next;
+    const uint16_t* e_src;
+    const uint16_t* al_blk;
+    const uint16_t* al_pool;
+    uint16_t* list;      // [0] = n, [1..n] = nodes in emission order
+    int i0, id, lane, round;
+    bool use_claims;
+};
+
+__device__ __forceinline__ bool bulk_ok(const BulkCtx& c, int s) {
+    if ((c.mark[s] & 3) == 2) return true;
+    if (s >= c.i0 && s < c.id) return true;                 // a lower lane of this round
+    if (c.use_claims) {
+        const int cl = c.claim[s];
+        if ((cl >> 5) == c.round && (cl & 31) < c.lane) return true;   // announced by a lower lane
+    }
+    const int n = c.list[0];
+    for (int k = 1; k <= n; ++k)
+        if (c.list[k] == s) return true;
+    return false;
+}
+
+__device__ bool bulk_visit(const BulkCtx& c, int p, int depth);
+
+__device__ __noinline__ bool bulk_sources(const BulkCtx& c, int v, int depth) {
+    int und[3], n_und = 0;
+    for (int e = c.in_head[v]; e != kNone; e = c.e_next[e]) {
+        const int s = c.e_src[e];
+        if (bulk_ok(c, s)) continue;
+        if (n_und == 3) return false;
+        und[n_und++] = s;
+    }
+    for (int u = n_und - 1; u >= 0; --u)
+        if (!bulk_ok(c, und[u]) && !bulk_visit(c, und[u], depth + 1)) return false;
+    return true;
+}
+
+__device__ __noinline__ bool bulk_visit(const BulkCtx& c, int p, int depth) {
+    if (depth > kBulkDepth || c.mark[p] != 0) return false;
+    const int nm = c.al_cnt[p];
+    const int blk = c.al_blk[p];
+    for (int k = nm - 1; k >= 0; --k) {
+        const int a = c.al_pool[blk * kAlSlots + k];
+        if (c.mark[a] != 0 || bulk_ok(c, a)) return false;
+        if (!bulk_sources(c, a, depth)) return false;
+    }
+    if (!bulk_sources(c, p, depth)) return false;
+    int n = c.list[0];
+    if (n + 1 + nm > 1 + kBulkMaxExtra) return false;
+    c.list[++n] = (uint16_t)p;
+    for (int k = 0; k < nm; ++k) c.list[++n] = c.al_pool[blk * kAlSlots + k];
+    c.list[0] = (uint16_t)n;
+    return true;
+}
+
+// Serial DFS from one root (lane 0), verbatim the reference's inner loop.
+__device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int root, int& nr) {
+    int sp = 0;
+    g.stack[sp++] = (uint16_t)root;
+    while (sp != 0) {
+        const int v = g.stack[sp - 1];
+        bool valid = true;
+        const int mv = g.mark[v];
+        if ((mv & 3) != 2) {
+            for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+                const int s = g.e_src[e];
+                if ((g.mark[s] & 3) != 2) {
+                    if (sp >= caps.scap) return false;
+                    g.stack[sp++] = (uint16_t)s;
+                    valid = false;
+                }
+            }
+            const bool check = (mv & 4) == 0;
+            const int cnt = g.al_cnt[v];
+            const int blk = g.al_blk[v];
+            if (check) {
+                for (int k = 0; k < cnt; ++k) {
+                    const int a = g.al_pool[blk * kAlSlots + k];
+                    const int ma = g.mark[a];
+                    if ((ma & 3) != 2) {
+                        if (sp >= caps.scap) return false;
+                        g.stack[sp++] = (uint16_t)a;
+                        g.mark[a] = (uint8_t)(ma | 4);
+                        valid = false;
+                    }
+                }
+            }
+            if (valid) {
+                g.mark[v] = (uint8_t)((mv & 4) | 2);
+                if (check) {
+                    g.r2n[nr++] = (uint16_t)v;
+                    for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * kAlSlots + k];
+                }
+            } else {
+                g.mark[v] = (uint8_t)((mv & 4) | 1);
+            }
+        }
+        if (valid) --sp;
+    }
+    return true;
+}
+
 __device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
     const int lane = lane_id();
     const int n = g.n_nodes;
-    for (int i = lane; i < n; i += 32) g.mark[i] = 0;
+    uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
+    for (int i = lane; i < n; i += 32) { g.mark[i] = 0; claim[i] = 0; }
     __syncwarp();
-    int ok = 1;
-    if (lane == 0) {
-        int nr = 0, sp = 0;
-        for (int i = 0; i < n && ok; ++i) {
-            if ((g.mark[i] & 3) != 0) continue;
-            g.stack[sp++] = (uint16_t)i;
-            while (sp != 0) {
-                const int v = g.stack[sp - 1];
-                bool valid = true;
-                const int mv = g.mark[v];
-                if ((mv & 3) != 2) {
-                    for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
-                        const int s = g.e_src[e];
-                        if ((g.mark[s] & 3) != 2) {
-                            if (sp >= caps.scap) { ok = 0; break; }
-                            g.stack[sp++] = (uint16_t)s;
-                            valid = false;
-                        }
-                    }
-                    if (!ok) break;
-                    const bool check = (mv & 4) == 0;
-                    const int cnt = g.al_cnt[v];
-                    const int blk = g.al_blk[v];
-                    if (check) {
-                        for (int k = 0; k < cnt; ++k) {
-                            const int a = g.al_pool[blk * kAlSlots + k];
-                            const int ma = g.mark[a];
-                            if ((ma & 3) != 2) {
-                                if (sp >= caps.scap) { ok = 0; break; }
-                                g.stack[sp++] = (uint16_t)a;
-                                g.mark[a] = (uint8_t)(ma | 4);
-                                valid = false;
-                            }
-                        }
-                        if (!ok) break;
-                    }
-                    if (valid) {
-                        g.mark[v] = (uint8_t)((mv & 4) | 2);
-                        if (check) {
-                            g.r2n[nr++] = (uint16_t)v;
-                            for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * kAlSlots + k];
-                        }
-                    } else {
-                        g.mark[v] = (uint8_t)((mv & 4) | 1);
-                    }
-                }
-                if (valid) --sp;
+    uint16_t* list = g.lists + lane * kBulkList;
+    int nr = 0, i0 = 0, round = 0;
+    while (i0 < n) {
+        if (++round == 2047) {   // claim encoding would wrap: start over with clean claims
+            for (int i = lane; i < n; i += 32) claim[i] = 0;
+            round = 1;
+            __syncwarp();
+        }
+        const int id = i0 + lane;
+        // status: 0 nothing to emit, 1 emit list, 2 undecided/failed, 3 superseded
+        int status = (id < n && (g.mark[id] & 3) != 2) ? 2 : 0;
+        BulkCtx c;
+        c.mark = g.mark; c.al_cnt = g.al_cnt; c.claim = claim; c.in_head = g.in_head; c.e_next = g.e_next;
+        c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool;
+        c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
+        for (int pass = 0; pass < 3; ++pass) {
+            bool changed = false;
+            if (status == 2) {
+                list[0] = 0;
+                c.use_claims = pass > 0;
+                if (bulk_visit(c, id, 0)) { status = 1; changed = true; }
+            }
+            __syncwarp();
+            if (changed) {
+                const int cnt = list[0];
+                for (int k = 1; k <= cnt; ++k)
+                    if (list[k] != id) claim[list[k]] = (uint16_t)((round << 5) | lane);
+            }
+            __syncwarp();
+            if (!__any_sync(kFull, changed)) break;
+            if (!__any_sync(kFull, status == 2)) break;
+        }
+        // a node announced by a lower lane is emitted there, not by its own lane
+        if (status == 1) {
+            const int cl = claim[id];
+            if ((cl >> 5) == round && (cl & 31) < lane) status = 3;
+        }
+        // where does the round end?
+        int cut = 32;
+        if (status == 2) cut = lane;
+        if (status == 3 && list[0] > 1) cut = lane;          // it announced extras it will not emit
+        if (status == 1) {
+            const int cnt = list[0];
+            for (int k = 1; k <= cnt; ++k) {
+                const int x = list[k];
+                if (x == id) continue;
+                const int cl = claim[x] & 31;
+                if (cl != lane) cut = min(cut, min(cl, lane));
             }
         }
+        cut = __reduce_min_sync(kFull, cut);
+        // commit the lanes below the cut, in lane order
+        const int cnt = (status == 1 && lane < cut) ? (int)list[0] : 0;
+        int off = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(kFull, off, d);
+            if (lane >= d) off += y;
+        }
+        const int total = __shfl_sync(kFull, off, 31);
+        off -= cnt;
+        for (int k = 1; k <= cnt; ++k) {
+            const int x = list[k];
+            g.r2n[nr + off + k - 1] = (uint16_t)x;
+            g.mark[x] = 2;
+        }
+        nr += total;
+        __syncwarp();
+        if (cut < 32 && i0 + cut < n) {
+            int ok = 1;
+            if (lane == 0 && (g.mark[i0 + cut] & 3) != 2) ok = dfs_from(g, caps, i0 + cut, nr) ? 1 : 0;
+            ok = __shfl_sync(kFull, ok, 0);
+            nr = __shfl_sync(kFull, nr, 0);
+            if (!ok) return false;
+            i0 += cut + 1;
+            __syncwarp();
+        } else {
+            i0 += 32;
+        }
     }
-    ok = __shfl_sync(kFull, ok, 0);
     __syncwarp();
-    if (!ok) return false;
     for (int r = lane; r < n; r += 32) g.n2r[g.r2n[r]] = (uint16_t)r;
     __syncwarp();
     return true;
+}
+
+// Per-rank row records for the DP and the traceback: predecessor rows in in-edge order (CSR),
+// letter code + sink flag, first predecessor row.
+__device__ __forceinline__ void build_rows(const Graph& g) {
+    const int lane = lane_id();
+    const int n = g.n_nodes;
+    int base = 0;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        const int r = r0 + lane;
+        int v = 0, deg = 0;
+        if (r < n) {
+            v = g.r2n[r];
+            deg = g.in_deg[v];
+            const int info = g.ninfo[v];
+            g.rcode[r] = (uint8_t)((info & 7) | ((info & 8) ? 0 : 8));   // bit 3 = sink (no out-edges)
+        }
+        int off = deg;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(kFull, off, d);
+            if (lane >= d) off += y;
+        }
+        const int total = __shfl_sync(kFull, off, 31);
+        off = base + off - deg;
+        if (r < n) {
+            g.pstart[r] = (uint16_t)off;
+            int k = off, first = 0;
+            for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+                const int prow = g.n2r[g.e_src[e]] + 1;
+                if (k == off) first = prow;
+                g.prows[k++] = (uint16_t)prow;
+            }
+            g.fp[r + 1] = (uint16_t)first;
+        }
+        base += total;
+    }
+    if (lane == 0) { g.pstart[n] = (uint16_t)base; g.fp[0] = 0; }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -525,9 +770,12 @@ __device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
 __device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
     const int n = g.n_nodes;
     const int node = g.r2n[rank];
-    for (int e = 0; e < g.n_edges; ++e) {
-        if (g.e_src[e] != node) continue;
-        for (int o = g.in_head[g.e_dst[e]]; o != kNone; o = g.e_next[o])
+    // for every successor d of node: invalidate the other sources of d's in-edges
+    for (int d = 0; d < n; ++d) {
+        bool succ = false;
+        for (int e = g.in_head[d]; e != kNone; e = g.e_next[e]) succ |= g.e_src[e] == node;
+        if (!succ) continue;
+        for (int o = g.in_head[d]; o != kNone; o = g.e_next[o])
             if (g.e_src[o] != node) g.score[g.e_src[o]] = -1;
     }
     int max_score = 0, max_id = 0;
@@ -553,6 +801,7 @@ __device__ __forceinline__ int heaviest_bundle(const Graph& g) {
     const int lane = lane_id();
     const int n = g.n_nodes;
     int len = 0;
+    __syncwarp();
     if (lane == 0) {
         int best = 0;
         for (int i = 0; i < n; ++i) g.score[i] = -1;
@@ -570,7 +819,7 @@ __device__ __forceinline__ int heaviest_bundle(const Graph& g) {
             if (g.score[best] < sv) best = v;
         }
         int guard = 0;
-        while (g.out_deg[best] != 0 && guard++ <= n) best = branch_completion(g, g.n2r[best]);
+        while ((g.ninfo[best] & 8) && guard++ <= n) best = branch_completion(g, g.n2r[best]);
         // backtrack (reversed in place afterwards)
         int k = 0;
         while (g.pred[best] != kNone && k < n) { g.cons[k++] = (uint16_t)best; best = g.pred[best]; }
@@ -590,7 +839,7 @@ __device__ __forceinline__ char code_to_char(int c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// One full POA round: add sequences [slot list] and leave the sorted graph in g.
+// One sequence: decode, align, fuse, re-sort.
 // ------------------------------------------------------------------------------------------
 struct SeqSrc {
     const uint8_t* bytes;   // packed source (nullptr => ASCII consensus in `ascii`)
@@ -602,8 +851,8 @@ struct SeqSrc {
 };
 
 template <bool kOneTile>
-__device__ __forceinline__ bool add_sequence(Graph& g, const Params& P, const Caps& caps, int16_t* H,
-                                             const SeqSrc& s, Scores sc, uint16_t* path) {
+__device__ __forceinline__ bool add_sequence(Graph& g, const Caps& caps, int16_t* H, const SeqSrc& s,
+                                             Scores sc, uint16_t* path) {
     const int lane = lane_id();
     const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
     if (len > caps.lcap) return false;
@@ -636,7 +885,9 @@ __device__ __forceinline__ bool add_sequence(Graph& g, const Params& P, const Ca
         span = traceback(g, H, cols, ec, s.type, sc, g.n_nodes + len + 4);
     }
     if (!add_to_graph(g, caps, len, span, path)) return false;
-    return topo_sort(g, caps);
+    if (!topo_sort(g, caps)) return false;
+    build_rows(g);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -661,30 +912,30 @@ __device__ __forceinline__ int run_short(Graph& g, const Params& P, const Caps& 
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
         s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
         s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
-        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
-        if (!add_sequence<kOneTile>(g, P, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const int nc = heaviest_bundle(g);
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
     const int n = nc >= 2 ? nc - 2 : 0;
-    for (int p = lane; p < n; p += 32) out[p] = code_to_char(g.letter[g.cons[p + 1]]);
+    for (int p = lane; p < n; p += 32) out[p] = code_to_char(g.ninfo[g.cons[p + 1]] & 7);
     return n;
 }
 
@@ -718,7 +969,7 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return false;
             if (lane == 0) pstart[g.n_seq] = used;
-            const bool ok = add_sequence<kOneTile>(g, P, caps, H, q, sc, pnodes + used);
+            const bool ok = add_sequence<kOneTile>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
             return ok;
         };
@@ -764,7 +1015,7 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
                 const int mv = msa[v];
                 while (c < nc && msa[g.cons[c]] < mv) ++c;
                 if (c >= nc) break;
-                if (msa[g.cons[c]] == mv && g.letter[v] == g.letter[g.cons[c]]) atomicAdd(&sup[c], 1u);
+                if (msa[g.cons[c]] == mv && (g.ninfo[v] & 7) == (g.ninfo[g.cons[c]] & 7)) atomicAdd(&sup[c], 1u);
             }
         }
         __syncwarp();
@@ -774,7 +1025,7 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
             const int c = c0 + lane;
             const bool keep = c < nc && sup[c] >= thres;
             const unsigned km = __ballot_sync(kFull, keep);
-            if (keep) out[kept + __popc(km & ((1u << lane) - 1u))] = code_to_char(g.letter[g.cons[c]]);
+            if (keep) out[kept + __popc(km & ((1u << lane) - 1u))] = code_to_char(g.ninfo[g.cons[c]] & 7);
             kept += __popc(km);
         }
         n_cons = kept;

@@ -13,8 +13,8 @@
 // with the per-column support counts + curation (:533-568, src/Window.cpp:239-254).
 //
 // Data placement:
-//   * the growing DAG (SoA, 16-bit indices) lives in shared memory (tier S) or in a
-//     global workspace (tier L, for windows that overflow the shared-memory capacities);
+//   * the growing DAG (SoA, 16-bit indices) lives in shared memory (tiers S) or in a
+//     global workspace (tiers L, for windows that overflow the shared-memory capacities);
 //   * the DP matrix lives in global memory and is sized to stay L2-resident; every warp
 //     keeps the previous row in registers so the common pred == previous-rank case never
 //     touches memory; rows are written once, coalesced, 8 bytes per lane;
@@ -50,6 +50,7 @@ constexpr int kAlSlots = 6;                  // clique <= 7 letters (J O A C G T
 constexpr int kNumCodes = 7;                 // A C G T N J O
 constexpr int kCodeJ = 5, kCodeO = 6;
 constexpr int kMaxH16 = 29000;               // int16 safety bound for |H^|
+constexpr int kBulkList = 10;                // per-lane emission list of the bulk topological sort
 
 enum AlignType { kNW = 0, kLOV = 1, kROV = 2 };
 
@@ -76,7 +77,7 @@ struct Params {
     uint32_t* overflow;          // [0] = count, [1..] = window ids that exceeded this tier
     int16_t* H;                  // DP workspace, one slot per warp
     uint64_t h_slot;             // elements per slot
-    uint8_t* gws;                // tier L: graph workspace, one slot per warp
+    uint8_t* gws;                // tiers L: graph workspace, one slot per warp
     uint64_t g_slot;             // bytes per slot
     uint16_t* paths;             // LONG: per-warp node paths, one slot per warp
     uint64_t p_slot;             // elements per slot
@@ -84,43 +85,76 @@ struct Params {
     int sr_m, sr_n, sr_g, lr_m, lr_n, lr_g;
 };
 
-// Bytes of graph arena one warp needs for the given capacities.
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
+// Per-warp graph arena.  Node arrays are indexed by node id, row arrays by rank (+1 = DP row).
 struct ArenaLayout {
-    uint32_t letter, in_head, in_tail, out_deg, al_blk, al_cnt, mark, n2r, r2n;
-    uint32_t e_src, e_dst, e_w, e_next, al_pool, stack, seq, cur, prof, total;
-    // epilogue scratch, aliased over [stack, seq, cur, prof] which are dead by then
-    uint32_t score, pred, cons;
+    // nodes
+    uint32_t ninfo;     // u8  letter code (bits 0-2) | has-out-edge (bit 3)
+    uint32_t al_cnt;    // u8  number of aligned nodes
+    uint32_t in_deg;    // u8  in-degree (saturating; 255 => tier overflow)
+    uint32_t in_head;   // u16 first in-edge (insertion order)
+    uint32_t al_blk;    // u16 block of al_pool holding aligned_nodes_ids_
+    uint32_t n2r;       // u16 node -> rank (claim scratch while sorting)
+    uint32_t r2n;       // u16 rank -> node
+    // edges
+    uint32_t e_src, e_w, e_next;   // u16 each
+    uint32_t al_pool;   // u16 [acap][kAlSlots]
+    // rows (rebuilt after every topological sort)
+    uint32_t pstart;    // u16 [ncap+2] CSR offsets into prows, by rank
+    uint32_t rcode;     // u8  [ncap+1] letter code | sink (bit 3), by rank
+    uint32_t prows;     // u16 [ecap] predecessor DP rows in in-edge order
+    uint32_t fp;        // u16 [ncap+1] first predecessor row of each DP row (0 = virtual row 0)
+    // scratch group (phases are disjoint in time)
+    uint32_t stack;     // u16 [scap]   DFS stack
+    uint32_t seq;       // u8  [lcap+1] current sequence (letter codes)
+    uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
+    uint32_t prof;      // i16 [7][tiles*128] query profile
+    uint32_t mark;      // u8  [ncap]   sort marks          (aliases prof)
+    uint32_t lists;     // u16 [32][kBulkList] bulk lists   (aliases prof)
+    uint32_t score;     // i32 [ncap]   epilogue           (aliases the scratch group)
+    uint32_t pred;      // u16 [ncap]
+    uint32_t cons;      // u16 [ncap]
+    uint32_t total;
 };
 
 __host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
     ArenaLayout L;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) { uint32_t r = o; o = align16(o + bytes); return r; };
-    L.letter = take(c.ncap);
-    L.in_head = take(2u * c.ncap);
-    L.in_tail = take(2u * c.ncap);
-    L.out_deg = take(2u * c.ncap);
-    L.al_blk = take(2u * c.ncap);
+    L.ninfo = take(c.ncap);
     L.al_cnt = take(c.ncap);
-    L.mark = take(c.ncap);
+    L.in_deg = take(c.ncap);
+    L.in_head = take(2u * c.ncap);
+    L.al_blk = take(2u * c.ncap);
     L.n2r = take(2u * c.ncap);
     L.r2n = take(2u * c.ncap);
     L.e_src = take(2u * c.ecap);
-    L.e_dst = take(2u * c.ecap);
     L.e_w = take(2u * c.ecap);
     L.e_next = take(2u * c.ecap);
     L.al_pool = take(2u * kAlSlots * c.acap);
+    L.pstart = take(2u * (c.ncap + 2));
+    L.rcode = take(c.ncap + 1);
+    L.prows = take(2u * c.ecap);
+    L.fp = take(2u * (c.ncap + 1));
+    const uint32_t scratch0 = o;
     L.stack = take(2u * c.scap);
     L.seq = take(c.lcap + 1);
     L.cur = take(2u * (c.lcap + 1));
     L.prof = take(2u * kNumCodes * c.tiles * kTileCols);
-    L.score = L.stack;
+    uint32_t end = o;
+    // toposort scratch over the (dead) profile
+    L.mark = L.prof;
+    L.lists = L.prof + align16(c.ncap);
+    uint32_t e2 = L.lists + 2u * 32 * kBulkList;
+    if (e2 > end) end = e2;
+    // epilogue scratch over the whole group
+    L.score = scratch0;
     L.pred = L.score + align16(4u * c.ncap);
     L.cons = L.pred + align16(2u * c.ncap);
-    uint32_t end = L.cons + align16(2u * c.ncap);
-    L.total = o > end ? o : end;
+    uint32_t e3 = L.cons + align16(2u * c.ncap);
+    if (e3 > end) end = e3;
+    L.total = align16(end);
     return L;
 }
 

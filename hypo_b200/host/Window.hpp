@@ -1,0 +1,125 @@
+// Window.hpp — host-side drop-in for hypo::Window on the POA path.
+//
+// Same public interface as the reference class (reference include/Window.hpp:41-146): a
+// window is filled with add_internal/add_prefix/add_suffix/add_empty exactly as
+// Contig::fill_short_windows / fill_long_windows do, `prepare_for_poa` fixes the score
+// parameters, `generate_consensus` produces `_consensus`.  What changes is WHERE the
+// consensus is computed: instead of one spoa graph per OpenMP thread, windows are flattened
+// into one batch (WindowBatch.hpp) and sent through the C ABI (include/hypo_b200.h) to the
+// B200.  `generate_consensus(engine_idx)` is kept for source compatibility and runs a batch
+// of one; the intended call is Window::generate_consensus_batch (see INTEGRATION.md for the
+// 12-line replacement of reference src/Hypo.cpp:236-248).
+#pragma once
+#include <functional>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "PackedSeq.hpp"
+
+namespace hypo {
+
+// reference include/globalDefs.hpp:58-66
+struct ScoreParams {
+    INT8 sr_match_score;
+    INT8 sr_misMatch_score;
+    INT8 sr_gap_penalty;
+    INT8 lr_match_score;
+    INT8 lr_misMatch_score;
+    INT8 lr_gap_penalty;
+};
+
+enum class WindowType : UINT8 { SHORT, LONG };
+
+class WindowBatch;
+
+class Window {
+public:
+    Window() : _wtype(WindowType::SHORT), _num_internal(0), _num_pre(0), _num_suf(0), _num_empty(0),
+               _longest_pre_len(0), _longest_suf_len(0) {}
+    Window(const PackedSeq<4>& ps, const size_t left_ind, const size_t right_ind, WindowType wt)
+        : _wtype(wt), _num_internal(0), _num_pre(0), _num_suf(0), _num_empty(0), _longest_pre_len(0),
+          _longest_suf_len(0), _draft(ps, left_ind, right_ind) {}
+
+    Window(const Window&) = delete;
+    Window& operator=(const Window&) = delete;
+    Window(Window&&) = delete;
+    Window& operator=(Window&&) = delete;
+    ~Window() = default;
+
+    // reference src/Window.cpp:31-42.  num_threads is accepted for source compatibility; the
+    // device replaces the per-thread engines.  `device` selects the CUDA ordinal.
+    static void prepare_for_poa(const ScoreParams& sp, const UINT32 num_threads, int device = 0);
+    // reference src/Window.cpp:44-61 (a batch of one; prefer generate_consensus_batch)
+    void generate_consensus(const UINT32 engine_idx);
+    // Replaces the OpenMP loop of reference src/Hypo.cpp:238-247 for a set of windows.
+    static void generate_consensus_batch(const std::vector<Window*>& windows);
+
+    std::string get_consensus() const { return _consensus; }
+    size_t get_window_len() const { return _draft.get_seq_size(); }
+
+    // LONG windows run every arm through hypo::Filter::is_good at insert time in the
+    // reference (include/Window.hpp:66-101).  The minimiser filter is upstream of the hot
+    // path and stays the maintainers' code; plug it in here (default: accept every arm).
+    using ArmFilter = std::function<bool(const Window&, const PackedSeq<2>&)>;
+    static void set_long_arm_filter(ArmFilter f) { _long_filter = std::move(f); }
+
+    void add_prefix(const PackedSeq<2>& ps) {
+        if (!accept(ps)) return;
+        UINT arm_len = (UINT)ps.get_seq_size();
+        ++_num_pre;
+        if (arm_len > _longest_pre_len) _longest_pre_len = arm_len;
+        _pre_arms.emplace_back(ps);
+    }
+    void add_suffix(const PackedSeq<2>& ps) {
+        if (!accept(ps)) return;
+        UINT arm_len = (UINT)ps.get_seq_size();
+        ++_num_suf;
+        if (arm_len > _longest_suf_len) _longest_suf_len = arm_len;
+        _suf_arms.emplace_back(ps);
+    }
+    void add_internal(const PackedSeq<2>& ps) {
+        if (!accept(ps)) return;
+        ++_num_internal;
+        _internal_arms.emplace_back(ps);
+    }
+    void add_empty() { ++_num_empty; }
+
+    UINT32 get_num_pre() const { return _num_pre; }
+    UINT32 get_num_suf() const { return _num_suf; }
+    UINT32 get_num_internal() const { return _num_internal + _num_empty; }
+    UINT32 get_num_total() const { return _num_internal + _num_empty + _num_pre + _num_suf; }
+    UINT32 get_maxlen_pre() const { return _longest_pre_len; }
+    UINT32 get_maxlen_suf() const { return _longest_suf_len; }
+    void clear_pre_suf() {
+        _num_pre = 0;
+        _num_suf = 0;
+        _pre_arms.clear();
+        _suf_arms.clear();
+        _pre_arms.shrink_to_fit();
+        _suf_arms.shrink_to_fit();
+    }
+    WindowType get_type() const { return _wtype; }
+    const PackedSeq<4>& draft() const { return _draft; }
+
+    friend std::ostream& operator<<(std::ostream&, const Window&);
+    friend class WindowBatch;
+
+private:
+    bool accept(const PackedSeq<2>& ps) const {
+        return _wtype != WindowType::LONG || !_long_filter || _long_filter(*this, ps);
+    }
+    void set_consensus(std::string con) { _consensus = std::move(con); }
+
+    WindowType _wtype;
+    UINT32 _num_internal, _num_pre, _num_suf, _num_empty;
+    UINT32 _longest_pre_len, _longest_suf_len;
+    PackedSeq<4> _draft;
+    std::vector<PackedSeq<2>> _internal_arms;
+    std::vector<PackedSeq<2>> _pre_arms;
+    std::vector<PackedSeq<2>> _suf_arms;
+    std::string _consensus;
+    static ArmFilter _long_filter;
+};
+
+}  // namespace hypo

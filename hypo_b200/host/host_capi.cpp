@@ -1,0 +1,188 @@
+// host_capi.cpp — C entry points of libhypo_host.so used by bench.py and the tests:
+//   * hypo_synth_*      seeded synthetic window generator (BASELINE.md §3 / SURVEY.md §8d shapes)
+//   * hypo_host_run     drives the hypo::Window mirror through its PUBLIC API (add_* /
+//                       prepare_for_poa / generate_consensus_batch / get_consensus) from a flat
+//                       batch, the way oracle/ref_driver.cpp drives the reference's Window.
+#include <omp.h>
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hypo_b200.h"
+#include "Window.hpp"
+#include "WindowBatch.hpp"
+
+namespace {
+
+struct Rng {   // splitmix64
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed) {}
+    uint64_t next() {
+        uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    }
+    double uni() { return (next() >> 11) * (1.0 / 9007199254740992.0); }
+    uint32_t below(uint32_t n) { return (uint32_t)(next() % n); }
+};
+
+// truth -> noisy copy: per base delete / substitute / keep, then maybe insert a random base
+void mutate(Rng& r, const uint8_t* src, uint32_t n, double sub, double ins, double del, std::vector<uint8_t>& dst) {
+    dst.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        const double u = r.uni();
+        if (u >= del) dst.push_back(u < del + sub ? (uint8_t)((src[i] + 1 + r.below(3)) & 3) : src[i]);
+        if (r.uni() < ins) dst.push_back((uint8_t)r.below(4));
+    }
+}
+
+struct GenCfg {
+    uint64_t seed;
+    uint32_t len, n_arms;
+    int kind;   // 0 internal, 1 backbone, 2 prefix-heavy, 3 suffix-heavy, 4 mixed
+    double err, draft_err;
+    uint32_t wtype;
+};
+
+int arm_kind(const GenCfg& c, uint32_t r) {   // 0 internal, 1 prefix, 2 suffix
+    switch (c.kind) {
+        case 0: return 0;
+        case 1: return r < c.n_arms / 2 ? 1 : 2;
+        case 2: return r < 3 ? 0 : 1;
+        case 3: return r < 3 ? 0 : 2;
+        default: { static const int k[5] = {0, 0, 0, 1, 2}; return k[r % 5]; }
+    }
+}
+
+// Generates window w; calls sink(kind, codes, n) for the draft (kind -1) and every arm in
+// generation order.  Deterministic in (seed, w) so the two passes agree and the result is
+// independent of the thread count.
+template <class Sink>
+void gen_window(const GenCfg& c, uint64_t w, Sink&& sink) {
+    Rng r(c.seed * 0x9e3779b97f4a7c15ull + w * 0xd1342543de82ef95ull + 1);
+    std::vector<uint8_t> truth(c.len), buf;
+    for (auto& b : truth) b = (uint8_t)r.below(4);
+    mutate(r, truth.data(), c.len, c.draft_err, c.draft_err, c.draft_err, buf);
+    if (buf.empty()) buf.push_back(0);
+    sink(-1, buf.data(), (uint32_t)buf.size());
+    for (uint32_t a = 0; a < c.n_arms; ++a) {
+        const int k = arm_kind(c, a);
+        if (k == 0) {
+            mutate(r, truth.data(), c.len, c.err, c.err, c.err, buf);
+        } else {
+            const uint32_t lo = c.len / 2 > 0 ? c.len / 2 : 1;
+            const uint32_t cut = c.len > 1 ? lo + r.below(c.len - lo) : 1;
+            if (k == 1) mutate(r, truth.data(), cut, c.err, c.err, c.err, buf);
+            else mutate(r, truth.data() + (c.len - cut), cut, c.err, c.err, c.err, buf);
+        }
+        sink(k, buf.data(), (uint32_t)buf.size());
+    }
+}
+
+std::string unpack2(const uint8_t* p, uint32_t len) {
+    std::string s(len, 'A');
+    for (uint32_t i = 0; i < len; ++i) s[i] = "ACGT"[(p[i >> 2] >> (6 - 2 * (i & 3))) & 3];
+    return s;
+}
+std::string unpack4(const uint8_t* p, uint32_t len) {
+    std::string s(len, 'A');
+    for (uint32_t i = 0; i < len; ++i) { int v = (p[i >> 1] >> ((i & 1) ? 0 : 4)) & 15; s[i] = "ACGTN"[v > 4 ? 4 : v]; }
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Worst-case packed bytes for the configuration (every base followed by an insertion).
+uint64_t hypo_synth_packed_bound(uint64_t n_win, uint32_t len, uint32_t n_arms) {
+    return n_win * ((uint64_t)(2 * len + 2) / 2 + 1 + (uint64_t)n_arms * ((2 * len + 2) / 4 + 1)) + 64;
+}
+
+// Fills win[n_win], arms[n_win*n_arms] (container order: internal, prefix, suffix) and the
+// packed slab.  Returns 0, or 1 if packed_cap is too small.
+int hypo_synth_generate(uint64_t seed, uint64_t n_win, uint32_t len, uint32_t n_arms, int kind, double err,
+                        double draft_err, uint32_t wtype, HypoWindowDesc* win, HypoArmDesc* arms, uint8_t* packed,
+                        uint64_t packed_cap, uint64_t* packed_used, int n_threads) {
+    GenCfg c{seed, len, n_arms, kind, err, draft_err, wtype};
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    std::vector<uint64_t> bytes(n_win + 1, 0);
+    // pass 1: sizes
+#pragma omp parallel for schedule(static, 256) num_threads(n_threads)
+    for (uint64_t w = 0; w < n_win; ++w) {
+        uint64_t b = 0;
+        gen_window(c, w, [&](int k, const uint8_t*, uint32_t n) { b += k < 0 ? (n + 1) / 2 : (n + 3) / 4; });
+        bytes[w + 1] = b;
+    }
+    for (uint64_t w = 0; w < n_win; ++w) bytes[w + 1] += bytes[w];
+    *packed_used = bytes[n_win];
+    if (bytes[n_win] > packed_cap) return 1;
+    // pass 2: fill
+#pragma omp parallel for schedule(static, 256) num_threads(n_threads)
+    for (uint64_t w = 0; w < n_win; ++w) {
+        uint64_t pos = bytes[w];
+        HypoWindowDesc& d = win[w];
+        memset(&d, 0, sizeof(d));
+        d.first_arm = w * n_arms;
+        d.wtype = wtype;
+        uint32_t cnt[3] = {0, 0, 0};
+        for (uint32_t a = 0; a < n_arms; ++a) cnt[arm_kind(c, a)]++;
+        d.n_internal = cnt[0]; d.n_pre = cnt[1]; d.n_suf = cnt[2];
+        uint32_t slot[3] = {0, cnt[0], cnt[0] + cnt[1]};
+        gen_window(c, w, [&](int k, const uint8_t* s, uint32_t n) {
+            if (k < 0) {
+                d.draft_off = pos; d.draft_len = n;
+                const uint64_t nb = (n + 1) / 2;
+                memset(packed + pos, 0, nb);
+                for (uint32_t i = 0; i < n; ++i) packed[pos + (i >> 1)] |= (uint8_t)(s[i] << ((i & 1) ? 0 : 4));
+                pos += nb;
+            } else {
+                HypoArmDesc& ad = arms[w * n_arms + slot[k]++];
+                ad.off = pos; ad.len = n; ad.reserved = 0;
+                const uint64_t nb = (n + 3) / 4;
+                memset(packed + pos, 0, nb);
+                for (uint32_t i = 0; i < n; ++i) packed[pos + (i >> 2)] |= (uint8_t)(s[i] << (6 - 2 * (i & 3)));
+                pos += nb;
+            }
+        });
+    }
+    return 0;
+}
+
+// Drives the Window mirror through its public API.  Mirrors hypo_ref_consensus_batch.
+int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win, uint64_t n_win,
+                  const HypoArmDesc* arms, const uint8_t* packed, char* out, uint64_t out_cap, uint64_t* out_off) {
+    using namespace hypo;
+    ScoreParams sp{scores[0], scores[1], scores[2], scores[3], scores[4], scores[5]};
+    Window::prepare_for_poa(sp, 1, device);
+    std::vector<std::unique_ptr<Window>> ws(n_win);
+    std::vector<Window*> ptrs(n_win);
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        ws[w].reset(new Window(draft, 0, d.draft_len, d.wtype == HYPO_WINDOW_LONG ? WindowType::LONG : WindowType::SHORT));
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) ws[w]->add_internal(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) ws[w]->add_prefix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) ws[w]->add_suffix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_empty; ++i) ws[w]->add_empty();
+        ptrs[w] = ws[w].get();
+    }
+    Window::generate_consensus_batch(ptrs);
+    uint64_t pos = 0;
+    for (uint64_t w = 0; w < n_win; ++w) {
+        out_off[w] = pos;
+        const std::string c = ws[w]->get_consensus();
+        if (pos + c.size() > out_cap) return HYPO_E_OUT_CAP;
+        memcpy(out + pos, c.data(), c.size());
+        pos += c.size();
+    }
+    out_off[n_win] = pos;
+    return HYPO_OK;
+}
+
+}  // extern "C"

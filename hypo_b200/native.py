@@ -20,6 +20,8 @@ ABI_SYMBOLS = (
     "hypo_gpu_out_bound",
     "hypo_gpu_consensus_batch",
     "hypo_gpu_consensus_batch_device",
+    "hypo_gpu_compact_device",
+    "hypo_gpu_last_timing",
     "hypo_gpu_launch_count",
     "hypo_gpu_last_error",
     "hypo_gpu_shutdown",
@@ -61,6 +63,11 @@ def lib():
         L.hypo_gpu_consensus_batch_device.argtypes = [
             C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hypo_gpu_compact_device.restype = C.c_int
+        L.hypo_gpu_compact_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                              C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+        L.hypo_gpu_last_timing.restype = C.c_int
+        L.hypo_gpu_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.hypo_gpu_launch_count.restype = C.c_uint64
         L.hypo_gpu_last_error.restype = C.c_char_p
         L.hypo_gpu_shutdown.restype = None
@@ -114,3 +121,21 @@ def consensus_batch_device(d_win: int, n_win: int, d_arms: int, n_arms: int, d_p
     """hypo_gpu_consensus_batch_device on raw device pointers (e.g. torch tensors' data_ptr())."""
     _check(lib().hypo_gpu_consensus_batch_device(d_win, n_win, d_arms, n_arms, d_packed, packed_bytes,
                                                  d_out, d_out_pos, d_out_len, stream))
+
+
+def compact_device(d_scratch: int, d_out_pos: int, d_out_len: int, n_win: int, d_compact: int,
+                   compact_cap: int, d_off: int, stream: int = 0) -> int:
+    """hypo_gpu_compact_device; returns the total number of consensus bytes."""
+    total = C.c_uint64(0)
+    _check(lib().hypo_gpu_compact_device(d_scratch, d_out_pos, d_out_len, n_win, d_compact, compact_cap,
+                                         d_off, C.byref(total), stream))
+    return int(total.value)
+
+
+def last_timing() -> Tuple[float, int, List[int]]:
+    """(POA-kernel device ms, POA launches, windows per tier) of the last batch call."""
+    ms = C.c_float(0)
+    n = C.c_uint32(0)
+    tiers = (C.c_uint32 * 4)()
+    lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
+    return float(ms.value), int(n.value), [int(x) for x in tiers]

@@ -134,6 +134,22 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
                                     char* d_out, const uint64_t* d_out_pos,
                                     uint32_t* d_out_len, void* stream);
 
+/*
+ * Packs the per-window results of hypo_gpu_consensus_batch_device into one contiguous,
+ * window-ordered byte string on the device (what the final consensus gather ships):
+ *   d_off[w]  = start of window w inside d_compact (n_win+1 entries, device)
+ *   *total    = total bytes (host); fails with HYPO_E_OUT_CAP if > compact_cap.
+ */
+int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, const uint32_t* d_out_len,
+                            uint64_t n_win, char* d_compact, uint64_t compact_cap, uint64_t* d_off,
+                            uint64_t* total, void* stream);
+
+/*
+ * Measurement hook: device time (CUDA events on the launching stream) and launch count of the
+ * POA kernels of the most recent batch call, and how many windows each capacity tier ran.
+ */
+int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[4]);
+
 /* Number of kernel launches issued by this library since hypo_gpu_init. */
 uint64_t hypo_gpu_launch_count(void);
 
