@@ -39,7 +39,23 @@ struct Graph {
     int n_nodes, n_edges, n_al, n_seq;
 };
 
-__device__ __forceinline__ Graph make_graph(uint8_t* base, const ArenaLayout& L) {
+// What persists per warp between the phases (kept in local memory; the phases are separate
+// functions so that each gets its own register allocation and the code stays small): where the
+// arena is, its layout, and the element counts.  Every phase rebuilds its typed view with
+// make_graph<kSmem>, which lets the compiler see that shared-memory tiers address __shared__
+// (LDS/STS with 32-bit addresses) instead of falling back to generic loads.
+struct GState {
+    uint8_t* gbase;      // tiers L: this warp's arena in global memory
+    uint32_t sbase;      // tiers S: byte offset of this warp's arena in dynamic shared memory
+    ArenaLayout L;
+    int n_nodes, n_edges, n_al, n_seq;
+};
+
+template <bool kSmem>
+__device__ __forceinline__ Graph make_graph(const GState& st) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* base = kSmem ? (smem + st.sbase) : st.gbase;
+    const ArenaLayout& L = st.L;
     Graph g;
     g.ninfo = base + L.ninfo;
     g.al_cnt = base + L.al_cnt;
@@ -65,7 +81,7 @@ __device__ __forceinline__ Graph make_graph(uint8_t* base, const ArenaLayout& L)
     g.score = (int32_t*)(base + L.score);
     g.pred = (uint16_t*)(base + L.pred);
     g.cons = (uint16_t*)(base + L.cons);
-    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+    g.n_nodes = st.n_nodes; g.n_edges = st.n_edges; g.n_al = st.n_al; g.n_seq = st.n_seq;
     return g;
 }
 
@@ -156,9 +172,10 @@ struct EndCell {
     int col;
 };
 
-template <bool kOneTile>
-__device__ __forceinline__ EndCell dp_fill(const Graph& g, int16_t* __restrict__ H, int len, int tiles,
-                                           int type, Scores sc) {
+template <bool kSmem, bool kOneTile>
+__device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ H, int len, int tiles,
+                                        int type, Scores sc) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int cols = kOneTile ? kTileCols : tiles * kTileCols;
     const uint32_t g2 = bcast16(sc.g);
@@ -196,6 +213,7 @@ __device__ __forceinline__ EndCell dp_fill(const Graph& g, int16_t* __restrict__
                 const uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
                 relax(x, p, left, pf, g2);
             } else {
+#pragma unroll 1
                 for (int k = ps; k < pe; ++k) {
                     const unsigned prow = g.prows[k];
                     uint32_t p[kNR];
@@ -261,8 +279,10 @@ struct AlnSpan {
     int first, last;
 };
 
-__device__ __forceinline__ AlnSpan traceback(const Graph& g, const int16_t* __restrict__ H, int cols,
-                                             EndCell ec, int type, Scores sc, int max_steps) {
+template <bool kSmem>
+__device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __restrict__ H, int cols,
+                                          EndCell ec, int type, Scores sc, int max_steps) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     int i = ec.row, j = ec.col;
     AlnSpan span;
@@ -274,14 +294,19 @@ __device__ __forceinline__ AlnSpan traceback(const Graph& g, const int16_t* __re
     while ((type == kROV ? (i != 0 && j != 0) : (i != 0 || j != 0)) && steps++ < max_steps) {
         if (i != 0 && j != 0) {
             // ---- speculative diagonal run through first predecessors
-            int my_r = 0, my_rn = 0;
-            int r = i;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const int rn = r != 0 ? (int)g.fp[r] : 0;
-                if (lane == k) { my_r = r; my_rn = rn; }
-                r = rn;
+            // chain[k] = row of step k (chain[0] = i); fp[0] = 0 keeps the walk total
+            uint16_t* chain = g.stack;
+            {
+                int r = i;
+                if (lane == 0) chain[0] = (uint16_t)r;
+#pragma unroll 4
+                for (int k = 1; k <= 32; ++k) {
+                    r = g.fp[r];
+                    if (lane == 0) chain[k] = (uint16_t)r;
+                }
             }
+            __syncwarp();
+            const int my_r = chain[lane], my_rn = chain[lane + 1];
             const int jj = j - lane;
             bool ok = my_r != 0 && jj >= 1;
             int hp = 0;
@@ -365,8 +390,10 @@ __device__ __forceinline__ void init_node(const Graph& g, int id, int code) {
     g.al_blk[id] = kNone;
 }
 
-__device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len, AlnSpan span,
-                                             uint16_t* path) {
+template <bool kSmem>
+__device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len, AlnSpan span,
+                                          uint16_t* path) {
+    Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     int first = span.first, last = span.last;
@@ -495,8 +522,10 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
         }
         n_edges += __popc(em);
     }
-    g.n_edges = n_edges;
-    g.n_seq += 1;
+    st.n_nodes = n_nodes;
+    st.n_al = n_al;
+    st.n_edges = n_edges;
+    st.n_seq = g.n_seq + 1;
     __syncwarp();
     return true;
 }
@@ -508,7 +537,7 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
 // The DFS's outer loop visits node ids in ascending order.  The warp processes 32 consecutive ids
 // per round: lane l replays, on its own, what the DFS would do when its outer loop reaches node
 // i0+l — assuming the lanes below it have already emitted — with a bounded recursion
-// (bulk_visit) that follows the reference's exploration order: aligned nodes last-to-first (only
+// (bulk_eval) that follows the reference's exploration order: aligned nodes last-to-first (only
 // their sources: their check_aligned flag is cleared), then the node's own not-yet-emitted
 // sources last-to-first, then the node followed by its aligned nodes.  Nodes a lane would emit
 // besides its own ("extras") are announced in a claim table; a lane may rely on extras announced
@@ -522,10 +551,9 @@ __device__ __forceinline__ bool add_to_graph(Graph& g, const Caps& caps, int len
 // aligned nodes" (check_aligned_nodes[id] == false).
 // ------------------------------------------------------------------------------------------
 constexpr int kBulkDepth = 4;
-constexpr int kBulkMaxExtra = kBulkList - 2;   // list[0] = count, then <= 1 + kBulkMaxExtra nodes
+constexpr int kBulkMaxNodes = kBulkList - 1;   // list[0] = count, then up to kBulkList-1 nodes
 
-struct BulkCtx {
-    // raw views (a copy, so that the warp's Graph itself can stay in registers)
+struct SortCtx {
     const uint8_t* mark;
     const uint8_t* al_cnt;
     const uint16_t* claim;
@@ -539,12 +567,14 @@ struct BulkCtx {
     bool use_claims;
 };
 
-__device__ __forceinline__ bool bulk_ok(const BulkCtx& c, int s) {
+// "emitted by the time it is needed": permanently marked, a lower lane of this round, announced by
+// a lower lane of this round (later passes), or already in this lane's own emission list.
+__device__ __forceinline__ bool s_ok(const SortCtx& c, int s) {
     if ((c.mark[s] & 3) == 2) return true;
-    if (s >= c.i0 && s < c.id) return true;                 // a lower lane of this round
+    if (s >= c.i0 && s < c.id) return true;
     if (c.use_claims) {
         const int cl = c.claim[s];
-        if ((cl >> 5) == c.round && (cl & 31) < c.lane) return true;   // announced by a lower lane
+        if ((cl >> 5) == c.round && (cl & 31) < c.lane) return true;
     }
     const int n = c.list[0];
     for (int k = 1; k <= n; ++k)
@@ -552,37 +582,83 @@ __device__ __forceinline__ bool bulk_ok(const BulkCtx& c, int s) {
     return false;
 }
 
-__device__ bool bulk_visit(const BulkCtx& c, int p, int depth);
-
-__device__ __noinline__ bool bulk_sources(const BulkCtx& c, int v, int depth) {
-    int und[3], n_und = 0;
-    for (int e = c.in_head[v]; e != kNone; e = c.e_next[e]) {
-        const int s = c.e_src[e];
-        if (bulk_ok(c, s)) continue;
-        if (n_und == 3) return false;
-        und[n_und++] = s;
-    }
-    for (int u = n_und - 1; u >= 0; --u)
-        if (!bulk_ok(c, und[u]) && !bulk_visit(c, und[u], depth + 1)) return false;
+__device__ __forceinline__ bool s_push(const SortCtx& c, int x) {
+    const int n = c.list[0];
+    if (n >= kBulkMaxNodes) return false;
+    c.list[n + 1] = (uint16_t)x;
+    c.list[0] = (uint16_t)(n + 1);
     return true;
 }
 
-__device__ __noinline__ bool bulk_visit(const BulkCtx& c, int p, int depth) {
-    if (depth > kBulkDepth || c.mark[p] != 0) return false;
-    const int nm = c.al_cnt[p];
-    const int blk = c.al_blk[p];
-    for (int k = nm - 1; k >= 0; --k) {
-        const int a = c.al_pool[blk * kAlSlots + k];
-        if (c.mark[a] != 0 || bulk_ok(c, a)) return false;
-        if (!bulk_sources(c, a, depth)) return false;
+// unit(u): u fresh; its aligned nodes fresh with all sources emitted; at most one not-yet-emitted
+// source per level, forming a chain of <= kBulkDepth fresh nodes without aligned nodes.
+// Emits chain (deepest first), u, aligned(u).
+__device__ __noinline__ bool s_unit(const SortCtx& c, int u) {
+    if (c.mark[u] != 0) return false;
+    const int mu = c.al_cnt[u];
+    const int ublk = c.al_blk[u];
+    for (int k = 0; k < mu; ++k) {
+        const int b = c.al_pool[ublk * kAlSlots + k];
+        if (c.mark[b] != 0 || s_ok(c, b)) return false;
+        for (int e = c.in_head[b]; e != kNone; e = c.e_next[e])
+            if (!s_ok(c, c.e_src[e])) return false;
     }
-    if (!bulk_sources(c, p, depth)) return false;
-    int n = c.list[0];
-    if (n + 1 + nm > 1 + kBulkMaxExtra) return false;
-    c.list[++n] = (uint16_t)p;
-    for (int k = 0; k < nm; ++k) c.list[++n] = c.al_pool[blk * kAlSlots + k];
-    c.list[0] = (uint16_t)n;
+    int chain[kBulkDepth];
+    int nc = 0, w = u;
+    for (;;) {
+        int next = -1;
+        for (int e = c.in_head[w]; e != kNone; e = c.e_next[e]) {
+            const int s = c.e_src[e];
+            if (s_ok(c, s)) continue;
+            if (next != -1) return false;
+            next = s;
+        }
+        if (next == -1) break;
+        if (nc == kBulkDepth || c.mark[next] != 0 || c.al_cnt[next] > 0) return false;
+#pragma unroll
+        for (int q = 0; q < kBulkDepth; ++q) if (q == nc) chain[q] = next;
+        ++nc;
+        w = next;
+    }
+#pragma unroll
+    for (int q = kBulkDepth - 1; q >= 0; --q)
+        if (q < nc && !s_push(c, chain[q])) return false;
+    if (!s_push(c, u)) return false;
+    for (int k = 0; k < mu; ++k)
+        if (!s_push(c, c.al_pool[ublk * kAlSlots + k])) return false;
     return true;
+}
+
+// Replay of what the DFS does when its outer loop reaches node c.id.  Returns 1 (emit c.list) or
+// 2 (cannot decide within the bounds).  Same code shape as bulk_eval in oracle/poa_oracle.c.
+__device__ __forceinline__ int bulk_eval(const SortCtx& c) {
+    const int id = c.id;
+    c.list[0] = 0;
+    if (c.mark[id] != 0) return 2;
+    const int nm = c.al_cnt[id];
+    const int blk = c.al_blk[id];
+    // targets: aligned nodes last-to-first (only their sources are explored), then the node itself
+    for (int t = nm - 1; t >= -1; --t) {
+        const int x = t >= 0 ? (int)c.al_pool[blk * kAlSlots + t] : id;
+        if (t >= 0 && (c.mark[x] != 0 || s_ok(c, x))) return 2;
+        int und[3];
+        int n_und = 0;
+        for (int e = c.in_head[x]; e != kNone; e = c.e_next[e]) {
+            const int s = c.e_src[e];
+            if (s_ok(c, s)) continue;
+            if (n_und == 3) return 2;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q == n_und) und[q] = s;
+            ++n_und;
+        }
+#pragma unroll
+        for (int q = 2; q >= 0; --q)
+            if (q < n_und && !s_ok(c, und[q]) && !s_unit(c, und[q])) return 2;
+    }
+    if (!s_push(c, id)) return 2;
+    for (int k = 0; k < nm; ++k)
+        if (!s_push(c, c.al_pool[blk * kAlSlots + k])) return 2;
+    return 1;
 }
 
 // Serial DFS from one root (lane 0), verbatim the reference's inner loop.
@@ -632,7 +708,9 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
     return true;
 }
 
-__device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
+template <bool kSmem>
+__device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
@@ -649,16 +727,15 @@ __device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
         const int id = i0 + lane;
         // status: 0 nothing to emit, 1 emit list, 2 undecided/failed, 3 superseded
         int status = (id < n && (g.mark[id] & 3) != 2) ? 2 : 0;
-        BulkCtx c;
+        SortCtx c;
         c.mark = g.mark; c.al_cnt = g.al_cnt; c.claim = claim; c.in_head = g.in_head; c.e_next = g.e_next;
         c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool;
         c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < 5; ++pass) {
             bool changed = false;
             if (status == 2) {
-                list[0] = 0;
                 c.use_claims = pass > 0;
-                if (bulk_visit(c, id, 0)) { status = 1; changed = true; }
+                if (bulk_eval(c) == 1) { status = 1; changed = true; }
             }
             __syncwarp();
             if (changed) {
@@ -685,7 +762,11 @@ __device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
                 const int x = list[k];
                 if (x == id) continue;
                 const int cl = claim[x] & 31;
-                if (cl != lane) cut = min(cut, min(cl, lane));
+                // announced twice: the lower lane emits it first and is right; the higher lane's
+                // replay assumed it was still missing, so the round ends at the higher lane.  If
+                // this lane's announcement was overwritten, lanes above it may have been
+                // misinformed: it still emits, but nothing above it does.
+                if (cl != lane) cut = min(cut, cl < lane ? lane : lane + 1);
             }
         }
         cut = __reduce_min_sync(kFull, cut);
@@ -726,7 +807,9 @@ __device__ __forceinline__ bool topo_sort(const Graph& g, const Caps& caps) {
 
 // Per-rank row records for the DP and the traceback: predecessor rows in in-edge order (CSR),
 // letter code + sink flag, first predecessor row.
-__device__ __forceinline__ void build_rows(const Graph& g) {
+template <bool kSmem>
+__device__ __noinline__ void build_rows(const GState& st) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     int base = 0;
@@ -797,7 +880,9 @@ __device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
     return max_id;
 }
 
-__device__ __forceinline__ int heaviest_bundle(const Graph& g) {
+template <bool kSmem>
+__device__ __noinline__ int heaviest_bundle(const GState& st) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     int len = 0;
@@ -850,9 +935,10 @@ struct SeqSrc {
     int type;
 };
 
-template <bool kOneTile>
-__device__ __forceinline__ bool add_sequence(Graph& g, const Caps& caps, int16_t* H, const SeqSrc& s,
-                                             Scores sc, uint16_t* path) {
+template <bool kSmem, bool kOneTile>
+__device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t* H, const SeqSrc& s,
+                                          Scores sc, uint16_t* path) {
+    const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
     if (len > caps.lcap) return false;
@@ -873,28 +959,32 @@ __device__ __forceinline__ bool add_sequence(Graph& g, const Caps& caps, int16_t
 
     AlnSpan span;
     span.first = -1; span.last = -1;
-    if (g.n_nodes > 0) {   // reference sisd_alignment_engine.cpp:249-251
+    if (st.n_nodes > 0) {   // reference sisd_alignment_engine.cpp:249-251
         const int tiles = kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols;
         const int cols = tiles * kTileCols;
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
-        if (S * (g.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
+        if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
         build_profile(g, len, cols, sc);
         __syncwarp();
-        EndCell ec = dp_fill<kOneTile>(g, H, len, tiles, s.type, sc);
-        span = traceback(g, H, cols, ec, s.type, sc, g.n_nodes + len + 4);
+        EndCell ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
+        span = traceback<kSmem>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
     }
-    if (!add_to_graph(g, caps, len, span, path)) return false;
-    if (!topo_sort(g, caps)) return false;
-    build_rows(g);
+    const int nodes_before = st.n_nodes, edges_before = st.n_edges;
+    if (!add_to_graph<kSmem>(st, caps, len, span, path)) return false;
+    // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence the
+    // reference's topological order, unchanged: nothing to re-sort
+    if (st.n_nodes == nodes_before && st.n_edges == edges_before) return true;
+    if (!topo_sort<kSmem>(st, caps)) return false;
+    build_rows<kSmem>(st);
     return true;
 }
 
 // ------------------------------------------------------------------------------------------
 // Window driver (reference src/Window.cpp:44-254)
 // ------------------------------------------------------------------------------------------
-template <bool kOneTile>
-__device__ __forceinline__ int run_short(Graph& g, const Params& P, const Caps& caps, int16_t* H,
+template <bool kSmem, bool kOneTile>
+__device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                          const WinDesc& w, char* out) {
     const int lane = lane_id();
     const ArmDesc* a = P.arms + w.first_arm;
@@ -912,37 +1002,38 @@ __device__ __forceinline__ int run_short(Graph& g, const Params& P, const Caps& 
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
         s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
         s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
-        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
-        if (!add_sequence<kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
-    const int nc = heaviest_bundle(g);
+    const int nc = heaviest_bundle<kSmem>(g);
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
     const int n = nc >= 2 ? nc - 2 : 0;
-    for (int p = lane; p < n; p += 32) out[p] = code_to_char(g.ninfo[g.cons[p + 1]] & 7);
+    const Graph v = make_graph<kSmem>(g);
+    for (int p = lane; p < n; p += 32) out[p] = code_to_char(v.ninfo[v.cons[p + 1]] & 7);
     return n;
 }
 
 // LONG windows: two rounds with the lr scores, all kNW, support counts and
 // curation (reference src/Window.cpp:156-254, graph.cpp:371-388,533-568).
-template <bool kOneTile>
-__device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& caps, int16_t* H,
+template <bool kSmem, bool kOneTile>
+__device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                         const WinDesc& w, char* out, uint16_t* paths, uint64_t p_slot) {
     const int lane = lane_id();
     const ArmDesc* a = P.arms + w.first_arm;
@@ -969,7 +1060,7 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return false;
             if (lane == 0) pstart[g.n_seq] = used;
-            const bool ok = add_sequence<kOneTile>(g, caps, H, q, sc, pnodes + used);
+            const bool ok = add_sequence<kSmem, kOneTile>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
             return ok;
         };
@@ -989,33 +1080,34 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
         if (lane == 0) pstart[g.n_seq] = used;
         __syncwarp();
 
-        const int nc = heaviest_bundle(g);
+        const int nc = heaviest_bundle<kSmem>(g);
+        const Graph gv = make_graph<kSmem>(g);
         // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
-        uint16_t* msa = g.n2r;
+        uint16_t* msa = gv.n2r;
         if (lane == 0) {
             int id = 0;
-            for (int i = 0; i < g.n_nodes; ++i) {
-                const int v = g.r2n[i];
+            for (int i = 0; i < gv.n_nodes; ++i) {
+                const int v = gv.r2n[i];
                 msa[v] = (uint16_t)id;
-                const int cnt = g.al_cnt[v];
-                for (int k = 0; k < cnt; ++k) msa[g.r2n[++i]] = (uint16_t)id;
+                const int cnt = gv.al_cnt[v];
+                for (int k = 0; k < cnt; ++k) msa[gv.r2n[++i]] = (uint16_t)id;
                 ++id;
             }
         }
         // support counts (graph.cpp:542-564) -> reuse score (free after the bundle)
-        uint32_t* sup = reinterpret_cast<uint32_t*>(g.score);
+        uint32_t* sup = reinterpret_cast<uint32_t*>(gv.score);
         __syncwarp();
         for (int c = lane; c < nc; c += 32) sup[c] = 0;
         __syncwarp();
-        for (int q = lane; q < g.n_seq; q += 32) {
+        for (int q = lane; q < gv.n_seq; q += 32) {
             const uint32_t b = pstart[q], e = pstart[q + 1];
             int c = 0;
             for (uint32_t k = b; k < e; ++k) {
                 const int v = pnodes[k];
                 const int mv = msa[v];
-                while (c < nc && msa[g.cons[c]] < mv) ++c;
+                while (c < nc && msa[gv.cons[c]] < mv) ++c;
                 if (c >= nc) break;
-                if (msa[g.cons[c]] == mv && (g.ninfo[v] & 7) == (g.ninfo[g.cons[c]] & 7)) atomicAdd(&sup[c], 1u);
+                if (msa[gv.cons[c]] == mv && (gv.ninfo[v] & 7) == (gv.ninfo[gv.cons[c]] & 7)) atomicAdd(&sup[c], 1u);
             }
         }
         __syncwarp();
@@ -1025,7 +1117,7 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
             const int c = c0 + lane;
             const bool keep = c < nc && sup[c] >= thres;
             const unsigned km = __ballot_sync(kFull, keep);
-            if (keep) out[kept + __popc(km & ((1u << lane) - 1u))] = code_to_char(g.ninfo[g.cons[c]] & 7);
+            if (keep) out[kept + __popc(km & ((1u << lane) - 1u))] = code_to_char(gv.ninfo[gv.cons[c]] & 7);
             kept += __popc(km);
         }
         n_cons = kept;
@@ -1035,17 +1127,19 @@ __device__ __forceinline__ int run_long(Graph& g, const Params& P, const Caps& c
     return n_cons;
 }
 
-template <bool kSmem, bool kOneTile>
+template <bool kSmem, bool kOneTile, bool kLong>
 __global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
-    extern __shared__ __align__(16) uint8_t smem[];
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
     const int gwarp = blockIdx.x * warps_per_cta + warp_in_cta;
     const Caps caps = P.caps;
     const ArenaLayout L = arena_layout(caps);
-    uint8_t* arena = kSmem ? (smem + (size_t)warp_in_cta * L.total) : (P.gws + (size_t)gwarp * P.g_slot);
-    Graph g = make_graph(arena, L);
+    GState g;
+    g.L = L;
+    g.sbase = kSmem ? (uint32_t)warp_in_cta * L.total : 0u;
+    g.gbase = kSmem ? nullptr : (P.gws + (size_t)gwarp * P.g_slot);
+    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 
@@ -1062,8 +1156,8 @@ __global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
         if (w.n_empty > n) {
             res = 0;   // reference src/Window.cpp:47-49
         } else if (n >= 2) {
-            if (w.wtype == 0) res = run_short<kOneTile>(g, P, caps, H, w, out);
-            else if (paths) res = run_long<kOneTile>(g, P, caps, H, w, out, paths, P.p_slot);
+            if (w.wtype == 0) res = run_short<kSmem, kOneTile>(g, P, caps, H, w, out);
+            else if (kLong && paths) res = run_long<kSmem, kOneTile>(g, P, caps, H, w, out, paths, P.p_slot);
             else res = -2;
         } else {
             res = -1;
@@ -1096,8 +1190,9 @@ __global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
 cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, int blocks, int warps_per_block,
                        size_t smem_bytes, cudaStream_t stream) {
     void (*k)(const Params) = nullptr;
-    if (smem_graph) k = one_tile ? poa_kernel<true, true> : poa_kernel<true, false>;
-    else k = one_tile ? poa_kernel<false, true> : poa_kernel<false, false>;
+    // one-tile tiers only ever run SHORT windows (the LONG driver is compiled out of them)
+    if (smem_graph) k = one_tile ? poa_kernel<true, true, false> : poa_kernel<true, false, true>;
+    else k = one_tile ? poa_kernel<false, true, false> : poa_kernel<false, false, true>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(P);
