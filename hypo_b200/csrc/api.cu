@@ -210,12 +210,15 @@ struct Tier {
     int warps_per_block, blocks_per_sm;
 };
 
-// T0: SHORT windows whose sequences fit one 128-column tile; DAG in shared memory,
-//     16 warps/SM.  T1: anything up to 1023 columns with a medium DAG in shared memory.
+// T0 : SHORT windows whose sequences fit one 128-column tile; DAG in shared memory, 16 warps/SM,
+//      previous DP row carried in registers.
+// T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 14 warps/SM.
+// T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 const Tier kTiers[] = {
     {true, true, false, false, 320, 576, 128, 320, 127, 8, 2},
-    {true, false, true, false, 1536, 3072, 512, 1536, 1023, 4, 1},
+    {true, false, false, false, 320, 576, 128, 320, 255, 7, 2},
+    {true, false, true, false, 1024, 2048, 384, 1024, 1023, 4, 1},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1},
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1},
 };
@@ -555,10 +558,10 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
     return HYPO_OK;
 }
 
-int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[4]) {
+int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[8]) {
     if (poa_kernel_ms) *poa_kernel_ms = g.poa_ms;
     if (poa_launches) *poa_launches = g.poa_launches;
-    if (tier_windows) for (int t = 0; t < 4; ++t) tier_windows[t] = g.tier_windows[t];
+    if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = g.tier_windows[t];
     return HYPO_OK;
 }
 

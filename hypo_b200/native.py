@@ -136,6 +136,6 @@ def last_timing() -> Tuple[float, int, List[int]]:
     """(POA-kernel device ms, POA launches, windows per tier) of the last batch call."""
     ms = C.c_float(0)
     n = C.c_uint32(0)
-    tiers = (C.c_uint32 * 4)()
+    tiers = (C.c_uint32 * 8)()
     lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
     return float(ms.value), int(n.value), [int(x) for x in tiers]

@@ -148,7 +148,7 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
  * Measurement hook: device time (CUDA events on the launching stream) and launch count of the
  * POA kernels of the most recent batch call, and how many windows each capacity tier ran.
  */
-int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[4]);
+int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[8]);
 
 /* Number of kernel launches issued by this library since hypo_gpu_init. */
 uint64_t hypo_gpu_launch_count(void);
