@@ -556,7 +556,7 @@ constexpr int kBulkMaxNodes = kBulkList - 1;   // list[0] = count, then up to kB
 struct SortCtx {
     const uint8_t* mark;
     const uint8_t* al_cnt;
-    const uint16_t* claim;
+    uint16_t* claim;     // node -> (round << 5 | lane) of the lane that announced it this round
     const uint16_t* in_head;
     const uint16_t* e_next;
     const uint16_t* e_src;
@@ -564,6 +564,7 @@ struct SortCtx {
     const uint16_t* al_pool;
     uint16_t* list;      // [0] = n, [1..n] = nodes in emission order
     int i0, id, lane, round;
+    unsigned emit_mask;  // lanes whose replay succeeded in an earlier pass
     bool use_claims;
 };
 
@@ -572,28 +573,29 @@ struct SortCtx {
 __device__ __forceinline__ bool s_ok(const SortCtx& c, int s) {
     if ((c.mark[s] & 3) == 2) return true;
     if (s >= c.i0 && s < c.id) return true;
-    if (c.use_claims) {
-        const int cl = c.claim[s];
-        if ((cl >> 5) == c.round && (cl & 31) < c.lane) return true;
-    }
-    const int n = c.list[0];
-    for (int k = 1; k <= n; ++k)
-        if (c.list[k] == s) return true;
-    return false;
+    const int cl = c.claim[s];
+    if (cl == ((c.round << 5) | c.lane)) return true;        // in this lane's own list
+    return c.use_claims && (cl >> 5) == c.round && (cl & 31) < c.lane && ((c.emit_mask >> (cl & 31)) & 1);
 }
 
+// Appends to the lane's emission list; extras are announced (and remembered) in the claim table.
 __device__ __forceinline__ bool s_push(const SortCtx& c, int x) {
     const int n = c.list[0];
     if (n >= kBulkMaxNodes) return false;
+    // Lanes run concurrently: another lane may have overwritten this lane's claim on x, after
+    // which s_ok no longer recognises x as already emitted here.  Never list a node twice.
+    for (int k = 1; k <= n; ++k)
+        if (c.list[k] == x) return false;
     c.list[n + 1] = (uint16_t)x;
     c.list[0] = (uint16_t)(n + 1);
+    if (x != c.id) c.claim[x] = (uint16_t)((c.round << 5) | c.lane);
     return true;
 }
 
 // unit(u): u fresh; its aligned nodes fresh with all sources emitted; at most one not-yet-emitted
 // source per level, forming a chain of <= kBulkDepth fresh nodes without aligned nodes.
 // Emits chain (deepest first), u, aligned(u).
-__device__ __noinline__ bool s_unit(const SortCtx& c, int u) {
+__device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
     if (c.mark[u] != 0) return false;
     const int mu = c.al_cnt[u];
     const int ublk = c.al_blk[u];
@@ -603,7 +605,7 @@ __device__ __noinline__ bool s_unit(const SortCtx& c, int u) {
         for (int e = c.in_head[b]; e != kNone; e = c.e_next[e])
             if (!s_ok(c, c.e_src[e])) return false;
     }
-    int chain[kBulkDepth];
+    unsigned long long chain = 0ull;   // up to kBulkDepth 16-bit node ids
     int nc = 0, w = u;
     for (;;) {
         int next = -1;
@@ -615,14 +617,13 @@ __device__ __noinline__ bool s_unit(const SortCtx& c, int u) {
         }
         if (next == -1) break;
         if (nc == kBulkDepth || c.mark[next] != 0 || c.al_cnt[next] > 0) return false;
-#pragma unroll
-        for (int q = 0; q < kBulkDepth; ++q) if (q == nc) chain[q] = next;
+        chain |= (unsigned long long)next << (16 * nc);
         ++nc;
         w = next;
     }
-#pragma unroll
-    for (int q = kBulkDepth - 1; q >= 0; --q)
-        if (q < nc && !s_push(c, chain[q])) return false;
+#pragma unroll 1
+    for (int q = nc - 1; q >= 0; --q)
+        if (!s_push(c, (int)((chain >> (16 * q)) & 0xffffull))) return false;
     if (!s_push(c, u)) return false;
     for (int k = 0; k < mu; ++k)
         if (!s_push(c, c.al_pool[ublk * kAlSlots + k])) return false;
@@ -631,7 +632,7 @@ __device__ __noinline__ bool s_unit(const SortCtx& c, int u) {
 
 // Replay of what the DFS does when its outer loop reaches node c.id.  Returns 1 (emit c.list) or
 // 2 (cannot decide within the bounds).  Same code shape as bulk_eval in oracle/poa_oracle.c.
-__device__ __forceinline__ int bulk_eval(const SortCtx& c) {
+__device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
     const int id = c.id;
     c.list[0] = 0;
     if (c.mark[id] != 0) return 2;
@@ -641,24 +642,39 @@ __device__ __forceinline__ int bulk_eval(const SortCtx& c) {
     for (int t = nm - 1; t >= -1; --t) {
         const int x = t >= 0 ? (int)c.al_pool[blk * kAlSlots + t] : id;
         if (t >= 0 && (c.mark[x] != 0 || s_ok(c, x))) return 2;
-        int und[3];
+        unsigned long long und = 0ull;   // up to three 16-bit node ids
         int n_und = 0;
         for (int e = c.in_head[x]; e != kNone; e = c.e_next[e]) {
             const int s = c.e_src[e];
             if (s_ok(c, s)) continue;
             if (n_und == 3) return 2;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) if (q == n_und) und[q] = s;
+            und |= (unsigned long long)s << (16 * n_und);
             ++n_und;
         }
-#pragma unroll
-        for (int q = 2; q >= 0; --q)
-            if (q < n_und && !s_ok(c, und[q]) && !s_unit(c, und[q])) return 2;
+#pragma unroll 1
+        for (int q = n_und - 1; q >= 0; --q) {
+            const int u = (int)((und >> (16 * q)) & 0xffffull);
+            if (!s_ok(c, u) && !s_unit(c, u)) return 2;
+        }
     }
     if (!s_push(c, id)) return 2;
     for (int k = 0; k < nm; ++k)
         if (!s_push(c, c.al_pool[blk * kAlSlots + k])) return 2;
     return 1;
+}
+
+__device__ __forceinline__ int bulk_eval(const SortCtx& c) {
+    const int r = bulk_eval_inner(c);
+    if (r == 2) {   // withdraw the announcements of the abandoned replay
+        const int n = c.list[0];
+        const int me = (c.round << 5) | c.lane;
+        for (int k = 1; k <= n; ++k) {
+            const int x = c.list[k];
+            if (c.claim[x] == me) c.claim[x] = 0;
+        }
+        c.list[0] = 0;
+    }
+    return r;
 }
 
 // Serial DFS from one root (lane 0), verbatim the reference's inner loop.
@@ -731,6 +747,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
         c.mark = g.mark; c.al_cnt = g.al_cnt; c.claim = claim; c.in_head = g.in_head; c.e_next = g.e_next;
         c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool;
         c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
+        c.emit_mask = 0u;
         for (int pass = 0; pass < 5; ++pass) {
             bool changed = false;
             if (status == 2) {
@@ -738,12 +755,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
                 if (bulk_eval(c) == 1) { status = 1; changed = true; }
             }
             __syncwarp();
-            if (changed) {
-                const int cnt = list[0];
-                for (int k = 1; k <= cnt; ++k)
-                    if (list[k] != id) claim[list[k]] = (uint16_t)((round << 5) | lane);
-            }
-            __syncwarp();
+            c.emit_mask = __ballot_sync(kFull, status == 1);
             if (!__any_sync(kFull, changed)) break;
             if (!__any_sync(kFull, status == 2)) break;
         }
@@ -762,11 +774,11 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
                 const int x = list[k];
                 if (x == id) continue;
                 const int cl = claim[x] & 31;
-                // announced twice: the lower lane emits it first and is right; the higher lane's
-                // replay assumed it was still missing, so the round ends at the higher lane.  If
-                // this lane's announcement was overwritten, lanes above it may have been
-                // misinformed: it still emits, but nothing above it does.
-                if (cl != lane) cut = min(cut, cl < lane ? lane : lane + 1);
+                // announced by two lanes (or withdrawn under this lane's feet): this lane's replay
+                // can no longer be trusted (lanes run concurrently, its own list may even hold the
+                // node twice), so the round ends here; the lane holding the claim, if higher, is
+                // cut as well, if lower it emits the node legitimately.
+                if (cl != lane) cut = min(cut, lane);
             }
         }
         cut = __reduce_min_sync(kFull, cut);

@@ -116,3 +116,17 @@ def test_errors_are_loud():
     b.arms["off"][0] = 1 << 40
     with pytest.raises(native.HypoGpuError):
         native.consensus(b)
+
+
+def test_large_random_parity_stresses_concurrent_sort():
+    """Thousands of windows per shape, including high-error ones whose graphs are full of cliques and
+    insertion chains: this is what exercises the warp-parallel topological sort (claims, conflicts,
+    serial fallback) under real concurrency.  Every window is compared with the oracle."""
+    from hypo_b200.hostlib import synth_batch
+    for seed, kw in ((31, dict(n_win=20000, length=120, n_arms=30, kind="internal", err=0.01)),
+                     (32, dict(n_win=3000, length=110, n_arms=30, kind="mixed", err=0.05)),
+                     (33, dict(n_win=3000, length=60, n_arms=25, kind="internal", err=0.12)),
+                     (34, dict(n_win=6000, length=12, n_arms=35, kind="mixed", err=0.03))):
+        b = synth_batch(seed, **kw)
+        want, _ = oracle_consensus(b)
+        _assert_same(native.consensus(b), want, b, f"large/{kw}")
