@@ -23,8 +23,7 @@ struct Graph {
     uint16_t* e_w;        // Edge::total_weight_ (2 per traversal)
     uint16_t* e_next;     // next in-edge of the same destination
     uint16_t* al_pool;
-    uint16_t* pstart;     // rank -> offset into prows (CSR)
-    uint8_t* rcode;       // rank -> letter code | sink (bit 3)
+    uint32_t* rowinfo;    // rank -> prows offset | #preds << 16 | letter code << 24 | sink << 27
     uint16_t* prows;      // predecessor DP rows, in-edge order
     uint16_t* fp;         // DP row -> first predecessor row
     uint16_t* stack;
@@ -68,8 +67,7 @@ __device__ __forceinline__ Graph make_graph(const GState& st) {
     g.e_w = (uint16_t*)(base + L.e_w);
     g.e_next = (uint16_t*)(base + L.e_next);
     g.al_pool = (uint16_t*)(base + L.al_pool);
-    g.pstart = (uint16_t*)(base + L.pstart);
-    g.rcode = base + L.rcode;
+    g.rowinfo = (uint32_t*)(base + L.rowinfo);
     g.prows = (uint16_t*)(base + L.prows);
     g.fp = (uint16_t*)(base + L.fp);
     g.stack = (uint16_t*)(base + L.stack);
@@ -152,15 +150,13 @@ __device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry, int lane)
         runb = __byte_perm(x[r], 0, 0x3232);                        // (x.hi, x.hi)
     }
     int tot = hi16(x[kNR - 1]);
+    // shfl_up hands lanes below the shift their own value back, so no lane predicate is needed
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int y = __shfl_up_sync(kFull, tot, d);
-        if (lane >= d) tot = max(tot, y);
-    }
+    for (int d = 1; d < 32; d <<= 1) tot = max(tot, __shfl_up_sync(kFull, tot, d));
     int excl = __shfl_up_sync(kFull, tot, 1);
     if (lane == 0) excl = kNegInf;
     if (!kOneTile) excl = max(excl, carry);
-    const uint32_t cb = bcast16(excl);
+    const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
 #pragma unroll
     for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
     if (kOneTile) return kNegInf;
@@ -191,10 +187,13 @@ __device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ 
 #pragma unroll
     for (int r = 0; r < kNR; ++r) prev[r] = 0u;
 
-    int ps = g.pstart[0];
+    uint32_t info_next = g.rowinfo[0];
     for (int rk = 0; rk < n; ++rk) {
-        const int pe = g.pstart[rk + 1];
-        const int code = g.rcode[rk] & 7;
+        const uint32_t info = info_next;
+        info_next = g.rowinfo[rk + 1];   // one row ahead (the array has a spare entry)
+        const int ps = info & 0xffff;
+        const int pe = ps + ((info >> 16) & 0xff);
+        const int code = (info >> 24) & 7;
         const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
         int carry = kNegInf;
         uint32_t x[kNR];
@@ -239,7 +238,6 @@ __device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ 
         }
         if (kOneTile) { prev[0] = x[0]; prev[1] = x[1]; }
         else __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
-        ps = pe;
     }
     __syncwarp();
 
@@ -247,7 +245,7 @@ __device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ 
     // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
     int best = INT_MIN, brow = 0x7fffffff;
     for (int r = lane; r < n; r += 32) {
-        const bool cand = (type == kLOV) || (g.rcode[r] & 8);
+        const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
         if (cand) {
             const int v = (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len];
             if (v > best) { best = v; brow = r + 1; }
@@ -313,7 +311,7 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
             if (ok) {
                 const int hc = (int)H[(unsigned)my_r * ucols + (unsigned)jj];
                 hp = (int)H[(unsigned)my_rn * ucols + (unsigned)(jj - 1)];
-                const int s = ((g.rcode[my_r - 1] & 7) == g.seq[jj - 1]) ? mm : nn;
+                const int s = (((g.rowinfo[my_r - 1] >> 24) & 7) == g.seq[jj - 1]) ? mm : nn;
                 ok = hc == hp + s;
             }
             const unsigned mask = __ballot_sync(kFull, ok);
@@ -334,9 +332,10 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
         int ni = i, nj = j, nh = hij;
         bool found = false;
         if (i != 0) {
-            const int ps = g.pstart[i - 1], pe = g.pstart[i];
+            const uint32_t info = g.rowinfo[i - 1];
+            const int ps = info & 0xffff, pe = ps + ((info >> 16) & 0xff);
             if (j != 0) {
-                const int s = ((g.rcode[i - 1] & 7) == g.seq[j - 1]) ? mm : nn;
+                const int s = (((info >> 24) & 7) == g.seq[j - 1]) ? mm : nn;
                 if (ps == pe) {
                     const int h = (int)H[j - 1];
                     if (hij == h + s) { ni = 0; nj = j - 1; nh = h; found = true; }
@@ -827,12 +826,12 @@ __device__ __noinline__ void build_rows(const GState& st) {
     int base = 0;
     for (int r0 = 0; r0 < n; r0 += 32) {
         const int r = r0 + lane;
-        int v = 0, deg = 0;
+        int v = 0, deg = 0, code = 0;
         if (r < n) {
             v = g.r2n[r];
             deg = g.in_deg[v];
             const int info = g.ninfo[v];
-            g.rcode[r] = (uint8_t)((info & 7) | ((info & 8) ? 0 : 8));   // bit 3 = sink (no out-edges)
+            code = (info & 7) | ((info & 8) ? 0 : 8);   // bit 3 = sink (no out-edges)
         }
         int off = deg;
 #pragma unroll
@@ -843,7 +842,7 @@ __device__ __noinline__ void build_rows(const GState& st) {
         const int total = __shfl_sync(kFull, off, 31);
         off = base + off - deg;
         if (r < n) {
-            g.pstart[r] = (uint16_t)off;
+            g.rowinfo[r] = (uint32_t)off | ((uint32_t)deg << 16) | ((uint32_t)code << 24);
             int k = off, first = 0;
             for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
                 const int prow = g.n2r[g.e_src[e]] + 1;
@@ -854,7 +853,7 @@ __device__ __noinline__ void build_rows(const GState& st) {
         }
         base += total;
     }
-    if (lane == 0) { g.pstart[n] = (uint16_t)base; g.fp[0] = 0; }
+    if (lane == 0) { g.rowinfo[n] = 0u; g.fp[0] = 0; }
     __syncwarp();
 }
 

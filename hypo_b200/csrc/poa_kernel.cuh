@@ -101,8 +101,7 @@ struct ArenaLayout {
     uint32_t e_src, e_w, e_next;   // u16 each
     uint32_t al_pool;   // u16 [acap][kAlSlots]
     // rows (rebuilt after every topological sort)
-    uint32_t pstart;    // u16 [ncap+2] CSR offsets into prows, by rank
-    uint32_t rcode;     // u8  [ncap+1] letter code | sink (bit 3), by rank
+    uint32_t rowinfo;   // u32 [ncap+1] by rank: prows offset (bits 0-15) | #preds (16-23) | letter code (24-26) | sink (27)
     uint32_t prows;     // u16 [ecap] predecessor DP rows in in-edge order
     uint32_t fp;        // u16 [ncap+1] first predecessor row of each DP row (0 = virtual row 0)
     // scratch group (phases are disjoint in time)
@@ -133,8 +132,7 @@ __host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
     L.e_w = take(2u * c.ecap);
     L.e_next = take(2u * c.ecap);
     L.al_pool = take(2u * kAlSlots * c.acap);
-    L.pstart = take(2u * (c.ncap + 2));
-    L.rcode = take(c.ncap + 1);
+    L.rowinfo = take(4u * (c.ncap + 1));
     L.prows = take(2u * c.ecap);
     L.fp = take(2u * (c.ncap + 1));
     const uint32_t scratch0 = o;
