@@ -48,6 +48,7 @@ struct GState {
     uint32_t sbase;      // tiers S: byte offset of this warp's arena in dynamic shared memory
     ArenaLayout L;
     int n_nodes, n_edges, n_al, n_seq;
+    bool exact;          // r2n/n2r currently hold spoa's exact DFS order (not just a valid one)
 };
 
 template <bool kSmem>
@@ -166,6 +167,7 @@ __device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry, int lane)
 struct EndCell {
     int row;   // 0 if no candidate (reference clamps max_i=-1 to 0)
     int col;
+    bool tie;  // two or more candidate rows share the best score (the rank order decides)
 };
 
 template <bool kSmem, bool kOneTile>
@@ -261,6 +263,15 @@ __device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ 
     const bool any = brow != 0x7fffffff;
     ec.row = any ? brow : 0;
     ec.col = any ? len : 0;
+    // does a second candidate reach the same score?  (only then does the exact order matter)
+    int same = 0;
+    if (any)
+        for (int r = lane; r < n; r += 32) {
+            const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
+            if (cand && (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len] == best) ++same;
+        }
+    same = __reduce_add_sync(kFull, same);
+    ec.tie = same > 1;
     return ec;
 }
 
@@ -816,6 +827,95 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// Incremental ("cheap") order maintenance.  H[node][j] does not depend on which topological order
+// the rows are processed in; spoa's exact DFS order only decides ties (end cell among equal
+// candidates, heaviest bundle, MSA columns).  So between exact sorts the warp keeps a VALID
+// topological order in which aligned cliques stay contiguous, by inserting the nodes the read just
+// created, in path order:
+//   * a new member of an existing clique goes to the end of that clique's block,
+//   * any other new node goes immediately before the block of the next pre-existing column on the
+//     read's path (or to the very end).
+// Anchors are non-decreasing along the path, so new node i (path order) with anchor a_i gets rank
+// a_i + i and an old node of rank r moves to r + #{i : a_i <= r}.  The exact order is re-derived
+// (topo_sort) only when an alignment's end cell is tied and before the consensus is extracted.
+// oracle/poa_oracle.c replays this scheme in checked mode and asserts it is a valid order.
+// ------------------------------------------------------------------------------------------
+template <bool kSmem>
+__device__ __noinline__ void order_update(const GState& st, int len, int nb) {
+    const Graph g = make_graph<kSmem>(st);
+    const int lane = lane_id();
+    const int n = g.n_nodes;
+    uint16_t* anch = reinterpret_cast<uint16_t*>(g.prof);   // per position (profile is dead here)
+    uint16_t* newa = g.stack;                               // per new node, path order
+
+    // pass A (reverse): anchor of every position that holds a new node
+    int carry = nb;   // block start of the next pre-existing column to the right (nb = none: the end)
+    for (int p0 = ((len - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
+        const int p = p0 + lane;
+        int colmin = 0x7fffffff;   // block start if column p is pre-existing (old node or new clique member)
+        int mate_anchor = -1;
+        bool is_new = false;
+        if (p < len) {
+            const int v = g.cur[p];
+            is_new = v >= nb;
+            const int cnt = g.al_cnt[v];
+            if (!is_new || cnt > 0) {
+                int mn = is_new ? 0x7fffffff : (int)g.n2r[v];
+                int mx = is_new ? -1 : (int)g.n2r[v];
+                const int blk = g.al_blk[v];
+                for (int k = 0; k < cnt; ++k) {
+                    const int m = g.al_pool[blk * kAlSlots + k];
+                    if (m < nb) { const int r = g.n2r[m]; mn = min(mn, r); mx = max(mx, r); }
+                }
+                colmin = mn;
+                if (is_new) mate_anchor = mx + 1;
+            }
+        }
+        // exclusive suffix min within the chunk, then the carry from the chunks to the right
+        int suf = colmin;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) suf = min(suf, __shfl_down_sync(kFull, suf, d));
+        int excl = __shfl_down_sync(kFull, suf, 1);
+        if (lane == 31) excl = 0x7fffffff;
+        excl = min(excl, carry);
+        if (is_new) anch[p] = (uint16_t)(mate_anchor >= 0 ? mate_anchor : excl);
+        carry = min(carry, __shfl_sync(kFull, suf, 0));
+    }
+    __syncwarp();
+    // pass B (forward): compact the new nodes in path order, give them their ranks
+    int K = 0;
+    for (int p0 = 0; p0 < len; p0 += 32) {
+        const int p = p0 + lane;
+        const int v = p < len ? (int)g.cur[p] : 0;
+        const bool is_new = p < len && v >= nb;
+        const unsigned m = __ballot_sync(kFull, is_new);
+        if (is_new) {
+            const int i = K + __popc(m & ((1u << lane) - 1u));
+            const int a = anch[p];
+            newa[i] = (uint16_t)a;
+            g.n2r[v] = (uint16_t)(a + i);
+        }
+        K += __popc(m);
+    }
+    __syncwarp();
+    // old nodes move right by the number of new nodes anchored at or before them
+    if (K > 0) {
+        for (int v = lane; v < nb; v += 32) {
+            const int r = g.n2r[v];
+            int lo = 0, hi = K;   // first index with newa[idx] > r
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)newa[mid] <= r) lo = mid + 1; else hi = mid;
+            }
+            g.n2r[v] = (uint16_t)(r + lo);
+        }
+        __syncwarp();
+        for (int v = lane; v < n; v += 32) g.r2n[g.n2r[v]] = (uint16_t)v;
+    }
+    __syncwarp();
+}
+
 // Per-rank row records for the DP and the traceback: predecessor rows in in-edge order (CSR),
 // letter code + sink flag, first predecessor row.
 template <bool kSmem>
@@ -979,14 +1079,26 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
         build_profile(g, len, cols, sc);
         __syncwarp();
         EndCell ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
+        if (ec.tie && !st.exact) {
+            // the reference breaks this tie by rank in ITS order: derive it and redo the fill
+            if (!topo_sort<kSmem>(st, caps)) return false;
+            st.exact = true;
+            build_rows<kSmem>(st);
+            build_profile(g, len, cols, sc);   // the sort used the profile area as scratch
+            __syncwarp();
+            ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
+        }
         span = traceback<kSmem>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
     }
     const int nodes_before = st.n_nodes, edges_before = st.n_edges;
     if (!add_to_graph<kSmem>(st, caps, len, span, path)) return false;
-    // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence the
-    // reference's topological order, unchanged: nothing to re-sort
+    // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence every
+    // order, unchanged
     if (st.n_nodes == nodes_before && st.n_edges == edges_before) return true;
-    if (!topo_sort<kSmem>(st, caps)) return false;
+    // new nodes must be ranked; new edges alone keep the current order valid (they follow it),
+    // but either may change what spoa's DFS would produce
+    if (st.n_nodes != nodes_before) order_update<kSmem>(st, len, nodes_before);
+    st.exact = false;
     build_rows<kSmem>(st);
     return true;
 }
@@ -1008,6 +1120,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     if (!added) return -1;   // caller copies the draft (:150-152)
 
     g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+    g.exact = true;
     SeqSrc s;
     s.ascii = nullptr;
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
@@ -1032,6 +1145,10 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
         if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+    }
+    if (!g.exact) {   // the consensus needs spoa's exact rank order
+        if (!topo_sort<kSmem>(g, caps)) return -2;
+        g.exact = true;
     }
     const int nc = heaviest_bundle<kSmem>(g);
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
@@ -1065,6 +1182,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     int n_cons = 0;
     for (int round = 0; round < 2; ++round) {
         g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+        g.exact = true;
         uint32_t used = 0;
         SeqSrc s;
         s.head = false; s.tail = false; s.type = kNW;
@@ -1091,6 +1209,10 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         if (lane == 0) pstart[g.n_seq] = used;
         __syncwarp();
 
+        if (!g.exact) {   // consensus and MSA columns need spoa's exact rank order
+            if (!topo_sort<kSmem>(g, caps)) return -2;
+            g.exact = true;
+        }
         const int nc = heaviest_bundle<kSmem>(g);
         const Graph gv = make_graph<kSmem>(g);
         // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
