@@ -1089,6 +1089,15 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
             ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
         }
         span = traceback<kSmem>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
+        // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
+        // written back: without this every DP row ends up in HBM (1 TB per million windows) just
+        // to be overwritten by the next read.
+        {
+            const unsigned lines = (unsigned)(st.n_nodes + 1) * (unsigned)cols / 64u;   // 128-byte lines
+            char* hb = reinterpret_cast<char*>(H);
+            for (unsigned l = lane; l < lines; l += 32)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(hb + (size_t)l * 128) : "memory");
+        }
     }
     const int nodes_before = st.n_nodes, edges_before = st.n_edges;
     if (!add_to_graph<kSmem>(st, caps, len, span, path)) return false;
