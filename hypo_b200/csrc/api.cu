@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -18,8 +19,8 @@
 #include "poa_kernel.cuh"
 
 namespace hypo_b200 {
-cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, int blocks, int warps_per_block,
-                       size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, bool compact, int blocks,
+                       int warps_per_block, size_t smem_bytes, cudaStream_t stream);
 }
 
 using namespace hypo_b200;
@@ -205,22 +206,26 @@ __global__ void widen_kernel(const uint32_t* __restrict__ len, uint64_t* __restr
 // Tier table
 // ---------------------------------------------------------------------------------------
 struct Tier {
-    bool smem_graph, one_tile, long_ok, from_bounds;
+    bool smem_graph, one_tile, long_ok, from_bounds, compact;
     int ncap, ecap, acap, scap, lcap;
     int warps_per_block, blocks_per_sm;
 };
 
-// T0 : SHORT windows whose sequences fit one 128-column tile; DAG in shared memory, 16 warps/SM,
+// Tc : SHORT windows whose sequences fit one 128-column tile and whose DAG stays small (the
+//      30 x 120 headline shape at ~1 % read error: 187 nodes on average, 209 at most in 3000
+//      windows): DAG in 8.4 KB of shared memory, 27 warps/SM (3 CTAs x 9 warps, <= 72 registers),
 //      previous DP row carried in registers.
-// T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 14 warps/SM.
+// T0 : same, larger DAG capacities, 18 warps/SM.  Windows that overflow Tc at run time land here.
+// T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 18 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 const Tier kTiers[] = {
-    {true, true, false, false, 320, 576, 128, 320, 127, 8, 2},
-    {true, false, false, false, 320, 576, 128, 320, 255, 7, 2},
-    {true, false, true, false, 1024, 2048, 384, 1024, 1023, 4, 1},
-    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1},
-    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1},
+    {true, true, false, false, true, 224, 352, 112, 224, 127, 9, 3},
+    {true, true, false, false, false, 320, 576, 128, 320, 127, 9, 2},
+    {true, false, false, false, false, 320, 576, 128, 320, 255, 9, 2},
+    {true, false, true, false, false, 1024, 2048, 384, 1024, 1023, 4, 1},
+    {false, false, true, true, false, 8192, 16384, 2048, 8192, 4095, 4, 1},
+    {false, false, true, true, false, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1},
 };
 const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 
@@ -316,13 +321,18 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         const ArenaLayout L = arena_layout(caps);
 
         int wpb = T.warps_per_block;
+        int bps = T.blocks_per_sm;
+        if (t == 0) {   // developer knobs for occupancy experiments (not part of the ABI)
+            if (const char* e = getenv("HYPO_B200_T0_WPB")) wpb = std::max(1, atoi(e));
+            if (const char* e = getenv("HYPO_B200_T0_BPS")) bps = std::max(1, atoi(e));
+        }
         size_t smem = 0;
         if (T.smem_graph) {
             smem = (size_t)L.total * wpb;
             while (smem > (size_t)g.smem_optin && wpb > 1) { wpb /= 2; smem = (size_t)L.total * wpb; }
             if (smem > (size_t)g.smem_optin) return fail(HYPO_E_CAPACITY, "tier %d does not fit shared memory", t);
         }
-        int blocks = g.sms * T.blocks_per_sm;
+        int blocks = g.sms * bps;
         uint64_t warps = (uint64_t)blocks * wpb;
         if (warps > n_work) { blocks = (int)((n_work + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
         const uint64_t h_slot = ((uint64_t)(caps.ncap + 1) * caps.tiles * kTileCols + 63) & ~63ull;
@@ -352,7 +362,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         P.sr_m = g.scores[0]; P.sr_n = g.scores[1]; P.sr_g = g.scores[2];
         P.lr_m = g.scores[3]; P.lr_n = g.scores[4]; P.lr_g = g.scores[5];
         CUDA_TRY(cudaEventRecord(g.ev0, stream));
-        CUDA_TRY(launch_poa(P, T.smem_graph, T.one_tile, blocks, wpb, smem, stream));
+        CUDA_TRY(launch_poa(P, T.smem_graph, T.one_tile, T.compact, blocks, wpb, smem, stream));
         CUDA_TRY(cudaEventRecord(g.ev1, stream));
         ++g.launches;
         CUDA_TRY(cudaMemcpyAsync(h_ovf_count, d_over, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));

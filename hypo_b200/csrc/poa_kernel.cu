@@ -26,12 +26,15 @@ struct Graph {
     uint32_t* rowinfo;    // rank -> prows offset | #preds << 16 | letter code << 24 | sink << 27
     uint16_t* prows;      // predecessor DP rows, in-edge order
     uint16_t* fp;         // DP row -> first predecessor row
-    uint16_t* stack;
-    uint8_t* seq;         // current sequence, letter codes
+    uint16_t* stack;      // toposort scratch: DFS stack
+    uint8_t* colseq;      // letter code of DP column j (colseq[0] and the padding columns hold 7)
+    uint8_t* seq;         // current sequence, letter codes (= colseq + 1)
     uint16_t* cur;        // per sequence position: aligned node / resolved node
-    int16_t* prof;        // [code][column] (match ? m : n) - g
+    uint16_t* chain;      // traceback scratch
     uint8_t* mark;        // toposort scratch
     uint16_t* lists;      // toposort scratch: per-lane emission lists
+    uint16_t* anch;       // order_update scratch
+    uint16_t* newa;
     int32_t* score;       // epilogue
     uint16_t* pred;
     uint16_t* cons;
@@ -72,11 +75,14 @@ __device__ __forceinline__ Graph make_graph(const GState& st) {
     g.prows = (uint16_t*)(base + L.prows);
     g.fp = (uint16_t*)(base + L.fp);
     g.stack = (uint16_t*)(base + L.stack);
-    g.seq = base + L.seq;
+    g.colseq = base + L.colseq;
+    g.seq = base + L.colseq + 1;
     g.cur = (uint16_t*)(base + L.cur);
-    g.prof = (int16_t*)(base + L.prof);
+    g.chain = (uint16_t*)(base + L.chain);
     g.mark = base + L.mark;
     g.lists = (uint16_t*)(base + L.lists);
+    g.anch = (uint16_t*)(base + L.anch);
+    g.newa = (uint16_t*)(base + L.newa);
     g.score = (int32_t*)(base + L.score);
     g.pred = (uint16_t*)(base + L.pred);
     g.cons = (uint16_t*)(base + L.cons);
@@ -105,23 +111,77 @@ __device__ __forceinline__ void decode4(const uint8_t* __restrict__ src, int len
     }
 }
 
-// Query profile (reference sisd_alignment_engine.cpp:101-108), g-normalised:
-// prof[c][j] = (decoder(c) == seq[j-1] ? m : n) - g for 1 <= j <= len, mismatch for the
-// padding columns, 0 for column 0 (its diagonal input is -inf anyway).
-__device__ __forceinline__ void build_profile(const Graph& g, int len, int cols, Scores sc) {
-    const int mm = sc.m - sc.g, nn = sc.n - sc.g;
-    for (int j = lane_id(); j < cols; j += 32) {
-        int letter = (j >= 1 && j <= len) ? g.seq[j - 1] : -1;
-#pragma unroll
-        for (int c = 0; c < kNumCodes; ++c)
-            g.prof[c * cols + j] = (int16_t)(j == 0 ? 0 : (letter == c ? mm : nn));
-    }
+// Query profile (reference sisd_alignment_engine.cpp:101-108), g-normalised and computed on the
+// fly: pf[j] = (letter(row) == colseq[j] ? m : n) - g.  A lane keeps the letter codes of its four
+// columns in one register (one byte each, 0..7).  XOR with the row's code replicated to four bytes
+// leaves a zero byte exactly where they match; 0x80 - 16*t moves that into bit 7 of each byte
+// (t <= 7, so no borrow crosses a byte); PRMT's sign-replicate mode widens bit 7 to a 16-bit mask
+// per column, which selects between the two packed constants.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ void profile_regs(uint32_t let4, uint32_t code, uint32_t mm2, uint32_t nn2,
+                                             uint32_t (&pf)[kNR]) {
+    const uint32_t t = let4 ^ (code * 0x01010101u);
+    const uint32_t z = 0x80808080u - 16u * t;
+    const uint32_t m01 = prmt(z, 0u, 0x9988u);
+    const uint32_t m23 = prmt(z, 0u, 0xBBAAu);
+    pf[0] = (m01 & mm2) | (~m01 & nn2);
+    pf[1] = (m23 & mm2) | (~m23 & nn2);
 }
 
 // ------------------------------------------------------------------------------------------
 // DP fill (reference sisd_alignment_engine.cpp:263-342, initialisation :158-159,197-211,
 // 229-239).  Lane l owns columns [4l, 4l+4) of each 128-column tile as two s16x2 registers.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+// Explicit address-space loads for the DP's inner loop: for the shared-memory tiers a 32-bit shared
+// address that ptxas cannot re-derive (it otherwise rebuilds the shared window base in every row).
+template <bool kSmem>
+struct Mem;
+template <>
+struct Mem<true> {
+    typedef uint32_t addr_t;
+    static __device__ __forceinline__ addr_t addr(const void* p) {
+        return opaque((uint32_t)__cvta_generic_to_shared(p));
+    }
+    static __device__ __forceinline__ uint32_t ld32(addr_t a) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ uint32_t ld16(addr_t a) {
+        uint32_t v;
+        asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+        return v;
+    }
+};
+template <>
+struct Mem<false> {
+    typedef const uint8_t* addr_t;
+    static __device__ __forceinline__ addr_t addr(const void* p) { return opaque_ptr((const uint8_t*)p); }
+    static __device__ __forceinline__ uint32_t ld32(addr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+    static __device__ __forceinline__ uint32_t ld16(addr_t a) { return *reinterpret_cast<const uint16_t*>(a); }
+};
+// DP rows in global memory, 8 bytes per lane (explicit .global: the pointers are opaque to ptxas)
+__device__ __forceinline__ void stg64(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ldg64(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
 
@@ -139,10 +199,8 @@ __device__ __forceinline__ void relax(uint32_t (&x)[kNR], const uint32_t (&p)[kN
 }
 
 // Horizontal pass: H^[i][j] = max(H^[i][j], H^[i][j-1]) == inclusive prefix max over columns.
-// In-lane over the 2*kNR columns, then a warp scan of the lane totals.
-// carry = prefix max of everything left of this tile (tile > 0) or kNegInf; returns the new carry.
-template <bool kOneTile>
-__device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry, int lane) {
+// In-lane over the 2*kNR columns; returns the lane total (its last column).
+__device__ __forceinline__ int scan_inlane(uint32_t (&x)[kNR]) {
     uint32_t runb = kNegInf2;   // running max broadcast to both halves
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
@@ -150,18 +208,25 @@ __device__ __forceinline__ int scan_row(uint32_t (&x)[kNR], int carry, int lane)
         x[r] = __vimax3_s16x2(x[r], t, runb);
         runb = __byte_perm(x[r], 0, 0x3232);                        // (x.hi, x.hi)
     }
-    int tot = hi16(x[kNR - 1]);
-    // shfl_up hands lanes below the shift their own value back, so no lane predicate is needed
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) tot = max(tot, __shfl_up_sync(kFull, tot, d));
-    int excl = __shfl_up_sync(kFull, tot, 1);
-    if (lane == 0) excl = kNegInf;
-    if (!kOneTile) excl = max(excl, carry);
-    const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
-#pragma unroll
-    for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
-    if (kOneTile) return kNegInf;
-    return max(__shfl_sync(kFull, tot, 31), carry);
+    return hi16(x[kNR - 1]);
+}
+
+// Exclusive prefix max of the lane totals across the warp, radix 4: four dependent shuffle rounds
+// (1, then 3 + 3 + 1 independent ones) instead of six.  shfl_up hands the lanes below the shift
+// their own value back, which is harmless once the sequence has been shifted by one lane.
+// `lane0_neg` is kNegInf2 on lane 0 and 0 elsewhere.
+__device__ __forceinline__ int warp_excl_max(int tot, uint32_t lane0_neg) {
+    int e = __shfl_up_sync(kFull, tot, 1);
+    e = lane0_neg ? kNegInf : e;
+    {
+        const int a1 = __shfl_up_sync(kFull, e, 1), a2 = __shfl_up_sync(kFull, e, 2), a3 = __shfl_up_sync(kFull, e, 3);
+        e = max(__vimax3_s32(e, a1, a2), a3);
+    }
+    {
+        const int b1 = __shfl_up_sync(kFull, e, 4), b2 = __shfl_up_sync(kFull, e, 8), b3 = __shfl_up_sync(kFull, e, 12);
+        e = max(__vimax3_s32(e, b1, b2), b3);
+    }
+    return max(e, __shfl_up_sync(kFull, e, 16));
 }
 
 struct EndCell {
@@ -170,81 +235,13 @@ struct EndCell {
     bool tie;  // two or more candidate rows share the best score (the rank order decides)
 };
 
-template <bool kSmem, bool kOneTile>
-__device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ H, int len, int tiles,
-                                        int type, Scores sc) {
-    const Graph g = make_graph<kSmem>(st);
+constexpr uint32_t kRowFast = 1u << 28;   // rowinfo: the only predecessor is the previous rank (or rank 0 without one)
+
+// End cell (reference :276-288,328-340): best last-column score over the candidate rows
+// (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
+__device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __restrict__ H, int n, int cols,
+                                            int len, int type) {
     const int lane = lane_id();
-    const int cols = kOneTile ? kTileCols : tiles * kTileCols;
-    const uint32_t g2 = bcast16(sc.g);
-    int16_t* Hl = H + lane * 4;
-    const int16_t* profl = g.prof + lane * 4;
-    const int n = g.n_nodes;
-
-    // row 0: H^[0][j] = 0
-    for (int t = 0; t < (kOneTile ? 1 : tiles); ++t)
-        *reinterpret_cast<uint2*>(Hl + t * kTileCols) = make_uint2(0u, 0u);
-
-    uint32_t prev[kNR];
-#pragma unroll
-    for (int r = 0; r < kNR; ++r) prev[r] = 0u;
-
-    uint32_t info_next = g.rowinfo[0];
-    for (int rk = 0; rk < n; ++rk) {
-        const uint32_t info = info_next;
-        info_next = g.rowinfo[rk + 1];   // one row ahead (the array has a spare entry)
-        const int ps = info & 0xffff;
-        const int pe = ps + ((info >> 16) & 0xff);
-        const int code = (info >> 24) & 7;
-        const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
-        int carry = kNegInf;
-        uint32_t x[kNR];
-        for (int t = 0; t < (kOneTile ? 1 : tiles); ++t) {
-            const unsigned toff = (unsigned)t * kTileCols;
-#pragma unroll
-            for (int r = 0; r < kNR; ++r) x[r] = kNegInf2;
-            uint32_t pf[kNR];
-            {
-                const uint2 q = *reinterpret_cast<const uint2*>(profl + (unsigned)code * (unsigned)cols + toff);
-                pf[0] = q.x; pf[1] = q.y;
-            }
-            if (ps == pe) {
-                // no predecessor: virtual row 0 (reference :300-301)
-                const uint32_t p[kNR] = {0u, 0u};
-                const uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
-                relax(x, p, left, pf, g2);
-            } else {
-#pragma unroll 1
-                for (int k = ps; k < pe; ++k) {
-                    const unsigned prow = g.prows[k];
-                    uint32_t p[kNR];
-                    if (kOneTile && prow == (unsigned)rk) {
-                        p[0] = prev[0]; p[1] = prev[1];
-                    } else {
-                        const uint2 q = *reinterpret_cast<const uint2*>(Hl + prow * (unsigned)cols + toff);
-                        p[0] = q.x; p[1] = q.y;
-                    }
-                    uint32_t left = __shfl_up_sync(kFull, p[kNR - 1], 1);
-                    if (lane == 0) {
-                        if (kOneTile || t == 0) left = kNegInf2;
-                        else left = (uint32_t)(uint16_t)H[prow * (unsigned)cols + toff - 1] << 16;
-                    }
-                    relax(x, p, left, pf, g2);
-                }
-            }
-            // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
-            // ROV pins it to 0 (reference :229-239)
-            if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
-            carry = scan_row<kOneTile>(x, carry, lane);
-            *reinterpret_cast<uint2*>(Hl + rowoff + toff) = make_uint2(x[0], x[1]);
-        }
-        if (kOneTile) { prev[0] = x[0]; prev[1] = x[1]; }
-        else __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
-    }
-    __syncwarp();
-
-    // end cell (reference :276-288,328-340): best last-column score over the candidate rows
-    // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
     int best = INT_MIN, brow = 0x7fffffff;
     for (int r = lane; r < n; r += 32) {
         const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
@@ -273,6 +270,149 @@ __device__ __noinline__ EndCell dp_fill(const GState& st, int16_t* __restrict__ 
     same = __reduce_add_sync(kFull, same);
     ec.tie = same > 1;
     return ec;
+}
+
+// One-tile fill (sequences of at most 127 symbols).  The previous row stays in registers together
+// with its exclusive prefix max, which is exactly the value the lane to the left holds in its
+// last column: rows whose only predecessor is the previous rank (rowinfo bit 28, the common case)
+// touch neither shared memory, nor the matrix, nor the shuffle unit before the scan.
+template <bool kSmem>
+__device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restrict__ H, int len, int type,
+                                            Scores sc) {
+    const Graph g = make_graph<kSmem>(st);
+    const int lane = lane_id();
+    // loop constants are made opaque so that ptxas keeps them in registers instead of
+    // re-deriving them in every row
+    const uint32_t g2 = opaque(bcast16(sc.g));
+    const uint32_t mm2 = opaque(bcast16(sc.m - sc.g)), nn2 = opaque(bcast16(sc.n - sc.g));
+    const int16_t* Hl = opaque_ptr(H + lane * 4);
+    const int n = g.n_nodes;
+    const uint32_t let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + lane * 4));
+    const uint32_t row0_left = opaque(lane == 0 ? kNegInf2 : 0u);
+    const uint32_t rov_mask = opaque((type == kROV && lane == 0) ? 0xffff0000u : 0xffffffffu);
+    typedef Mem<kSmem> M;
+    typename M::addr_t ri = M::addr(g.rowinfo);
+    const typename M::addr_t prows = M::addr(g.prows);
+
+    // row 0: H^[0][j] = 0
+    int16_t* Hrow = opaque_ptr(H + lane * 4);
+    stg64(Hrow, 0u, 0u);
+    uint32_t prev[kNR] = {0u, 0u};
+    uint32_t prev_left = row0_left;
+
+    uint32_t info_next = M::ld32(ri);
+    for (int rk = 0; rk < n; ++rk) {
+        const uint32_t info = info_next;
+        ri += 4;
+        info_next = M::ld32(ri);   // one row ahead (the array has a spare entry)
+        uint32_t pf[kNR];
+        profile_regs(let4, (info >> 24) & 7u, mm2, nn2, pf);
+        uint32_t x[kNR] = {kNegInf2, kNegInf2};
+        if (info & kRowFast) {
+            relax(x, prev, prev_left, pf, g2);
+        } else {
+            const int np = (info >> 16) & 0xff;
+            if (np == 0) {
+                // no predecessor: virtual row 0 (reference :300-301)
+                const uint32_t p[kNR] = {0u, 0u};
+                relax(x, p, row0_left, pf, g2);
+            } else {
+                typename M::addr_t pa = prows + 2u * (info & 0xffffu);
+#pragma unroll 1
+                for (int k = 0; k < np; ++k, pa += 2) {
+                    const unsigned prow = M::ld16(pa);
+                    if (prow == (unsigned)rk) {
+                        relax(x, prev, prev_left, pf, g2);
+                    } else {
+                        const uint2 q = ldg64(Hl + prow * (unsigned)kTileCols);
+                        const uint32_t p[kNR] = {q.x, q.y};
+                        uint32_t left = __shfl_up_sync(kFull, q.y, 1);
+                        left = row0_left ? kNegInf2 : left;
+                        relax(x, p, left, pf, g2);
+                    }
+                }
+            }
+        }
+        // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
+        // ROV pins it to 0 (reference :229-239)
+        x[0] &= rov_mask;
+        const int excl = warp_excl_max(scan_inlane(x), row0_left);
+        const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
+#pragma unroll
+        for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
+        Hrow += kTileCols;
+        stg64(Hrow, x[0], x[1]);
+        prev[0] = x[0]; prev[1] = x[1];
+        prev_left = cb;   // == last column of the lane to the left (kNegInf for lane 0)
+    }
+    __syncwarp();
+    return end_cell(g, H, n, kTileCols, len, type);
+}
+
+// Multi-tile fill: rows of up to `tiles` 128-column tiles, every predecessor row read back from the
+// matrix; `carry` threads the prefix max across the tiles of a row.
+template <bool kSmem>
+__device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restrict__ H, int len, int tiles,
+                                              int type, Scores sc) {
+    const Graph g = make_graph<kSmem>(st);
+    const int lane = lane_id();
+    const int cols = tiles * kTileCols;
+    const uint32_t g2 = bcast16(sc.g);
+    const uint32_t mm2 = bcast16(sc.m - sc.g), nn2 = bcast16(sc.n - sc.g);
+    int16_t* Hl = H + lane * 4;
+    const int n = g.n_nodes;
+
+    // row 0: H^[0][j] = 0
+    for (int t = 0; t < tiles; ++t)
+        *reinterpret_cast<uint2*>(Hl + t * kTileCols) = make_uint2(0u, 0u);
+    __syncwarp();
+
+    uint32_t info_next = g.rowinfo[0];
+    for (int rk = 0; rk < n; ++rk) {
+        const uint32_t info = info_next;
+        info_next = g.rowinfo[rk + 1];   // one row ahead (the array has a spare entry)
+        const int ps = info & 0xffff;
+        const int pe = ps + ((info >> 16) & 0xff);
+        const uint32_t code = (info >> 24) & 7u;
+        const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
+        int carry = kNegInf;
+        for (int t = 0; t < tiles; ++t) {
+            const unsigned toff = (unsigned)t * kTileCols;
+            uint32_t x[kNR] = {kNegInf2, kNegInf2};
+            uint32_t pf[kNR];
+            profile_regs(*reinterpret_cast<const uint32_t*>(g.colseq + toff + lane * 4), code, mm2, nn2, pf);
+            if (ps == pe) {
+                // no predecessor: virtual row 0 (reference :300-301)
+                const uint32_t p[kNR] = {0u, 0u};
+                const uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
+                relax(x, p, left, pf, g2);
+            } else {
+#pragma unroll 1
+                for (int k = ps; k < pe; ++k) {
+                    const unsigned prow = g.prows[k];
+                    const uint2 q = *reinterpret_cast<const uint2*>(Hl + prow * (unsigned)cols + toff);
+                    const uint32_t p[kNR] = {q.x, q.y};
+                    uint32_t left = __shfl_up_sync(kFull, q.y, 1);
+                    if (lane == 0) {
+                        if (t == 0) left = kNegInf2;
+                        else left = (uint32_t)(uint16_t)H[prow * (unsigned)cols + toff - 1] << 16;
+                    }
+                    relax(x, p, left, pf, g2);
+                }
+            }
+            if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
+            const int tot = scan_inlane(x);
+            const int excl = max(warp_excl_max(tot, lane == 0 ? kNegInf2 : 0u), carry);
+            const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);
+#pragma unroll
+            for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
+            carry = __shfl_sync(kFull, max(excl, tot), 31);
+            *reinterpret_cast<uint2*>(Hl + rowoff + toff) = make_uint2(x[0], x[1]);
+        }
+        __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
+    }
+    __syncwarp();
+    return end_cell(g, H, n, cols, len, type);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,7 +444,7 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
         if (i != 0 && j != 0) {
             // ---- speculative diagonal run through first predecessors
             // chain[k] = row of step k (chain[0] = i); fp[0] = 0 keeps the walk total
-            uint16_t* chain = g.stack;
+            uint16_t* chain = g.chain;
             {
                 int r = i;
                 if (lane == 0) chain[0] = (uint16_t)r;
@@ -846,8 +986,8 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
     const Graph g = make_graph<kSmem>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
-    uint16_t* anch = reinterpret_cast<uint16_t*>(g.prof);   // per position (profile is dead here)
-    uint16_t* newa = g.stack;                               // per new node, path order
+    uint16_t* anch = g.anch;   // per position (the row records are dead here)
+    uint16_t* newa = g.newa;   // per new node, path order
 
     // pass A (reverse): anchor of every position that holds a new node
     int carry = nb;   // block start of the next pre-existing column to the right (nb = none: the end)
@@ -942,7 +1082,6 @@ __device__ __noinline__ void build_rows(const GState& st) {
         const int total = __shfl_sync(kFull, off, 31);
         off = base + off - deg;
         if (r < n) {
-            g.rowinfo[r] = (uint32_t)off | ((uint32_t)deg << 16) | ((uint32_t)code << 24);
             int k = off, first = 0;
             for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
                 const int prow = g.n2r[g.e_src[e]] + 1;
@@ -950,6 +1089,9 @@ __device__ __noinline__ void build_rows(const GState& st) {
                 g.prows[k++] = (uint16_t)prow;
             }
             g.fp[r + 1] = (uint16_t)first;
+            // fast rows: the only predecessor row is the one the DP still holds in registers
+            const bool fast = (deg == 1 && first == r) || (deg == 0 && r == 0);
+            g.rowinfo[r] = (uint32_t)off | ((uint32_t)deg << 16) | ((uint32_t)code << 24) | (fast ? kRowFast : 0u);
         }
         base += total;
     }
@@ -1065,6 +1207,11 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
     if (lane == 0) {
         if (s.head) g.seq[0] = kCodeJ;
         if (s.tail) g.seq[len - 1] = kCodeO;
+        g.colseq[0] = 7;   // column 0 and the padding columns match no letter
+    }
+    {
+        const int ncols = (kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols) * kTileCols;
+        for (int j = len + 1 + lane; j < ncols; j += 32) g.colseq[j] = 7;
     }
     __syncwarp();
 
@@ -1076,17 +1223,15 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
         if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
-        build_profile(g, len, cols, sc);
-        __syncwarp();
-        EndCell ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
+        EndCell ec = kOneTile ? dp_fill_one<kSmem>(st, H, len, s.type, sc)
+                              : dp_fill_tiles<kSmem>(st, H, len, tiles, s.type, sc);
         if (ec.tie && !st.exact) {
             // the reference breaks this tie by rank in ITS order: derive it and redo the fill
             if (!topo_sort<kSmem>(st, caps)) return false;
             st.exact = true;
             build_rows<kSmem>(st);
-            build_profile(g, len, cols, sc);   // the sort used the profile area as scratch
-            __syncwarp();
-            ec = dp_fill<kSmem, kOneTile>(st, H, len, tiles, s.type, sc);
+            ec = kOneTile ? dp_fill_one<kSmem>(st, H, len, s.type, sc)
+                          : dp_fill_tiles<kSmem>(st, H, len, tiles, s.type, sc);
         }
         span = traceback<kSmem>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
         // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
@@ -1269,8 +1414,9 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     return n_cons;
 }
 
-template <bool kSmem, bool kOneTile, bool kLong>
-__global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
+// kMinBlocks = 3: the compact tier (27 warps / SM, <= 72 registers); 2: every other tier.
+template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks>
+__global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
@@ -1329,12 +1475,14 @@ __global__ void __launch_bounds__(256, 2) poa_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------
 // Host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, int blocks, int warps_per_block,
-                       size_t smem_bytes, cudaStream_t stream) {
+cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, bool compact, int blocks,
+                       int warps_per_block, size_t smem_bytes, cudaStream_t stream) {
     void (*k)(const Params) = nullptr;
+    if (warps_per_block * 32 > 288) return cudaErrorInvalidConfiguration;
     // one-tile tiers only ever run SHORT windows (the LONG driver is compiled out of them)
-    if (smem_graph) k = one_tile ? poa_kernel<true, true, false> : poa_kernel<true, false, true>;
-    else k = one_tile ? poa_kernel<false, true, false> : poa_kernel<false, false, true>;
+    if (smem_graph && one_tile && compact) k = poa_kernel<true, true, false, 3>;
+    else if (smem_graph) k = one_tile ? poa_kernel<true, true, false, 2> : poa_kernel<true, false, true, 2>;
+    else k = one_tile ? poa_kernel<false, true, false, 2> : poa_kernel<false, false, true, 2>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(P);

@@ -100,20 +100,24 @@ struct ArenaLayout {
     // edges
     uint32_t e_src, e_w, e_next;   // u16 each
     uint32_t al_pool;   // u16 [acap][kAlSlots]
-    // rows (rebuilt after every topological sort)
-    uint32_t rowinfo;   // u32 [ncap+1] by rank: prows offset (bits 0-15) | #preds (16-23) | letter code (24-26) | sink (27)
+    // rows (rebuilt by build_rows after every change of the order; dead while the order is being
+    // changed and once the last read has been aligned, so the sort / order-update / epilogue
+    // scratch aliases this region)
+    uint32_t rowinfo;   // u32 [ncap+1] by rank: prows offset (bits 0-15) | #preds (16-23) | letter code (24-26) | sink (27) | fast (28)
     uint32_t prows;     // u16 [ecap] predecessor DP rows in in-edge order
     uint32_t fp;        // u16 [ncap+1] first predecessor row of each DP row (0 = virtual row 0)
-    // scratch group (phases are disjoint in time)
-    uint32_t stack;     // u16 [scap]   DFS stack
-    uint32_t seq;       // u8  [lcap+1] current sequence (letter codes)
-    uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
-    uint32_t prof;      // i16 [7][tiles*128] query profile
-    uint32_t mark;      // u8  [ncap]   sort marks          (aliases prof)
-    uint32_t lists;     // u16 [32][kBulkList] bulk lists   (aliases prof)
-    uint32_t score;     // i32 [ncap]   epilogue           (aliases the scratch group)
+    uint32_t mark;      // u8  [ncap]   sort marks            (aliases rows)
+    uint32_t lists;     // u16 [32][kBulkList] bulk lists     (aliases rows)
+    uint32_t stack;     // u16 [scap]   DFS stack             (aliases rows)
+    uint32_t anch;      // u16 [lcap+1] order_update anchors  (aliases rows)
+    uint32_t newa;      // u16 [lcap+1] order_update          (aliases rows)
+    uint32_t score;     // i32 [ncap]   epilogue              (aliases rows)
     uint32_t pred;      // u16 [ncap]
     uint32_t cons;      // u16 [ncap]
+    // per-read scratch
+    uint32_t colseq;    // u8  [tiles*128] letter code of DP column j (= seq[j-1]); 7 = matches nothing
+    uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
+    uint32_t chain;     // u16 [40]     traceback: rows of a speculative diagonal run
     uint32_t total;
 };
 
@@ -132,27 +136,33 @@ __host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
     L.e_w = take(2u * c.ecap);
     L.e_next = take(2u * c.ecap);
     L.al_pool = take(2u * kAlSlots * c.acap);
+    const uint32_t rows0 = o;
     L.rowinfo = take(4u * (c.ncap + 1));
     L.prows = take(2u * c.ecap);
     L.fp = take(2u * (c.ncap + 1));
-    const uint32_t scratch0 = o;
-    L.stack = take(2u * c.scap);
-    L.seq = take(c.lcap + 1);
-    L.cur = take(2u * (c.lcap + 1));
-    L.prof = take(2u * kNumCodes * c.tiles * kTileCols);
     uint32_t end = o;
-    // toposort scratch over the (dead) profile
-    L.mark = L.prof;
-    L.lists = L.prof + align16(c.ncap);
-    uint32_t e2 = L.lists + 2u * 32 * kBulkList;
-    if (e2 > end) end = e2;
-    // epilogue scratch over the whole group
-    L.score = scratch0;
-    L.pred = L.score + align16(4u * c.ncap);
-    L.cons = L.pred + align16(2u * c.ncap);
-    uint32_t e3 = L.cons + align16(2u * c.ncap);
-    if (e3 > end) end = e3;
-    L.total = align16(end);
+    // topological-sort scratch over the (dead) rows
+    o = rows0;
+    L.mark = take(c.ncap);
+    L.lists = take(2u * 32 * kBulkList);
+    L.stack = take(2u * c.scap);
+    if (o > end) end = o;
+    // order-update scratch
+    o = rows0;
+    L.anch = take(2u * (c.lcap + 1));
+    L.newa = take(2u * (c.lcap + 1));
+    if (o > end) end = o;
+    // epilogue scratch
+    o = rows0;
+    L.score = take(4u * c.ncap);
+    L.pred = take(2u * c.ncap);
+    L.cons = take(2u * c.ncap);
+    if (o > end) end = o;
+    o = end;
+    L.colseq = take((uint32_t)c.tiles * kTileCols);
+    L.cur = take(2u * (c.lcap + 1));
+    L.chain = take(2u * 40);
+    L.total = align16(o);
     return L;
 }
 
