@@ -102,9 +102,11 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // (reference include/Window.hpp:30-33, src/Window.cpp:98,105,116,127).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void decode2(const uint8_t* __restrict__ src, int len, uint8_t* dst) {
+#pragma unroll 1
     for (int p = lane_id(); p < len; p += 32) dst[p] = (src[p >> 2] >> (6 - 2 * (p & 3))) & 3;
 }
 __device__ __forceinline__ void decode4(const uint8_t* __restrict__ src, int len, uint8_t* dst) {
+#pragma unroll 1
     for (int p = lane_id(); p < len; p += 32) {
         int v = (src[p >> 1] >> ((p & 1) ? 0 : 4)) & 15;
         dst[p] = v > 4 ? 4 : v;
@@ -235,7 +237,9 @@ struct EndCell {
     bool tie;  // two or more candidate rows share the best score (the rank order decides)
 };
 
-constexpr uint32_t kRowFast = 1u << 28;   // rowinfo: the only predecessor is the previous rank (or rank 0 without one)
+// rowinfo bits 28-30: every predecessor row lies 1, 2 or 3 rows back (bit d-1 set for distance d;
+// rank 0 without predecessor counts as distance 1: the virtual row 0).  0 = take the general path.
+constexpr int kRowNearShift = 28;
 
 // End cell (reference :276-288,328-340): best last-column score over the candidate rows
 // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
@@ -243,6 +247,7 @@ __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __res
                                             int len, int type) {
     const int lane = lane_id();
     int best = INT_MIN, brow = 0x7fffffff;
+#pragma unroll 1
     for (int r = lane; r < n; r += 32) {
         const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
         if (cand) {
@@ -262,11 +267,13 @@ __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __res
     ec.col = any ? len : 0;
     // does a second candidate reach the same score?  (only then does the exact order matter)
     int same = 0;
-    if (any)
+    if (any) {
+#pragma unroll 1
         for (int r = lane; r < n; r += 32) {
             const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
             if (cand && (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len] == best) ++same;
         }
+    }
     same = __reduce_add_sync(kFull, same);
     ec.tie = same > 1;
     return ec;
@@ -297,10 +304,12 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
     // row 0: H^[0][j] = 0
     int16_t* Hrow = opaque_ptr(H + lane * 4);
     stg64(Hrow, 0u, 0u);
-    uint32_t prev[kNR] = {0u, 0u};
-    uint32_t prev_left = row0_left;
+    // the last three rows and, for each, the value its left neighbour lane holds in its last column
+    uint32_t p1[kNR] = {0u, 0u}, p2[kNR] = {0u, 0u}, p3[kNR] = {0u, 0u};
+    uint32_t l1 = row0_left, l2 = row0_left, l3 = row0_left;
 
     uint32_t info_next = M::ld32(ri);
+#pragma unroll 1
     for (int rk = 0; rk < n; ++rk) {
         const uint32_t info = info_next;
         ri += 4;
@@ -308,8 +317,11 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
         uint32_t pf[kNR];
         profile_regs(let4, (info >> 24) & 7u, mm2, nn2, pf);
         uint32_t x[kNR] = {kNegInf2, kNegInf2};
-        if (info & kRowFast) {
-            relax(x, prev, prev_left, pf, g2);
+        const uint32_t near = info >> kRowNearShift;
+        if (near) {
+            if (near & 1u) relax(x, p1, l1, pf, g2);
+            if (near & 2u) relax(x, p2, l2, pf, g2);
+            if (near & 4u) relax(x, p3, l3, pf, g2);
         } else {
             const int np = (info >> 16) & 0xff;
             if (np == 0) {
@@ -322,7 +334,7 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
                 for (int k = 0; k < np; ++k, pa += 2) {
                     const unsigned prow = M::ld16(pa);
                     if (prow == (unsigned)rk) {
-                        relax(x, prev, prev_left, pf, g2);
+                        relax(x, p1, l1, pf, g2);
                     } else {
                         const uint2 q = ldg64(Hl + prow * (unsigned)kTileCols);
                         const uint32_t p[kNR] = {q.x, q.y};
@@ -342,8 +354,10 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
         for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
         Hrow += kTileCols;
         stg64(Hrow, x[0], x[1]);
-        prev[0] = x[0]; prev[1] = x[1];
-        prev_left = cb;   // == last column of the lane to the left (kNegInf for lane 0)
+        p3[0] = p2[0]; p3[1] = p2[1]; l3 = l2;
+        p2[0] = p1[0]; p2[1] = p1[1]; l2 = l1;
+        p1[0] = x[0]; p1[1] = x[1];
+        l1 = cb;   // == last column of the lane to the left (kNegInf for lane 0)
     }
     __syncwarp();
     return end_cell(g, H, n, kTileCols, len, type);
@@ -363,11 +377,13 @@ __device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restr
     const int n = g.n_nodes;
 
     // row 0: H^[0][j] = 0
+#pragma unroll 1
     for (int t = 0; t < tiles; ++t)
         *reinterpret_cast<uint2*>(Hl + t * kTileCols) = make_uint2(0u, 0u);
     __syncwarp();
 
     uint32_t info_next = g.rowinfo[0];
+#pragma unroll 1
     for (int rk = 0; rk < n; ++rk) {
         const uint32_t info = info_next;
         info_next = g.rowinfo[rk + 1];   // one row ahead (the array has a spare entry)
@@ -376,6 +392,7 @@ __device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restr
         const uint32_t code = (info >> 24) & 7u;
         const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
         int carry = kNegInf;
+#pragma unroll 1
         for (int t = 0; t < tiles; ++t) {
             const unsigned toff = (unsigned)t * kTileCols;
             uint32_t x[kNR] = {kNegInf2, kNegInf2};
@@ -440,24 +457,28 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
     int hij = (int)H[(unsigned)i * ucols + (unsigned)j];
     const int mm = sc.m - sc.g, nn = sc.n - sc.g;
     int steps = 0;
+    int chunk = 16;   // lanes used by the next speculative run: 8, 16 or 32
+#pragma unroll 1
     while ((type == kROV ? (i != 0 && j != 0) : (i != 0 || j != 0)) && steps++ < max_steps) {
         if (i != 0 && j != 0) {
-            // ---- speculative diagonal run through first predecessors
-            // chain[k] = row of step k (chain[0] = i); fp[0] = 0 keeps the walk total
-            uint16_t* chain = g.chain;
+            // ---- speculative diagonal run through first predecessors: lane k takes step k.
+            // Every lane walks the chain of first-predecessor rows (broadcast loads; fp[0] = 0
+            // keeps the walk total) and keeps the row of its own step.
+            int my_r = i;
             {
                 int r = i;
-                if (lane == 0) chain[0] = (uint16_t)r;
-#pragma unroll 4
-                for (int k = 1; k <= 32; ++k) {
-                    r = g.fp[r];
-                    if (lane == 0) chain[k] = (uint16_t)r;
+#pragma unroll 1
+                for (int k = 0; k < chunk; k += 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (lane == k + q) my_r = r;
+                        r = g.fp[r];
+                    }
                 }
             }
-            __syncwarp();
-            const int my_r = chain[lane], my_rn = chain[lane + 1];
+            const int my_rn = g.fp[my_r];
             const int jj = j - lane;
-            bool ok = my_r != 0 && jj >= 1;
+            bool ok = lane < chunk && my_r != 0 && jj >= 1;
             int hp = 0;
             if (ok) {
                 const int hc = (int)H[(unsigned)my_r * ucols + (unsigned)jj];
@@ -466,54 +487,88 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
                 ok = hc == hp + s;
             }
             const unsigned mask = __ballot_sync(kFull, ok);
-            const int run = __ffs(~mask) - 1;   // leading all-true lanes (mask == ~0 -> -1 -> 32)
-            const int nrun = run < 0 ? 32 : run;
-            if (nrun > 0) {
-                if (lane < nrun) g.cur[jj - 1] = g.r2n[my_r - 1];
+            const int nrun = __ffs(~mask) - 1;   // leading all-true lanes (mask == ~0 -> -1; only with chunk == 32)
+            const int run = nrun < 0 ? 32 : nrun;
+            if (run > 0) {
+                if (lane < run) g.cur[jj - 1] = g.r2n[my_r - 1];
                 if (span.last < 0) span.last = j - 1;
-                span.first = j - nrun;
-                i = __shfl_sync(kFull, my_rn, nrun - 1);
-                hij = __shfl_sync(kFull, hp, nrun - 1);
-                j -= nrun;
-                steps += nrun - 1;
+                span.first = j - run;
+                i = __shfl_sync(kFull, my_rn, run - 1);
+                hij = __shfl_sync(kFull, hp, run - 1);
+                j -= run;
+                steps += run - 1;
+                // a run that used every lane was probably cut by the chunk, not by the alignment
+                chunk = run == chunk ? min(2 * chunk, 32) : (run < 8 ? 8 : 16);
                 continue;
             }
+            chunk = 8;
         }
-        // ---- one general step
+        // ---- one general step.  Candidates in the reference's preference order map to lanes:
+        // lane k < 15: diagonal via in-edge k; lane 15 + k: vertical via in-edge k; lane 30:
+        // horizontal.  All candidate cells are fetched at once and the lowest matching lane wins.
         int ni = i, nj = j, nh = hij;
         bool found = false;
+        uint32_t info = 0;
+        int ps = 0, deg = 0;
         if (i != 0) {
-            const uint32_t info = g.rowinfo[i - 1];
-            const int ps = info & 0xffff, pe = ps + ((info >> 16) & 0xff);
+            info = g.rowinfo[i - 1];
+            ps = info & 0xffff;
+            deg = (info >> 16) & 0xff;
+        }
+        if (deg <= 15) {
+            const int slots = deg == 0 ? 1 : deg;   // no in-edge: virtual row 0 (reference :300-301)
+            int pi = i, h = 0;
+            bool match = false;
+            if (i != 0 && lane < 30) {
+                const int k = lane < 15 ? lane : lane - 15;
+                const bool diag = lane < 15;
+                if (k < slots && (!diag || j != 0)) {
+                    pi = deg == 0 ? 0 : (int)g.prows[ps + k];
+                    if (diag) {
+                        const int s = (((info >> 24) & 7) == g.seq[j - 1]) ? mm : nn;
+                        h = (int)H[(unsigned)pi * ucols + (unsigned)(j - 1)];
+                        match = hij == h + s;
+                    } else {
+                        h = (int)H[(unsigned)pi * ucols + (unsigned)j];
+                        match = hij == h + sc.g;
+                    }
+                }
+            } else if (lane == 30 && j != 0) {
+                h = (int)H[(unsigned)i * ucols + (unsigned)(j - 1)];
+                match = hij == h;
+            }
+            const unsigned mm_ = __ballot_sync(kFull, match);
+            if (mm_ != 0u) {
+                const int w = __ffs(mm_) - 1;
+                ni = __shfl_sync(kFull, pi, w);
+                nh = __shfl_sync(kFull, h, w);
+                nj = (w < 15 || w == 30) ? j - 1 : j;
+                found = true;
+            }
+        } else {
+            // very high in-degree: the serial walk, verbatim
+            const int pe = ps + deg;
             if (j != 0) {
                 const int s = (((info >> 24) & 7) == g.seq[j - 1]) ? mm : nn;
-                if (ps == pe) {
-                    const int h = (int)H[j - 1];
-                    if (hij == h + s) { ni = 0; nj = j - 1; nh = h; found = true; }
-                } else {
-                    for (int k = ps; k < pe; ++k) {
-                        const int pi = g.prows[k];
-                        const int h = (int)H[(unsigned)pi * ucols + (unsigned)(j - 1)];
-                        if (hij == h + s) { ni = pi; nj = j - 1; nh = h; found = true; break; }
-                    }
+#pragma unroll 1
+                for (int k = ps; k < pe; ++k) {
+                    const int pi = g.prows[k];
+                    const int h = (int)H[(unsigned)pi * ucols + (unsigned)(j - 1)];
+                    if (hij == h + s) { ni = pi; nj = j - 1; nh = h; found = true; break; }
                 }
             }
             if (!found) {
-                if (ps == pe) {
-                    const int h = (int)H[j];
-                    if (hij == h + sc.g) { ni = 0; nj = j; nh = h; found = true; }
-                } else {
-                    for (int k = ps; k < pe; ++k) {
-                        const int pi = g.prows[k];
-                        const int h = (int)H[(unsigned)pi * ucols + (unsigned)j];
-                        if (hij == h + sc.g) { ni = pi; nj = j; nh = h; found = true; break; }
-                    }
+#pragma unroll 1
+                for (int k = ps; k < pe; ++k) {
+                    const int pi = g.prows[k];
+                    const int h = (int)H[(unsigned)pi * ucols + (unsigned)j];
+                    if (hij == h + sc.g) { ni = pi; nj = j; nh = h; found = true; break; }
                 }
             }
-        }
-        if (!found && j != 0) {
-            const int h = (int)H[(unsigned)i * ucols + (unsigned)(j - 1)];
-            if (hij == h) { ni = i; nj = j - 1; nh = h; found = true; }
+            if (!found && j != 0) {
+                const int h = (int)H[(unsigned)i * ucols + (unsigned)(j - 1)];
+                if (hij == h) { ni = i; nj = j - 1; nh = h; found = true; }
+            }
         }
         if (!found) break;   // impossible for a consistent H; never spin
         if (nj != j) {
@@ -553,6 +608,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
     if (base + head_n + tail_n > caps.ncap) return false;
 
     // head chain [0, first) and tail chain (last, len): fresh nodes, allocated FIRST (:194-200)
+#pragma unroll 1
     for (int p = lane; p < len; p += 32) {
         int id = -1;
         if (p < first) id = base + p;
@@ -567,6 +623,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
     __syncwarp();
 
     // aligned part [first, last]: reuse / clique lookup / new node (:206-245)
+#pragma unroll 1
     for (int p0 = first; p0 <= last; p0 += 32) {
         const int p = p0 + lane;
         const bool act = p <= last;
@@ -584,6 +641,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
                 const int blk = g.al_blk[x];
                 if (blk != kNone) {
                     const int cnt = g.al_cnt[x];
+#pragma unroll 1
                     for (int k = 0; k < cnt; ++k) {
                         int a = g.al_pool[blk * kAlSlots + k];
                         if ((g.ninfo[a] & 7) == code) { res = a; need_new = false; break; }
@@ -615,6 +673,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
             g.al_blk[res] = (uint16_t)yb;
             const int cnt = g.al_cnt[x];
             // y.list = x.list + [x]; every a in x.list gets y appended; x.list += y (:228-240)
+#pragma unroll 1
             for (int k = 0; k < cnt; ++k) {
                 const int a = g.al_pool[xb * kAlSlots + k];
                 g.al_pool[yb * kAlSlots + k] = (uint16_t)a;
@@ -638,6 +697,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
     // edges (cur[p-1] -> cur[p]), weight 1+1 per traversal (:99-115,251-265,283-288).  Every
     // node of a sequence is distinct, so lanes touch disjoint in-lists / source nodes.
     int n_edges = g.n_edges;
+#pragma unroll 1
     for (int p0 = 0; p0 < len; p0 += 32) {
         const int p = p0 + lane;
         bool need_edge = false, sat = false;
@@ -648,6 +708,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len,
             if (p >= 1) {
                 src = g.cur[p - 1];
                 need_edge = true;
+#pragma unroll 1
                 for (int e = g.in_head[dst]; e != kNone; e = g.e_next[e]) {
                     if (g.e_src[e] == src) {
                         g.e_w[e] = (uint16_t)(g.e_w[e] + 2);
@@ -734,6 +795,7 @@ __device__ __forceinline__ bool s_push(const SortCtx& c, int x) {
     if (n >= kBulkMaxNodes) return false;
     // Lanes run concurrently: another lane may have overwritten this lane's claim on x, after
     // which s_ok no longer recognises x as already emitted here.  Never list a node twice.
+#pragma unroll 1
     for (int k = 1; k <= n; ++k)
         if (c.list[k] == x) return false;
     c.list[n + 1] = (uint16_t)x;
@@ -749,16 +811,20 @@ __device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
     if (c.mark[u] != 0) return false;
     const int mu = c.al_cnt[u];
     const int ublk = c.al_blk[u];
+#pragma unroll 1
     for (int k = 0; k < mu; ++k) {
         const int b = c.al_pool[ublk * kAlSlots + k];
         if (c.mark[b] != 0 || s_ok(c, b)) return false;
+#pragma unroll 1
         for (int e = c.in_head[b]; e != kNone; e = c.e_next[e])
             if (!s_ok(c, c.e_src[e])) return false;
     }
     unsigned long long chain = 0ull;   // up to kBulkDepth 16-bit node ids
     int nc = 0, w = u;
+#pragma unroll 1
     for (;;) {
         int next = -1;
+#pragma unroll 1
         for (int e = c.in_head[w]; e != kNone; e = c.e_next[e]) {
             const int s = c.e_src[e];
             if (s_ok(c, s)) continue;
@@ -775,6 +841,7 @@ __device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
     for (int q = nc - 1; q >= 0; --q)
         if (!s_push(c, (int)((chain >> (16 * q)) & 0xffffull))) return false;
     if (!s_push(c, u)) return false;
+#pragma unroll 1
     for (int k = 0; k < mu; ++k)
         if (!s_push(c, c.al_pool[ublk * kAlSlots + k])) return false;
     return true;
@@ -789,11 +856,13 @@ __device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
     const int nm = c.al_cnt[id];
     const int blk = c.al_blk[id];
     // targets: aligned nodes last-to-first (only their sources are explored), then the node itself
+#pragma unroll 1
     for (int t = nm - 1; t >= -1; --t) {
         const int x = t >= 0 ? (int)c.al_pool[blk * kAlSlots + t] : id;
         if (t >= 0 && (c.mark[x] != 0 || s_ok(c, x))) return 2;
         unsigned long long und = 0ull;   // up to three 16-bit node ids
         int n_und = 0;
+#pragma unroll 1
         for (int e = c.in_head[x]; e != kNone; e = c.e_next[e]) {
             const int s = c.e_src[e];
             if (s_ok(c, s)) continue;
@@ -808,6 +877,7 @@ __device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
         }
     }
     if (!s_push(c, id)) return 2;
+#pragma unroll 1
     for (int k = 0; k < nm; ++k)
         if (!s_push(c, c.al_pool[blk * kAlSlots + k])) return 2;
     return 1;
@@ -818,6 +888,7 @@ __device__ __forceinline__ int bulk_eval(const SortCtx& c) {
     if (r == 2) {   // withdraw the announcements of the abandoned replay
         const int n = c.list[0];
         const int me = (c.round << 5) | c.lane;
+#pragma unroll 1
         for (int k = 1; k <= n; ++k) {
             const int x = c.list[k];
             if (c.claim[x] == me) c.claim[x] = 0;
@@ -831,11 +902,13 @@ __device__ __forceinline__ int bulk_eval(const SortCtx& c) {
 __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int root, int& nr) {
     int sp = 0;
     g.stack[sp++] = (uint16_t)root;
+#pragma unroll 1
     while (sp != 0) {
         const int v = g.stack[sp - 1];
         bool valid = true;
         const int mv = g.mark[v];
         if ((mv & 3) != 2) {
+#pragma unroll 1
             for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
                 const int s = g.e_src[e];
                 if ((g.mark[s] & 3) != 2) {
@@ -848,6 +921,7 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
             const int cnt = g.al_cnt[v];
             const int blk = g.al_blk[v];
             if (check) {
+#pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
                     const int a = g.al_pool[blk * kAlSlots + k];
                     const int ma = g.mark[a];
@@ -863,6 +937,7 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
                 g.mark[v] = (uint8_t)((mv & 4) | 2);
                 if (check) {
                     g.r2n[nr++] = (uint16_t)v;
+#pragma unroll 1
                     for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * kAlSlots + k];
                 }
             } else {
@@ -880,12 +955,15 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
     const int lane = lane_id();
     const int n = g.n_nodes;
     uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) { g.mark[i] = 0; claim[i] = 0; }
     __syncwarp();
     uint16_t* list = g.lists + lane * kBulkList;
     int nr = 0, i0 = 0, round = 0;
+#pragma unroll 1
     while (i0 < n) {
         if (++round == 2047) {   // claim encoding would wrap: start over with clean claims
+#pragma unroll 1
             for (int i = lane; i < n; i += 32) claim[i] = 0;
             round = 1;
             __syncwarp();
@@ -898,6 +976,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
         c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool;
         c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
         c.emit_mask = 0u;
+#pragma unroll 1
         for (int pass = 0; pass < 5; ++pass) {
             bool changed = false;
             if (status == 2) {
@@ -920,6 +999,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
         if (status == 3 && list[0] > 1) cut = lane;          // it announced extras it will not emit
         if (status == 1) {
             const int cnt = list[0];
+#pragma unroll 1
             for (int k = 1; k <= cnt; ++k) {
                 const int x = list[k];
                 if (x == id) continue;
@@ -942,6 +1022,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
         }
         const int total = __shfl_sync(kFull, off, 31);
         off -= cnt;
+#pragma unroll 1
         for (int k = 1; k <= cnt; ++k) {
             const int x = list[k];
             g.r2n[nr + off + k - 1] = (uint16_t)x;
@@ -962,6 +1043,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
         }
     }
     __syncwarp();
+#pragma unroll 1
     for (int r = lane; r < n; r += 32) g.n2r[g.r2n[r]] = (uint16_t)r;
     __syncwarp();
     return true;
@@ -991,6 +1073,7 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
 
     // pass A (reverse): anchor of every position that holds a new node
     int carry = nb;   // block start of the next pre-existing column to the right (nb = none: the end)
+#pragma unroll 1
     for (int p0 = ((len - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
         const int p = p0 + lane;
         int colmin = 0x7fffffff;   // block start if column p is pre-existing (old node or new clique member)
@@ -1004,6 +1087,7 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
                 int mn = is_new ? 0x7fffffff : (int)g.n2r[v];
                 int mx = is_new ? -1 : (int)g.n2r[v];
                 const int blk = g.al_blk[v];
+#pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
                     const int m = g.al_pool[blk * kAlSlots + k];
                     if (m < nb) { const int r = g.n2r[m]; mn = min(mn, r); mx = max(mx, r); }
@@ -1025,6 +1109,7 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
     __syncwarp();
     // pass B (forward): compact the new nodes in path order, give them their ranks
     int K = 0;
+#pragma unroll 1
     for (int p0 = 0; p0 < len; p0 += 32) {
         const int p = p0 + lane;
         const int v = p < len ? (int)g.cur[p] : 0;
@@ -1041,9 +1126,11 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
     __syncwarp();
     // old nodes move right by the number of new nodes anchored at or before them
     if (K > 0) {
+#pragma unroll 1
         for (int v = lane; v < nb; v += 32) {
             const int r = g.n2r[v];
             int lo = 0, hi = K;   // first index with newa[idx] > r
+#pragma unroll 1
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if ((int)newa[mid] <= r) lo = mid + 1; else hi = mid;
@@ -1051,6 +1138,7 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
             g.n2r[v] = (uint16_t)(r + lo);
         }
         __syncwarp();
+#pragma unroll 1
         for (int v = lane; v < n; v += 32) g.r2n[g.n2r[v]] = (uint16_t)v;
     }
     __syncwarp();
@@ -1064,6 +1152,7 @@ __device__ __noinline__ void build_rows(const GState& st) {
     const int lane = lane_id();
     const int n = g.n_nodes;
     int base = 0;
+#pragma unroll 1
     for (int r0 = 0; r0 < n; r0 += 32) {
         const int r = r0 + lane;
         int v = 0, deg = 0, code = 0;
@@ -1083,15 +1172,20 @@ __device__ __noinline__ void build_rows(const GState& st) {
         off = base + off - deg;
         if (r < n) {
             int k = off, first = 0;
+            // near rows: every predecessor row is one of the three the DP still holds in registers
+            uint32_t near = (deg == 0 && r == 0) ? 1u : 0u;
+            bool far = deg == 0 && r != 0;
+#pragma unroll 1
             for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
                 const int prow = g.n2r[g.e_src[e]] + 1;
                 if (k == off) first = prow;
                 g.prows[k++] = (uint16_t)prow;
+                const int dist = r + 1 - prow;
+                if (dist >= 1 && dist <= 3) near |= 1u << (dist - 1); else far = true;
             }
+            if (far) near = 0u;
             g.fp[r + 1] = (uint16_t)first;
-            // fast rows: the only predecessor row is the one the DP still holds in registers
-            const bool fast = (deg == 1 && first == r) || (deg == 0 && r == 0);
-            g.rowinfo[r] = (uint32_t)off | ((uint32_t)deg << 16) | ((uint32_t)code << 24) | (fast ? kRowFast : 0u);
+            g.rowinfo[r] = (uint32_t)off | ((uint32_t)deg << 16) | ((uint32_t)code << 24) | (near << kRowNearShift);
         }
         base += total;
     }
@@ -1107,17 +1201,22 @@ __device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
     const int n = g.n_nodes;
     const int node = g.r2n[rank];
     // for every successor d of node: invalidate the other sources of d's in-edges
+#pragma unroll 1
     for (int d = 0; d < n; ++d) {
         bool succ = false;
+#pragma unroll 1
         for (int e = g.in_head[d]; e != kNone; e = g.e_next[e]) succ |= g.e_src[e] == node;
         if (!succ) continue;
+#pragma unroll 1
         for (int o = g.in_head[d]; o != kNone; o = g.e_next[o])
             if (g.e_src[o] != node) g.score[g.e_src[o]] = -1;
     }
     int max_score = 0, max_id = 0;
+#pragma unroll 1
     for (int r = rank + 1; r < n; ++r) {
         const int v = g.r2n[r];
         int sv = -1, pv = kNone;
+#pragma unroll 1
         for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
             const int s = g.e_src[e];
             const int ss = g.score[s];
@@ -1142,10 +1241,13 @@ __device__ __noinline__ int heaviest_bundle(const GState& st) {
     __syncwarp();
     if (lane == 0) {
         int best = 0;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) g.score[i] = -1;
+#pragma unroll 1
         for (int r = 0; r < n; ++r) {
             const int v = g.r2n[r];
             int sv = -1, pv = kNone;
+#pragma unroll 1
             for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
                 const int s = g.e_src[e];
                 const int w = g.e_w[e];
@@ -1157,11 +1259,14 @@ __device__ __noinline__ int heaviest_bundle(const GState& st) {
             if (g.score[best] < sv) best = v;
         }
         int guard = 0;
+#pragma unroll 1
         while ((g.ninfo[best] & 8) && guard++ <= n) best = branch_completion(g, g.n2r[best]);
         // backtrack (reversed in place afterwards)
         int k = 0;
+#pragma unroll 1
         while (g.pred[best] != kNone && k < n) { g.cons[k++] = (uint16_t)best; best = g.pred[best]; }
         g.cons[k++] = (uint16_t)best;
+#pragma unroll 1
         for (int a = 0, b = k - 1; a < b; ++a, --b) {
             uint16_t t = g.cons[a]; g.cons[a] = g.cons[b]; g.cons[b] = t;
         }
@@ -1199,6 +1304,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
     if (s.bytes) {
         if (s.nb == 2) decode2(s.bytes, s.len, dst); else decode4(s.bytes, s.len, dst);
     } else {
+#pragma unroll 1
         for (int p = lane; p < s.len; p += 32) {
             const char c = s.ascii[p];
             dst[p] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
@@ -1211,6 +1317,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
     }
     {
         const int ncols = (kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols) * kTileCols;
+#pragma unroll 1
         for (int j = len + 1 + lane; j < ncols; j += 32) g.colseq[j] = 7;
     }
     __syncwarp();
@@ -1240,6 +1347,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
         {
             const unsigned lines = (unsigned)(st.n_nodes + 1) * (unsigned)cols / 64u;   // 128-byte lines
             char* hb = reinterpret_cast<char*>(H);
+#pragma unroll 1
             for (unsigned l = lane; l < lines; l += 32)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(hb + (size_t)l * 128) : "memory");
         }
@@ -1269,6 +1377,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     const int n_arms = w.n_internal + w.n_pre + w.n_suf;
     // arms_added (reference :90,106,117,128)
     bool added = false;
+#pragma unroll 1
     for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
     added = __any_sync(kFull, added);
     if (!added) return -1;   // caller copies the draft (:150-152)
@@ -1283,18 +1392,21 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
         if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
+#pragma unroll 1
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
         if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
+#pragma unroll 1
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
         if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
+#pragma unroll 1
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
@@ -1308,6 +1420,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
     const int n = nc >= 2 ? nc - 2 : 0;
     const Graph v = make_graph<kSmem>(g);
+#pragma unroll 1
     for (int p = lane; p < n; p += 32) out[p] = code_to_char(v.ninfo[v.cons[p + 1]] & 7);
     return n;
 }
@@ -1322,6 +1435,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     const Scores sc = {P.lr_m, P.lr_n, P.lr_g};
     const int n_arms = w.n_internal + w.n_pre + w.n_suf;
     bool added = false;
+#pragma unroll 1
     for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
     added = __any_sync(kFull, added);
     if (!added) return -1;
@@ -1334,6 +1448,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     const uint64_t pcap = p_slot - 2 * (n_arms + 2);
 
     int n_cons = 0;
+#pragma unroll 1
     for (int round = 0; round < 2; ++round) {
         g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
         g.exact = true;
@@ -1355,6 +1470,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
             if (!add(s)) return -2;
         }
         s.ascii = nullptr; s.nb = 2;
+#pragma unroll 1
         for (int k = 0; k < n_arms; ++k) {   // :180-207 (container order, engine stays kNW)
             if (a[k].len == 0) continue;
             s.bytes = P.packed + a[k].off; s.len = a[k].len;
@@ -1373,10 +1489,12 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         uint16_t* msa = gv.n2r;
         if (lane == 0) {
             int id = 0;
+#pragma unroll 1
             for (int i = 0; i < gv.n_nodes; ++i) {
                 const int v = gv.r2n[i];
                 msa[v] = (uint16_t)id;
                 const int cnt = gv.al_cnt[v];
+#pragma unroll 1
                 for (int k = 0; k < cnt; ++k) msa[gv.r2n[++i]] = (uint16_t)id;
                 ++id;
             }
@@ -1384,14 +1502,18 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         // support counts (graph.cpp:542-564) -> reuse score (free after the bundle)
         uint32_t* sup = reinterpret_cast<uint32_t*>(gv.score);
         __syncwarp();
+#pragma unroll 1
         for (int c = lane; c < nc; c += 32) sup[c] = 0;
         __syncwarp();
+#pragma unroll 1
         for (int q = lane; q < gv.n_seq; q += 32) {
             const uint32_t b = pstart[q], e = pstart[q + 1];
             int c = 0;
+#pragma unroll 1
             for (uint32_t k = b; k < e; ++k) {
                 const int v = pnodes[k];
                 const int mv = msa[v];
+#pragma unroll 1
                 while (c < nc && msa[gv.cons[c]] < mv) ++c;
                 if (c >= nc) break;
                 if (msa[gv.cons[c]] == mv && (gv.ninfo[v] & 7) == (gv.ninfo[gv.cons[c]] & 7)) atomicAdd(&sup[c], 1u);
@@ -1400,6 +1522,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         __syncwarp();
         // curate (src/Window.cpp:239-254): ordered compaction
         int kept = 0;
+#pragma unroll 1
         for (int c0 = 0; c0 < nc; c0 += 32) {
             const int c = c0 + lane;
             const bool keep = c < nc && sup[c] >= thres;
@@ -1431,6 +1554,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 
+#pragma unroll 1
     for (;;) {
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(P.queue, 1u);
@@ -1452,6 +1576,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         }
         if (res == -1) {   // draft copy (reference :58-60,150-152,233-235)
             const uint8_t* src = P.packed + w.draft_off;
+#pragma unroll 1
             for (int p = lane; p < (int)w.draft_len; p += 32) {
                 int v = (src[p >> 1] >> ((p & 1) ? 0 : 4)) & 15;
                 out[p] = code_to_char(v > 4 ? 4 : v);
