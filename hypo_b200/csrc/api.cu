@@ -213,14 +213,14 @@ struct Tier {
 
 // Tc : SHORT windows whose sequences fit one 128-column tile and whose DAG stays small (the
 //      30 x 120 headline shape at ~1 % read error: 187 nodes on average, 209 at most in 3000
-//      windows): DAG in 8.4 KB of shared memory, 27 warps/SM (3 CTAs x 9 warps, <= 72 registers),
+//      windows): DAG in 8.3 KB of shared memory, 27 warps/SM (3 CTAs x 9 warps, <= 72 registers),
 //      previous DP row carried in registers.
 // T0 : same, larger DAG capacities, 18 warps/SM.  Windows that overflow Tc at run time land here.
 // T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 18 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 const Tier kTiers[] = {
-    {true, true, false, false, true, 224, 352, 112, 224, 127, 9, 3},
+    {true, true, false, false, true, 212, 328, 112, 212, 127, 9, 3},
     {true, true, false, false, false, 320, 576, 128, 320, 127, 9, 2},
     {true, false, false, false, false, 320, 576, 128, 320, 255, 9, 2},
     {true, false, true, false, false, 1024, 2048, 384, 1024, 1023, 4, 1},
@@ -335,7 +335,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         int blocks = g.sms * bps;
         uint64_t warps = (uint64_t)blocks * wpb;
         if (warps > n_work) { blocks = (int)((n_work + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
-        const uint64_t h_slot = ((uint64_t)(caps.ncap + 1) * caps.tiles * kTileCols + 63) & ~63ull;
+        const uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 63) & ~63ull;   // + dummy rows
         // keep the DP workspace bounded: shrink the grid if the slots would exceed ~24 GB
         while (warps * h_slot * 2 > (24ull << 30) && blocks > 1) { blocks = (blocks + 1) / 2; warps = (uint64_t)blocks * wpb; }
         CUDA_TRY(g.H.reserve(warps * h_slot * sizeof(int16_t)));

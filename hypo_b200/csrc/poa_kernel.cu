@@ -26,11 +26,11 @@ struct Graph {
     uint32_t* rowinfo;    // rank -> prows offset | #preds << 16 | letter code << 24 | sink << 27
     uint16_t* prows;      // predecessor DP rows, in-edge order
     uint16_t* fp;         // DP row -> first predecessor row
+    uint16_t* fp4;        // DP row -> fp applied four times
     uint16_t* stack;      // toposort scratch: DFS stack
     uint8_t* colseq;      // letter code of DP column j (colseq[0] and the padding columns hold 7)
     uint8_t* seq;         // current sequence, letter codes (= colseq + 1)
     uint16_t* cur;        // per sequence position: aligned node / resolved node
-    uint16_t* chain;      // traceback scratch
     uint8_t* mark;        // toposort scratch
     uint16_t* lists;      // toposort scratch: per-lane emission lists
     uint16_t* anch;       // order_update scratch
@@ -74,11 +74,11 @@ __device__ __forceinline__ Graph make_graph(const GState& st) {
     g.rowinfo = (uint32_t*)(base + L.rowinfo);
     g.prows = (uint16_t*)(base + L.prows);
     g.fp = (uint16_t*)(base + L.fp);
+    g.fp4 = (uint16_t*)(base + L.fp4);
     g.stack = (uint16_t*)(base + L.stack);
     g.colseq = base + L.colseq;
     g.seq = base + L.colseq + 1;
     g.cur = (uint16_t*)(base + L.cur);
-    g.chain = (uint16_t*)(base + L.chain);
     g.mark = base + L.mark;
     g.lists = (uint16_t*)(base + L.lists);
     g.anch = (uint16_t*)(base + L.anch);
@@ -279,10 +279,91 @@ __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __res
     return ec;
 }
 
-// One-tile fill (sequences of at most 127 symbols).  The previous row stays in registers together
-// with its exclusive prefix max, which is exactly the value the lane to the left holds in its
-// last column: rows whose only predecessor is the previous rank (rowinfo bit 28, the common case)
-// touch neither shared memory, nor the matrix, nor the shuffle unit before the scan.
+// One-tile fill (sequences of at most 127 symbols).  The last three rows stay in registers, each
+// with its exclusive prefix max, which is exactly the value the lane to the left holds in its last
+// column: rows whose predecessors all lie within three ranks (rowinfo bits 28-30; 97 % of the rows
+// of the 30 x 120 shape) touch neither shared memory, nor the matrix, nor the shuffle unit before
+// the scan.  The loop is unrolled by three so that the roles of the three register sets rotate
+// without moves; build_rows pads the row records with harmless dummy rows to a multiple of three.
+struct RowRegs {
+    uint32_t x[kNR];   // the lane's four columns
+    uint32_t left;     // last column of the lane to the left, in both halves (kNegInf2 on lane 0)
+};
+
+// Rare rows with a predecessor further back (or none at all): predecessor rows come from the matrix.
+// (inlined: a call inside the row loop costs 2 % even though it is almost never taken)
+#ifdef HYPO_FAR_NOINLINE
+#define HYPO_FAR_ATTR __noinline__
+#else
+#define HYPO_FAR_ATTR __forceinline__
+#endif
+template <bool kSmem>
+__device__ HYPO_FAR_ATTR uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint32_t info, int rk,
+                                        const int16_t* __restrict__ Hl, uint32_t p1a, uint32_t p1b,
+                                        uint32_t l1, uint32_t pf0, uint32_t pf1, uint32_t g2,
+                                        uint32_t row0_left) {
+    typedef Mem<kSmem> M;
+    uint32_t x[kNR] = {kNegInf2, kNegInf2};
+    const uint32_t pf[kNR] = {pf0, pf1};
+    const int np = (info >> 16) & 0xff;
+    if (np == 0) {
+        // no predecessor: virtual row 0 (reference :300-301)
+        const uint32_t p[kNR] = {0u, 0u};
+        relax(x, p, row0_left, pf, g2);
+    } else {
+        typename M::addr_t pa = prows + 2u * (info & 0xffffu);
+#pragma unroll 1
+        for (int k = 0; k < np; ++k, pa += 2) {
+            const unsigned prow = M::ld16(pa);
+            if (prow == (unsigned)rk) {
+                const uint32_t p[kNR] = {p1a, p1b};
+                relax(x, p, l1, pf, g2);
+            } else {
+                const uint2 q = ldg64(Hl + prow * (unsigned)kTileCols);
+                const uint32_t p[kNR] = {q.x, q.y};
+                uint32_t left = __shfl_up_sync(kFull, q.y, 1);
+                left = row0_left ? kNegInf2 : left;
+                relax(x, p, left, pf, g2);
+            }
+        }
+    }
+    return make_uint2(x[0], x[1]);
+}
+
+struct DpConst {
+    uint32_t g2, mm2, nn2, let4, row0_left, rov_mask;
+};
+
+// One DP row: d1/d2/d3 hold the rows 1/2/3 ranks back; the new row replaces d3.
+template <bool kSmem>
+__device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1, const RowRegs& d2, RowRegs& d3,
+                                       const DpConst& c, typename Mem<kSmem>::addr_t prows,
+                                       const int16_t* __restrict__ Hl, int16_t*& Hrow) {
+    uint32_t pf[kNR];
+    profile_regs(c.let4, (info >> 24) & 7u, c.mm2, c.nn2, pf);
+    uint32_t x[kNR] = {kNegInf2, kNegInf2};
+    const uint32_t near = info >> kRowNearShift;
+    if (near) {
+        if (near & 1u) relax(x, d1.x, d1.left, pf, c.g2);
+        if (near & 2u) relax(x, d2.x, d2.left, pf, c.g2);
+        if (near & 4u) relax(x, d3.x, d3.left, pf, c.g2);
+    } else {
+        const uint2 q = relax_far<kSmem>(prows, info, rk, Hl, d1.x[0], d1.x[1], d1.left, pf[0], pf[1], c.g2,
+                                         c.row0_left);
+        x[0] = q.x; x[1] = q.y;
+    }
+    // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
+    // ROV pins it to 0 (reference :229-239)
+    x[0] &= c.rov_mask;
+    const int excl = warp_excl_max(scan_inlane(x), c.row0_left);
+    const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
+    d3.x[0] = __vmaxs2(x[0], cb);
+    d3.x[1] = __vmaxs2(x[1], cb);
+    d3.left = cb;   // == last column of the lane to the left (kNegInf for lane 0)
+    Hrow += kTileCols;
+    stg64(Hrow, d3.x[0], d3.x[1]);
+}
+
 template <bool kSmem>
 __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restrict__ H, int len, int type,
                                             Scores sc) {
@@ -290,13 +371,15 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
     const int lane = lane_id();
     // loop constants are made opaque so that ptxas keeps them in registers instead of
     // re-deriving them in every row
-    const uint32_t g2 = opaque(bcast16(sc.g));
-    const uint32_t mm2 = opaque(bcast16(sc.m - sc.g)), nn2 = opaque(bcast16(sc.n - sc.g));
+    DpConst c;
+    c.g2 = opaque(bcast16(sc.g));
+    c.mm2 = opaque(bcast16(sc.m - sc.g));
+    c.nn2 = opaque(bcast16(sc.n - sc.g));
+    c.let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + lane * 4));
+    c.row0_left = opaque(lane == 0 ? kNegInf2 : 0u);
+    c.rov_mask = opaque((type == kROV && lane == 0) ? 0xffff0000u : 0xffffffffu);
     const int16_t* Hl = opaque_ptr(H + lane * 4);
     const int n = g.n_nodes;
-    const uint32_t let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + lane * 4));
-    const uint32_t row0_left = opaque(lane == 0 ? kNegInf2 : 0u);
-    const uint32_t rov_mask = opaque((type == kROV && lane == 0) ? 0xffff0000u : 0xffffffffu);
     typedef Mem<kSmem> M;
     typename M::addr_t ri = M::addr(g.rowinfo);
     const typename M::addr_t prows = M::addr(g.prows);
@@ -304,61 +387,36 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
     // row 0: H^[0][j] = 0
     int16_t* Hrow = opaque_ptr(H + lane * 4);
     stg64(Hrow, 0u, 0u);
-    // the last three rows and, for each, the value its left neighbour lane holds in its last column
-    uint32_t p1[kNR] = {0u, 0u}, p2[kNR] = {0u, 0u}, p3[kNR] = {0u, 0u};
-    uint32_t l1 = row0_left, l2 = row0_left, l3 = row0_left;
+    RowRegs A, B, C;
+    A.x[0] = A.x[1] = 0u; A.left = c.row0_left;
+    B = A; C = A;
 
-    uint32_t info_next = M::ld32(ri);
+    uint32_t info = M::ld32(ri);
+#ifdef HYPO_DP_UNROLL3
+    // Rotating the roles of the three register sets by unrolling saves nine moves per row, but the
+    // tripled loop body no longer fits the L0 instruction cache next to the other phases (measured:
+    // -13 % instructions, +10 % time), so the rolled loop below is the default.
+#pragma unroll 1
+    for (int rk = 0; rk < n; rk += 3) {
+        // three rows per trip (records n .. n+2 are dummies), the next trip's first record ahead
+        const uint32_t i0 = info, i1 = M::ld32(ri + 4), i2 = M::ld32(ri + 8);
+        info = M::ld32(ri + 12);
+        ri += 12;
+        dp_row<kSmem>(i0, rk, A, B, C, c, prows, Hl, Hrow);       // new row -> C
+        dp_row<kSmem>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow);   // new row -> B
+        dp_row<kSmem>(i2, rk + 2, B, C, A, c, prows, Hl, Hrow);   // new row -> A
+    }
+#else
 #pragma unroll 1
     for (int rk = 0; rk < n; ++rk) {
-        const uint32_t info = info_next;
+        const uint32_t i0 = info;
         ri += 4;
-        info_next = M::ld32(ri);   // one row ahead (the array has a spare entry)
-        uint32_t pf[kNR];
-        profile_regs(let4, (info >> 24) & 7u, mm2, nn2, pf);
-        uint32_t x[kNR] = {kNegInf2, kNegInf2};
-        const uint32_t near = info >> kRowNearShift;
-        if (near) {
-            if (near & 1u) relax(x, p1, l1, pf, g2);
-            if (near & 2u) relax(x, p2, l2, pf, g2);
-            if (near & 4u) relax(x, p3, l3, pf, g2);
-        } else {
-            const int np = (info >> 16) & 0xff;
-            if (np == 0) {
-                // no predecessor: virtual row 0 (reference :300-301)
-                const uint32_t p[kNR] = {0u, 0u};
-                relax(x, p, row0_left, pf, g2);
-            } else {
-                typename M::addr_t pa = prows + 2u * (info & 0xffffu);
-#pragma unroll 1
-                for (int k = 0; k < np; ++k, pa += 2) {
-                    const unsigned prow = M::ld16(pa);
-                    if (prow == (unsigned)rk) {
-                        relax(x, p1, l1, pf, g2);
-                    } else {
-                        const uint2 q = ldg64(Hl + prow * (unsigned)kTileCols);
-                        const uint32_t p[kNR] = {q.x, q.y};
-                        uint32_t left = __shfl_up_sync(kFull, q.y, 1);
-                        left = row0_left ? kNegInf2 : left;
-                        relax(x, p, left, pf, g2);
-                    }
-                }
-            }
-        }
-        // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
-        // ROV pins it to 0 (reference :229-239)
-        x[0] &= rov_mask;
-        const int excl = warp_excl_max(scan_inlane(x), row0_left);
-        const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
-#pragma unroll
-        for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
-        Hrow += kTileCols;
-        stg64(Hrow, x[0], x[1]);
-        p3[0] = p2[0]; p3[1] = p2[1]; l3 = l2;
-        p2[0] = p1[0]; p2[1] = p1[1]; l2 = l1;
-        p1[0] = x[0]; p1[1] = x[1];
-        l1 = cb;   // == last column of the lane to the left (kNegInf for lane 0)
+        info = M::ld32(ri);   // one row ahead (the array has spare entries)
+        dp_row<kSmem>(i0, rk, A, B, C, c, prows, Hl, Hrow);   // new row -> C
+        const RowRegs t = C;
+        C = B; B = A; A = t;
     }
+#endif
     __syncwarp();
     return end_cell(g, H, n, kTileCols, len, type);
 }
@@ -457,23 +515,27 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
     int hij = (int)H[(unsigned)i * ucols + (unsigned)j];
     const int mm = sc.m - sc.g, nn = sc.n - sc.g;
     int steps = 0;
-    int chunk = 16;   // lanes used by the next speculative run: 8, 16 or 32
+    int chunk = 32;   // lanes used by the next speculative run: 8, 16 or 32
+    bool spec = true;  // false right after a run that was cut short: its last test already failed
 #pragma unroll 1
     while ((type == kROV ? (i != 0 && j != 0) : (i != 0 || j != 0)) && steps++ < max_steps) {
-        if (i != 0 && j != 0) {
-            // ---- speculative diagonal run through first predecessors: lane k takes step k.
-            // Every lane walks the chain of first-predecessor rows (broadcast loads; fp[0] = 0
-            // keeps the walk total) and keeps the row of its own step.
+        if (spec && i != 0 && j != 0) {
+            // ---- speculative diagonal run through first predecessors: lane k takes step k, i.e.
+            // needs row fp^k(i).  k = 4a + b: a jumps of four (fp4), then b single steps
+            // (fp[0] = fp4[0] = 0 keeps the walk total).
             int my_r = i;
             {
-                int r = i;
+                const int a = lane >> 2, b = lane & 3;
+                const int na = (chunk >> 2) - 1;
 #pragma unroll 1
-                for (int k = 0; k < chunk; k += 4) {
+                for (int s = 0; s < na; ++s) {
+                    const int t = g.fp4[my_r];
+                    if (a > s) my_r = t;
+                }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (lane == k + q) my_r = r;
-                        r = g.fp[r];
-                    }
+                for (int s = 0; s < 3; ++s) {
+                    const int t = g.fp[my_r];
+                    if (b > s) my_r = t;
                 }
             }
             const int my_rn = g.fp[my_r];
@@ -498,11 +560,17 @@ __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __res
                 j -= run;
                 steps += run - 1;
                 // a run that used every lane was probably cut by the chunk, not by the alignment
+                // a cut below the chunk size means the next cell fails this very test (or the
+                // run reached row 0 / column 0): take the general step directly
+#ifndef HYPO_TB_NOSKIP
+                spec = run == chunk;
+#endif
                 chunk = run == chunk ? min(2 * chunk, 32) : (run < 8 ? 8 : 16);
                 continue;
             }
             chunk = 8;
         }
+        spec = true;
         // ---- one general step.  Candidates in the reference's preference order map to lanes:
         // lane k < 15: diagonal via in-edge k; lane 15 + k: vertical via in-edge k; lane 30:
         // horizontal.  All candidate cells are fetched at once and the lowest matching lane wins.
@@ -1189,7 +1257,13 @@ __device__ __noinline__ void build_rows(const GState& st) {
         }
         base += total;
     }
-    if (lane == 0) { g.rowinfo[n] = 0u; g.fp[0] = 0; }
+    // dummy records n .. n+2 (the one-tile fill works in trips of three rows) + the one read ahead
+    if (lane < 4) g.rowinfo[n + lane] = 1u << kRowNearShift;
+    if (lane == 0) { g.fp[0] = 0; g.fp4[0] = 0; }
+    __syncwarp();
+    // jump pointers for the traceback's speculative runs
+#pragma unroll 1
+    for (int r = 1 + lane; r <= n; r += 32) g.fp4[r] = g.fp[g.fp[g.fp[g.fp[r]]]];
     __syncwarp();
 }
 

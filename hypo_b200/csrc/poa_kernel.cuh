@@ -103,9 +103,10 @@ struct ArenaLayout {
     // rows (rebuilt by build_rows after every change of the order; dead while the order is being
     // changed and once the last read has been aligned, so the sort / order-update / epilogue
     // scratch aliases this region)
-    uint32_t rowinfo;   // u32 [ncap+1] by rank: prows offset (bits 0-15) | #preds (16-23) | letter code (24-26) | sink (27) | fast (28)
+    uint32_t rowinfo;   // u32 [ncap+4] by rank: prows offset (bits 0-15) | #preds (16-23) | letter code (24-26) | sink (27) | fast (28)
     uint32_t prows;     // u16 [ecap] predecessor DP rows in in-edge order
     uint32_t fp;        // u16 [ncap+1] first predecessor row of each DP row (0 = virtual row 0)
+    uint32_t fp4;       // u16 [ncap+1] fp applied four times (traceback jump pointers)
     uint32_t mark;      // u8  [ncap]   sort marks            (aliases rows)
     uint32_t lists;     // u16 [32][kBulkList] bulk lists     (aliases rows)
     uint32_t stack;     // u16 [scap]   DFS stack             (aliases rows)
@@ -117,7 +118,6 @@ struct ArenaLayout {
     // per-read scratch
     uint32_t colseq;    // u8  [tiles*128] letter code of DP column j (= seq[j-1]); 7 = matches nothing
     uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
-    uint32_t chain;     // u16 [40]     traceback: rows of a speculative diagonal run
     uint32_t total;
 };
 
@@ -137,9 +137,10 @@ __host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
     L.e_next = take(2u * c.ecap);
     L.al_pool = take(2u * kAlSlots * c.acap);
     const uint32_t rows0 = o;
-    L.rowinfo = take(4u * (c.ncap + 1));
+    L.rowinfo = take(4u * (c.ncap + 4));
     L.prows = take(2u * c.ecap);
     L.fp = take(2u * (c.ncap + 1));
+    L.fp4 = take(2u * (c.ncap + 1));
     uint32_t end = o;
     // topological-sort scratch over the (dead) rows
     o = rows0;
@@ -161,7 +162,6 @@ __host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
     o = end;
     L.colseq = take((uint32_t)c.tiles * kTileCols);
     L.cur = take(2u * (c.lcap + 1));
-    L.chain = take(2u * 40);
     L.total = align16(o);
     return L;
 }
