@@ -48,11 +48,42 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=12000, help="windows timed on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mix", default="", choices=["", "pipeline"],
+                    help="pipeline: window shapes as the reference CLI produces them (SURVEY.md §6: draft length "
+                         "p50 9 / p90 68 / max 100, 10-48 arms, 8 %% of the windows with prefix/suffix arms) "
+                         "instead of one fixed shape; --windows is the total")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.mix == "pipeline":
+        return (f"synthetic {a.windows} windows/GPU, pipeline shape mix (draft 6-100 bp, median 9; 11-48 arms; "
+                f"8 % with prefix/suffix arms; SHORT, err {a.err})")
     return f"synthetic {a.windows} windows/GPU ({a.arms} reads x {a.length} bp, {a.kind}, SHORT, err {a.err})"
+
+
+# (draft length, weight) and (arms, weight): the two datasets measured in SURVEY.md §6
+PIPELINE_LEN = ((6, 0.20), (9, 0.32), (14, 0.14), (25, 0.12), (40, 0.08), (68, 0.08), (100, 0.06))
+PIPELINE_ARMS = ((11, 0.30), (16, 0.15), (30, 0.15), (39, 0.25), (48, 0.15))
+
+
+def make_batch(a, seed):
+    """The synthetic shard of one rank (one fixed shape, or the pipeline shape mix)."""
+    from hypo_b200.batch import concat_batches
+    from hypo_b200.hostlib import synth_batch
+    if a.mix != "pipeline":
+        return synth_batch(seed, a.windows, a.length, a.arms, a.kind, a.err)
+    parts, k = [], 0
+    for ln, wl in PIPELINE_LEN:
+        for na, wa in PIPELINE_ARMS:
+            for kind, wk in (("internal", 0.92), ("mixed", 0.08)):
+                n = int(round(a.windows * wl * wa * wk))
+                k += 1
+                if n > 0:
+                    parts.append(synth_batch(seed + 104729 * k, n, ln, na, kind, a.err))
+    b = concat_batches(parts, {"mix": "pipeline"})
+    perm = np.random.default_rng(seed).permutation(b.n_win)
+    return b.select(perm)
 
 
 class ClockSampler:
@@ -143,7 +174,9 @@ def run_reference(a):
         return
     from hypo_b200.hostlib import synth_batch
     n_gen = max(a.cpu_sample, 1000)
-    batch = synth_batch(a.seed, n_gen, a.length, a.arms, a.kind, a.err)
+    gen = argparse.Namespace(**vars(a))
+    gen.windows = n_gen   # the reference arm times a bounded sample of the same workload
+    batch = make_batch(gen, a.seed)
     # bounded sample per step so that steps+warmup finish within minutes
     per_step = max(500, min(a.cpu_sample, n_gen) // 3)
     vals = []
@@ -188,7 +221,7 @@ def main():
     native.init(SCORES, local)
 
     # ---- synthetic shard of this rank --------------------------------------------------
-    batch = synth_batch(a.seed + 7919 * rank, a.windows, a.length, a.arms, a.kind, a.err)
+    batch = make_batch(a, a.seed + 7919 * rank)
     n_win, n_arms = batch.n_win, batch.n_arms
     bp = batch.polished_bp
     bound = batch.out_bound()
@@ -315,7 +348,8 @@ def main():
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("windows") == a.windows and tj.get("arms") == a.arms and tj.get("length") == a.length:
+            if (not a.mix and tj.get("windows") == a.windows and tj.get("arms") == a.arms
+                    and tj.get("length") == a.length):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass

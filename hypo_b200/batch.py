@@ -9,7 +9,7 @@ reference's PackedSeq (reference src/PackedSeq.cpp:45-48,58-88):
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Iterable, List, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 
@@ -183,6 +183,23 @@ def build_batch(specs: Iterable[WindowSpec]) -> WindowBatch:
     # 16 bytes of slack so vectorised device loads may over-read the last arm safely
     packed = np.concatenate([packed, np.zeros(16, np.uint8)])
     return WindowBatch(win, arms, packed)
+
+
+def concat_batches(batches: Sequence[WindowBatch], meta: Optional[dict] = None) -> WindowBatch:
+    """One batch holding the windows of all `batches` in order (descriptors re-based onto one
+    arm table and one packed slab)."""
+    wins, arms, packed = [], [], []
+    arm_base, byte_base = 0, 0
+    for b in batches:
+        w = b.win.copy()
+        a = b.arms.copy()
+        w["first_arm"] += arm_base
+        w["draft_off"] += byte_base
+        a["off"] += byte_base
+        wins.append(w); arms.append(a); packed.append(b.packed)
+        arm_base += b.n_arms
+        byte_base += int(b.packed.size)
+    return WindowBatch(np.concatenate(wins), np.concatenate(arms), np.concatenate(packed), dict(meta or {}))
 
 
 def split_consensus(out: np.ndarray, out_off: np.ndarray) -> List[str]:

@@ -19,7 +19,7 @@
 #include "poa_kernel.cuh"
 
 namespace hypo_b200 {
-cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, bool compact, int blocks,
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream);
 }
 
@@ -219,6 +219,8 @@ struct Tier {
 // T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 18 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
+// The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
+// (poa_kernel.cuh: fixed_caps); they are repeated here only as documentation and checked at start-up.
 const Tier kTiers[] = {
     {true, true, false, false, true, 212, 328, 112, 212, 127, 9, 3},
     {true, true, false, false, false, 320, 576, 128, 320, 127, 9, 2},
@@ -362,7 +364,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         P.sr_m = g.scores[0]; P.sr_n = g.scores[1]; P.sr_g = g.scores[2];
         P.lr_m = g.scores[3]; P.lr_n = g.scores[4]; P.lr_g = g.scores[5];
         CUDA_TRY(cudaEventRecord(g.ev0, stream));
-        CUDA_TRY(launch_poa(P, T.smem_graph, T.one_tile, T.compact, blocks, wpb, smem, stream));
+        CUDA_TRY(launch_poa(P, t, T.smem_graph, T.one_tile, blocks, wpb, smem, stream));
         CUDA_TRY(cudaEventRecord(g.ev1, stream));
         ++g.launches;
         CUDA_TRY(cudaMemcpyAsync(h_ovf_count, d_over, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -434,6 +436,13 @@ int hypo_gpu_init(const int8_t scores[6], int device) {
     g.device = device;
     g.sms = prop.multiProcessorCount;
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int t = 0; t < kNumFixedTiers; ++t) {   // the table must agree with the kernels' constants
+        const Caps c = fixed_caps(t);
+        const Tier& T = kTiers[t];
+        if (c.ncap != T.ncap || c.ecap != T.ecap || c.acap != T.acap || c.scap != T.scap || c.lcap != T.lcap ||
+            T.from_bounds || !T.smem_graph)
+            return fail(HYPO_E_ARG, "internal: tier table row %d disagrees with fixed_caps", t);
+    }
     memcpy(g.scores, scores, 6);
     g.launches = 0;
     g.init = true;

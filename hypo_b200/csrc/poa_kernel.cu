@@ -55,10 +55,9 @@ struct GState {
 };
 
 template <bool kSmem>
-__device__ __forceinline__ Graph make_graph(const GState& st) {
+__device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout& L) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* base = kSmem ? (smem + st.sbase) : st.gbase;
-    const ArenaLayout& L = st.L;
     Graph g;
     g.ninfo = base + L.ninfo;
     g.al_cnt = base + L.al_cnt;
@@ -88,6 +87,29 @@ __device__ __forceinline__ Graph make_graph(const GState& st) {
     g.cons = (uint16_t*)(base + L.cons);
     g.n_nodes = st.n_nodes; g.n_edges = st.n_edges; g.n_al = st.n_al; g.n_seq = st.n_seq;
     return g;
+}
+
+// kTier >= 0: a tier with compile-time capacities (every offset folds into an immediate and the
+// layout never has to be fetched from the per-thread GState); kTier < 0: layout from st.L.
+template <bool kSmem, int kTier>
+__device__ __forceinline__ Graph make_graph(const GState& st) {
+    if constexpr (kTier >= 0) {
+        constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
+        return bind_graph<kSmem>(st, L);
+    } else {
+        return bind_graph<kSmem>(st, st.L);
+    }
+}
+
+// The capacities a phase checks against: constants for the fixed tiers.
+template <int kTier>
+__device__ __forceinline__ Caps tier_caps(const Caps& dyn) {
+    if constexpr (kTier >= 0) {
+        constexpr Caps c = fixed_caps(kTier);
+        return c;
+    } else {
+        return dyn;
+    }
 }
 
 struct Scores {
@@ -297,7 +319,7 @@ struct RowRegs {
 #else
 #define HYPO_FAR_ATTR __forceinline__
 #endif
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ HYPO_FAR_ATTR uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint32_t info, int rk,
                                         const int16_t* __restrict__ Hl, uint32_t p1a, uint32_t p1b,
                                         uint32_t l1, uint32_t pf0, uint32_t pf1, uint32_t g2,
@@ -335,7 +357,7 @@ struct DpConst {
 };
 
 // One DP row: d1/d2/d3 hold the rows 1/2/3 ranks back; the new row replaces d3.
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1, const RowRegs& d2, RowRegs& d3,
                                        const DpConst& c, typename Mem<kSmem>::addr_t prows,
                                        const int16_t* __restrict__ Hl, int16_t*& Hrow) {
@@ -348,7 +370,7 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
         if (near & 2u) relax(x, d2.x, d2.left, pf, c.g2);
         if (near & 4u) relax(x, d3.x, d3.left, pf, c.g2);
     } else {
-        const uint2 q = relax_far<kSmem>(prows, info, rk, Hl, d1.x[0], d1.x[1], d1.left, pf[0], pf[1], c.g2,
+        const uint2 q = relax_far<kSmem, kTier>(prows, info, rk, Hl, d1.x[0], d1.x[1], d1.left, pf[0], pf[1], c.g2,
                                          c.row0_left);
         x[0] = q.x; x[1] = q.y;
     }
@@ -364,10 +386,10 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
     stg64(Hrow, d3.x[0], d3.x[1]);
 }
 
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restrict__ H, int len, int type,
                                             Scores sc) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     // loop constants are made opaque so that ptxas keeps them in registers instead of
     // re-deriving them in every row
@@ -402,9 +424,9 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
         const uint32_t i0 = info, i1 = M::ld32(ri + 4), i2 = M::ld32(ri + 8);
         info = M::ld32(ri + 12);
         ri += 12;
-        dp_row<kSmem>(i0, rk, A, B, C, c, prows, Hl, Hrow);       // new row -> C
-        dp_row<kSmem>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow);   // new row -> B
-        dp_row<kSmem>(i2, rk + 2, B, C, A, c, prows, Hl, Hrow);   // new row -> A
+        dp_row<kSmem, kTier>(i0, rk, A, B, C, c, prows, Hl, Hrow);       // new row -> C
+        dp_row<kSmem, kTier>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow);   // new row -> B
+        dp_row<kSmem, kTier>(i2, rk + 2, B, C, A, c, prows, Hl, Hrow);   // new row -> A
     }
 #else
 #pragma unroll 1
@@ -412,7 +434,7 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
         const uint32_t i0 = info;
         ri += 4;
         info = M::ld32(ri);   // one row ahead (the array has spare entries)
-        dp_row<kSmem>(i0, rk, A, B, C, c, prows, Hl, Hrow);   // new row -> C
+        dp_row<kSmem, kTier>(i0, rk, A, B, C, c, prows, Hl, Hrow);   // new row -> C
         const RowRegs t = C;
         C = B; B = A; A = t;
     }
@@ -423,10 +445,10 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
 
 // Multi-tile fill: rows of up to `tiles` 128-column tiles, every predecessor row read back from the
 // matrix; `carry` threads the prefix max across the tiles of a row.
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restrict__ H, int len, int tiles,
                                               int type, Scores sc) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int cols = tiles * kTileCols;
     const uint32_t g2 = bcast16(sc.g);
@@ -503,10 +525,10 @@ struct AlnSpan {
     int first, last;
 };
 
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __restrict__ H, int cols,
                                           EndCell ec, int type, Scores sc, int max_steps) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     int i = ec.row, j = ec.col;
     AlnSpan span;
@@ -663,10 +685,11 @@ __device__ __forceinline__ void init_node(const Graph& g, int id, int code) {
     g.al_blk[id] = kNone;
 }
 
-template <bool kSmem>
-__device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps, int len, AlnSpan span,
+template <bool kSmem, int kTier>
+__device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int len, AlnSpan span,
                                           uint16_t* path) {
-    Graph g = make_graph<kSmem>(st);
+    const Caps caps = tier_caps<kTier>(caps_dyn);
+    Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     int first = span.first, last = span.last;
@@ -1017,9 +1040,10 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
     return true;
 }
 
-template <bool kSmem>
-__device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
-    const Graph g = make_graph<kSmem>(st);
+template <bool kSmem, int kTier>
+__device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps_dyn) {
+    const Caps caps = tier_caps<kTier>(caps_dyn);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
@@ -1131,9 +1155,9 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps) {
 // (topo_sort) only when an alignment's end cell is tied and before the consensus is extracted.
 // oracle/poa_oracle.c replays this scheme in checked mode and asserts it is a valid order.
 // ------------------------------------------------------------------------------------------
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     uint16_t* anch = g.anch;   // per position (the row records are dead here)
@@ -1214,9 +1238,9 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
 
 // Per-rank row records for the DP and the traceback: predecessor rows in in-edge order (CSR),
 // letter code + sink flag, first predecessor row.
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ void build_rows(const GState& st) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     int base = 0;
@@ -1306,9 +1330,9 @@ __device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
     return max_id;
 }
 
-template <bool kSmem>
+template <bool kSmem, int kTier>
 __device__ __noinline__ int heaviest_bundle(const GState& st) {
-    const Graph g = make_graph<kSmem>(st);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     int len = 0;
@@ -1367,10 +1391,11 @@ struct SeqSrc {
     int type;
 };
 
-template <bool kSmem, bool kOneTile>
-__device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t* H, const SeqSrc& s,
+template <bool kSmem, bool kOneTile, int kTier>
+__device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int16_t* H, const SeqSrc& s,
                                           Scores sc, uint16_t* path) {
-    const Graph g = make_graph<kSmem>(st);
+    const Caps caps = tier_caps<kTier>(caps_dyn);
+    const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
     if (len > caps.lcap) return false;
@@ -1404,17 +1429,17 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
         if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
-        EndCell ec = kOneTile ? dp_fill_one<kSmem>(st, H, len, s.type, sc)
-                              : dp_fill_tiles<kSmem>(st, H, len, tiles, s.type, sc);
+        EndCell ec = kOneTile ? dp_fill_one<kSmem, kTier>(st, H, len, s.type, sc)
+                              : dp_fill_tiles<kSmem, kTier>(st, H, len, tiles, s.type, sc);
         if (ec.tie && !st.exact) {
             // the reference breaks this tie by rank in ITS order: derive it and redo the fill
-            if (!topo_sort<kSmem>(st, caps)) return false;
+            if (!topo_sort<kSmem, kTier>(st, caps)) return false;
             st.exact = true;
-            build_rows<kSmem>(st);
-            ec = kOneTile ? dp_fill_one<kSmem>(st, H, len, s.type, sc)
-                          : dp_fill_tiles<kSmem>(st, H, len, tiles, s.type, sc);
+            build_rows<kSmem, kTier>(st);
+            ec = kOneTile ? dp_fill_one<kSmem, kTier>(st, H, len, s.type, sc)
+                          : dp_fill_tiles<kSmem, kTier>(st, H, len, tiles, s.type, sc);
         }
-        span = traceback<kSmem>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
+        span = traceback<kSmem, kTier>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
         // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
         // written back: without this every DP row ends up in HBM (1 TB per million windows) just
         // to be overwritten by the next read.
@@ -1427,22 +1452,22 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps, int16_t*
         }
     }
     const int nodes_before = st.n_nodes, edges_before = st.n_edges;
-    if (!add_to_graph<kSmem>(st, caps, len, span, path)) return false;
+    if (!add_to_graph<kSmem, kTier>(st, caps, len, span, path)) return false;
     // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence every
     // order, unchanged
     if (st.n_nodes == nodes_before && st.n_edges == edges_before) return true;
     // new nodes must be ranked; new edges alone keep the current order valid (they follow it),
     // but either may change what spoa's DFS would produce
-    if (st.n_nodes != nodes_before) order_update<kSmem>(st, len, nodes_before);
+    if (st.n_nodes != nodes_before) order_update<kSmem, kTier>(st, len, nodes_before);
     st.exact = false;
-    build_rows<kSmem>(st);
+    build_rows<kSmem, kTier>(st);
     return true;
 }
 
 // ------------------------------------------------------------------------------------------
 // Window driver (reference src/Window.cpp:44-254)
 // ------------------------------------------------------------------------------------------
-template <bool kSmem, bool kOneTile>
+template <bool kSmem, bool kOneTile, int kTier>
 __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                          const WinDesc& w, char* out) {
     const int lane = lane_id();
@@ -1463,37 +1488,37 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
         s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
         s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
 #pragma unroll 1
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
 #pragma unroll 1
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
-        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
 #pragma unroll 1
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
-        if (!add_sequence<kSmem, kOneTile>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
     }
     if (!g.exact) {   // the consensus needs spoa's exact rank order
-        if (!topo_sort<kSmem>(g, caps)) return -2;
+        if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
         g.exact = true;
     }
-    const int nc = heaviest_bundle<kSmem>(g);
+    const int nc = heaviest_bundle<kSmem, kTier>(g);
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
     const int n = nc >= 2 ? nc - 2 : 0;
-    const Graph v = make_graph<kSmem>(g);
+    const Graph v = make_graph<kSmem, kTier>(g);
 #pragma unroll 1
     for (int p = lane; p < n; p += 32) out[p] = code_to_char(v.ninfo[v.cons[p + 1]] & 7);
     return n;
@@ -1501,7 +1526,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
 
 // LONG windows: two rounds with the lr scores, all kNW, support counts and
 // curation (reference src/Window.cpp:156-254, graph.cpp:371-388,533-568).
-template <bool kSmem, bool kOneTile>
+template <bool kSmem, bool kOneTile, int kTier>
 __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                         const WinDesc& w, char* out, uint16_t* paths, uint64_t p_slot) {
     const int lane = lane_id();
@@ -1532,7 +1557,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return false;
             if (lane == 0) pstart[g.n_seq] = used;
-            const bool ok = add_sequence<kSmem, kOneTile>(g, caps, H, q, sc, pnodes + used);
+            const bool ok = add_sequence<kSmem, kOneTile, kTier>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
             return ok;
         };
@@ -1554,11 +1579,11 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         __syncwarp();
 
         if (!g.exact) {   // consensus and MSA columns need spoa's exact rank order
-            if (!topo_sort<kSmem>(g, caps)) return -2;
+            if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
             g.exact = true;
         }
-        const int nc = heaviest_bundle<kSmem>(g);
-        const Graph gv = make_graph<kSmem>(g);
+        const int nc = heaviest_bundle<kSmem, kTier>(g);
+        const Graph gv = make_graph<kSmem, kTier>(g);
         // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
         uint16_t* msa = gv.n2r;
         if (lane == 0) {
@@ -1612,17 +1637,23 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
 }
 
 // kMinBlocks = 3: the compact tier (27 warps / SM, <= 72 registers); 2: every other tier.
-template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks>
+template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks, int kTier>
 __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
     const int gwarp = blockIdx.x * warps_per_cta + warp_in_cta;
-    const Caps caps = P.caps;
-    const ArenaLayout L = arena_layout(caps);
+    const Caps caps = tier_caps<kTier>(P.caps);
     GState g;
-    g.L = L;
-    g.sbase = kSmem ? (uint32_t)warp_in_cta * L.total : 0u;
+    uint32_t arena_bytes;
+    if constexpr (kTier >= 0) {
+        constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
+        arena_bytes = L.total;
+    } else {
+        g.L = arena_layout(caps);
+        arena_bytes = g.L.total;
+    }
+    g.sbase = kSmem ? (uint32_t)warp_in_cta * arena_bytes : 0u;
     g.gbase = kSmem ? nullptr : (P.gws + (size_t)gwarp * P.g_slot);
     g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
@@ -1642,8 +1673,8 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         if (w.n_empty > n) {
             res = 0;   // reference src/Window.cpp:47-49
         } else if (n >= 2) {
-            if (w.wtype == 0) res = run_short<kSmem, kOneTile>(g, P, caps, H, w, out);
-            else if (kLong && paths) res = run_long<kSmem, kOneTile>(g, P, caps, H, w, out, paths, P.p_slot);
+            if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier>(g, P, caps, H, w, out);
+            else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier>(g, P, caps, H, w, out, paths, P.p_slot);
             else res = -2;
         } else {
             res = -1;
@@ -1674,14 +1705,20 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------
 // Host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_poa(const Params& P, bool smem_graph, bool one_tile, bool compact, int blocks,
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream) {
     void (*k)(const Params) = nullptr;
     if (warps_per_block * 32 > 288) return cudaErrorInvalidConfiguration;
     // one-tile tiers only ever run SHORT windows (the LONG driver is compiled out of them)
-    if (smem_graph && one_tile && compact) k = poa_kernel<true, true, false, 3>;
-    else if (smem_graph) k = one_tile ? poa_kernel<true, true, false, 2> : poa_kernel<true, false, true, 2>;
-    else k = one_tile ? poa_kernel<false, true, false, 2> : poa_kernel<false, false, true, 2>;
+    switch (tier) {
+        case 0: k = poa_kernel<true, true, false, 3, 0>; break;    // Tc
+        case 1: k = poa_kernel<true, true, false, 2, 1>; break;    // T0
+        case 2: k = poa_kernel<true, false, true, 2, 2>; break;    // T0b
+        case 3: k = poa_kernel<true, false, true, 2, 3>; break;    // T1
+        default:                                                   // bound-driven tiers, DAG in global memory
+            if (smem_graph) return cudaErrorInvalidConfiguration;
+            k = one_tile ? poa_kernel<false, true, false, 2, -1> : poa_kernel<false, false, true, 2, -1>;
+    }
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(P);

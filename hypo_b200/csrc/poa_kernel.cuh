@@ -85,7 +85,7 @@ struct Params {
     int sr_m, sr_n, sr_g, lr_m, lr_n, lr_g;
 };
 
-__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 // Per-warp graph arena.  Node arrays are indexed by node id, row arrays by rank (+1 = DP row).
 struct ArenaLayout {
@@ -121,49 +121,68 @@ struct ArenaLayout {
     uint32_t total;
 };
 
-__host__ __device__ inline ArenaLayout arena_layout(const Caps& c) {
-    ArenaLayout L;
-    uint32_t o = 0;
-    auto take = [&](uint32_t bytes) { uint32_t r = o; o = align16(o + bytes); return r; };
-    L.ninfo = take(c.ncap);
-    L.al_cnt = take(c.ncap);
-    L.in_deg = take(c.ncap);
-    L.in_head = take(2u * c.ncap);
-    L.al_blk = take(2u * c.ncap);
-    L.n2r = take(2u * c.ncap);
-    L.r2n = take(2u * c.ncap);
-    L.e_src = take(2u * c.ecap);
-    L.e_w = take(2u * c.ecap);
-    L.e_next = take(2u * c.ecap);
-    L.al_pool = take(2u * kAlSlots * c.acap);
-    const uint32_t rows0 = o;
-    L.rowinfo = take(4u * (c.ncap + 4));
-    L.prows = take(2u * c.ecap);
-    L.fp = take(2u * (c.ncap + 1));
-    L.fp4 = take(2u * (c.ncap + 1));
-    uint32_t end = o;
+struct LayoutCursor {
+    uint32_t o;
+    __host__ __device__ constexpr uint32_t take(uint32_t bytes) {
+        const uint32_t r = o;
+        o = (o + bytes + 15u) & ~15u;
+        return r;
+    }
+};
+
+__host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
+    ArenaLayout L{};
+    LayoutCursor k{0};
+    L.ninfo = k.take(c.ncap);
+    L.al_cnt = k.take(c.ncap);
+    L.in_deg = k.take(c.ncap);
+    L.in_head = k.take(2u * c.ncap);
+    L.al_blk = k.take(2u * c.ncap);
+    L.n2r = k.take(2u * c.ncap);
+    L.r2n = k.take(2u * c.ncap);
+    L.e_src = k.take(2u * c.ecap);
+    L.e_w = k.take(2u * c.ecap);
+    L.e_next = k.take(2u * c.ecap);
+    L.al_pool = k.take(2u * kAlSlots * c.acap);
+    const uint32_t rows0 = k.o;
+    L.rowinfo = k.take(4u * (c.ncap + 4));
+    L.prows = k.take(2u * c.ecap);
+    L.fp = k.take(2u * (c.ncap + 1));
+    L.fp4 = k.take(2u * (c.ncap + 1));
+    uint32_t end = k.o;
     // topological-sort scratch over the (dead) rows
-    o = rows0;
-    L.mark = take(c.ncap);
-    L.lists = take(2u * 32 * kBulkList);
-    L.stack = take(2u * c.scap);
-    if (o > end) end = o;
+    k.o = rows0;
+    L.mark = k.take(c.ncap);
+    L.lists = k.take(2u * 32 * kBulkList);
+    L.stack = k.take(2u * c.scap);
+    if (k.o > end) end = k.o;
     // order-update scratch
-    o = rows0;
-    L.anch = take(2u * (c.lcap + 1));
-    L.newa = take(2u * (c.lcap + 1));
-    if (o > end) end = o;
+    k.o = rows0;
+    L.anch = k.take(2u * (c.lcap + 1));
+    L.newa = k.take(2u * (c.lcap + 1));
+    if (k.o > end) end = k.o;
     // epilogue scratch
-    o = rows0;
-    L.score = take(4u * c.ncap);
-    L.pred = take(2u * c.ncap);
-    L.cons = take(2u * c.ncap);
-    if (o > end) end = o;
-    o = end;
-    L.colseq = take((uint32_t)c.tiles * kTileCols);
-    L.cur = take(2u * (c.lcap + 1));
-    L.total = align16(o);
+    k.o = rows0;
+    L.score = k.take(4u * c.ncap);
+    L.pred = k.take(2u * c.ncap);
+    L.cons = k.take(2u * c.ncap);
+    if (k.o > end) end = k.o;
+    k.o = end;
+    L.colseq = k.take((uint32_t)c.tiles * kTileCols);
+    L.cur = k.take(2u * (c.lcap + 1));
+    L.total = (k.o + 15u) & ~15u;
     return L;
+}
+
+// Capacities of the shared-memory tiers are compile-time constants (the kernels fold every arena
+// offset into an immediate); tiers >= kNumFixedTiers take theirs from Params at run time.
+constexpr int kNumFixedTiers = 4;
+__host__ __device__ constexpr Caps fixed_caps(int tier) {
+    //                 ncap  ecap  acap  scap  lcap  tiles
+    return tier == 0 ? Caps{212, 328, 112, 212, 127, 1}      // Tc : compact, 27 warps / SM
+         : tier == 1 ? Caps{320, 576, 128, 320, 127, 1}      // T0 : one tile
+         : tier == 2 ? Caps{320, 576, 128, 320, 255, 2}      // T0b: two tiles
+                     : Caps{1024, 2048, 384, 1024, 1023, 8}; // T1 : LONG windows, medium DAG
 }
 
 }  // namespace hypo_b200
