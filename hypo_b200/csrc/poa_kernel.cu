@@ -223,34 +223,38 @@ __device__ __forceinline__ void relax(uint32_t (&x)[kNR], const uint32_t (&p)[kN
 }
 
 // Horizontal pass: H^[i][j] = max(H^[i][j], H^[i][j-1]) == inclusive prefix max over columns.
-// In-lane over the 2*kNR columns; returns the lane total (its last column).
-__device__ __forceinline__ int scan_inlane(uint32_t (&x)[kNR]) {
-    uint32_t runb = kNegInf2;   // running max broadcast to both halves
+// In-lane over the 2*kNR columns; returns the lane total (its last column) in both halves.
+// `neg2` is kNegInf2 held in a register.
+__device__ __forceinline__ uint32_t scan_inlane(uint32_t (&x)[kNR], uint32_t neg2) {
+    uint32_t runb = neg2;   // running max broadcast to both halves
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
-        uint32_t t = __byte_perm(x[r], kNegInf2, 0x1054);          // (lo: -inf, hi: x.lo)
+        uint32_t t = __byte_perm(x[r], neg2, 0x1054);          // (lo: -inf, hi: x.lo)
         x[r] = __vimax3_s16x2(x[r], t, runb);
-        runb = __byte_perm(x[r], 0, 0x3232);                        // (x.hi, x.hi)
+        runb = __byte_perm(x[r], 0, 0x3232);                    // (x.hi, x.hi)
     }
-    return hi16(x[kNR - 1]);
+    return runb;
 }
 
 // Exclusive prefix max of the lane totals across the warp, radix 4: four dependent shuffle rounds
 // (1, then 3 + 3 + 1 independent ones) instead of six.  shfl_up hands the lanes below the shift
-// their own value back, which is harmless once the sequence has been shifted by one lane.
+// their own value back, which is harmless once the sequence has been shifted by one lane.  The
+// totals travel packed in both halves of a register, so the result is the broadcast the row needs.
 // `lane0_neg` is kNegInf2 on lane 0 and 0 elsewhere.
-__device__ __forceinline__ int warp_excl_max(int tot, uint32_t lane0_neg) {
-    int e = __shfl_up_sync(kFull, tot, 1);
-    e = lane0_neg ? kNegInf : e;
+__device__ __forceinline__ uint32_t warp_excl_max(uint32_t tot2, uint32_t lane0_neg, uint32_t neg2) {
+    uint32_t e = __shfl_up_sync(kFull, tot2, 1);
+    e = lane0_neg ? neg2 : e;
     {
-        const int a1 = __shfl_up_sync(kFull, e, 1), a2 = __shfl_up_sync(kFull, e, 2), a3 = __shfl_up_sync(kFull, e, 3);
-        e = max(__vimax3_s32(e, a1, a2), a3);
+        const uint32_t a1 = __shfl_up_sync(kFull, e, 1), a2 = __shfl_up_sync(kFull, e, 2),
+                       a3 = __shfl_up_sync(kFull, e, 3);
+        e = __vmaxs2(__vimax3_s16x2(e, a1, a2), a3);
     }
     {
-        const int b1 = __shfl_up_sync(kFull, e, 4), b2 = __shfl_up_sync(kFull, e, 8), b3 = __shfl_up_sync(kFull, e, 12);
-        e = max(__vimax3_s32(e, b1, b2), b3);
+        const uint32_t b1 = __shfl_up_sync(kFull, e, 4), b2 = __shfl_up_sync(kFull, e, 8),
+                       b3 = __shfl_up_sync(kFull, e, 12);
+        e = __vmaxs2(__vimax3_s16x2(e, b1, b2), b3);
     }
-    return max(e, __shfl_up_sync(kFull, e, 16));
+    return __vmaxs2(e, __shfl_up_sync(kFull, e, 16));
 }
 
 struct EndCell {
@@ -323,9 +327,9 @@ template <bool kSmem, int kTier>
 __device__ HYPO_FAR_ATTR uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint32_t info, int rk,
                                         const int16_t* __restrict__ Hl, uint32_t p1a, uint32_t p1b,
                                         uint32_t l1, uint32_t pf0, uint32_t pf1, uint32_t g2,
-                                        uint32_t row0_left) {
+                                        uint32_t row0_left, uint32_t xinit0) {
     typedef Mem<kSmem> M;
-    uint32_t x[kNR] = {kNegInf2, kNegInf2};
+    uint32_t x[kNR] = {xinit0, kNegInf2};
     const uint32_t pf[kNR] = {pf0, pf1};
     const int np = (info >> 16) & 0xff;
     if (np == 0) {
@@ -353,7 +357,7 @@ __device__ HYPO_FAR_ATTR uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint
 }
 
 struct DpConst {
-    uint32_t g2, mm2, nn2, let4, row0_left, rov_mask;
+    uint32_t g2, mm2, nn2, let4, row0_left, neg2, xinit0;
 };
 
 // One DP row: d1/d2/d3 hold the rows 1/2/3 ranks back; the new row replaces d3.
@@ -363,22 +367,23 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
                                        const int16_t* __restrict__ Hl, int16_t*& Hrow) {
     uint32_t pf[kNR];
     profile_regs(c.let4, (info >> 24) & 7u, c.mm2, c.nn2, pf);
-    uint32_t x[kNR] = {kNegInf2, kNegInf2};
+    // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf); ROV pins it to
+    // 0 (reference :229-239): lane 0 starts its first column at 0, which every candidate
+    // (-inf diagonal, 0 + g vertical, g <= 0) leaves in place
+    uint32_t x[kNR] = {c.xinit0, c.neg2};
     const uint32_t near = info >> kRowNearShift;
-    if (near) {
+    if (near == 1u) {
+        relax(x, d1.x, d1.left, pf, c.g2);
+    } else if (near) {
         if (near & 1u) relax(x, d1.x, d1.left, pf, c.g2);
         if (near & 2u) relax(x, d2.x, d2.left, pf, c.g2);
         if (near & 4u) relax(x, d3.x, d3.left, pf, c.g2);
     } else {
         const uint2 q = relax_far<kSmem, kTier>(prows, info, rk, Hl, d1.x[0], d1.x[1], d1.left, pf[0], pf[1], c.g2,
-                                         c.row0_left);
+                                         c.row0_left, c.xinit0);
         x[0] = q.x; x[1] = q.y;
     }
-    // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf),
-    // ROV pins it to 0 (reference :229-239)
-    x[0] &= c.rov_mask;
-    const int excl = warp_excl_max(scan_inlane(x), c.row0_left);
-    const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);   // low half broadcast to both halves
+    const uint32_t cb = warp_excl_max(scan_inlane(x, c.neg2), c.row0_left, c.neg2);
     d3.x[0] = __vmaxs2(x[0], cb);
     d3.x[1] = __vmaxs2(x[1], cb);
     d3.left = cb;   // == last column of the lane to the left (kNegInf for lane 0)
@@ -399,7 +404,8 @@ __device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restric
     c.nn2 = opaque(bcast16(sc.n - sc.g));
     c.let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + lane * 4));
     c.row0_left = opaque(lane == 0 ? kNegInf2 : 0u);
-    c.rov_mask = opaque((type == kROV && lane == 0) ? 0xffff0000u : 0xffffffffu);
+    c.neg2 = opaque(kNegInf2);
+    c.xinit0 = opaque((type == kROV && lane == 0) ? (kNegInf2 & 0xffff0000u) : kNegInf2);
     const int16_t* Hl = opaque_ptr(H + lane * 4);
     const int n = g.n_nodes;
     typedef Mem<kSmem> M;
@@ -471,7 +477,7 @@ __device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restr
         const int pe = ps + ((info >> 16) & 0xff);
         const uint32_t code = (info >> 24) & 7u;
         const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
-        int carry = kNegInf;
+        uint32_t carry = kNegInf2;   // prefix max of the tiles to the left, in both halves
 #pragma unroll 1
         for (int t = 0; t < tiles; ++t) {
             const unsigned toff = (unsigned)t * kTileCols;
@@ -498,12 +504,11 @@ __device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restr
                 }
             }
             if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
-            const int tot = scan_inlane(x);
-            const int excl = max(warp_excl_max(tot, lane == 0 ? kNegInf2 : 0u), carry);
-            const uint32_t cb = __byte_perm((uint32_t)excl, 0u, 0x1010);
+            const uint32_t tot2 = scan_inlane(x, kNegInf2);
+            const uint32_t cb = __vmaxs2(warp_excl_max(tot2, lane == 0 ? kNegInf2 : 0u, kNegInf2), carry);
 #pragma unroll
             for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
-            carry = __shfl_sync(kFull, max(excl, tot), 31);
+            carry = __shfl_sync(kFull, __vmaxs2(cb, tot2), 31);
             *reinterpret_cast<uint2*>(Hl + rowoff + toff) = make_uint2(x[0], x[1]);
         }
         __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
@@ -1477,7 +1482,12 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     // arms_added (reference :90,106,117,128)
     bool added = false;
 #pragma unroll 1
-    for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
+    for (int k = lane; k < n_arms; k += 32) {
+        const ArmDesc d = a[k];
+        added |= d.len > 0;
+        // the reads' packed bytes are needed one read at a time: pull them into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + d.off));
+    }
     added = __any_sync(kFull, added);
     if (!added) return -1;   // caller copies the draft (:150-152)
 
