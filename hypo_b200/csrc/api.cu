@@ -96,6 +96,7 @@ struct Ctx {
     float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
     uint32_t poa_launches = 0;
     uint32_t tier_windows[8] = {0};
+    uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
 } g;
 
 std::mutex g_mu;
@@ -158,14 +159,18 @@ __global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* 
 // lists: [tier][n_win] window ids; counts[tier]; tmax[tier] running maxima.
 __global__ void route_kernel(const WinDesc* __restrict__ win, const WinStat* __restrict__ st,
                              uint64_t n_win, int n_tiers, const uint32_t* __restrict__ tier_lcap,
-                             const uint32_t* __restrict__ tier_long_ok, uint32_t* __restrict__ lists,
-                             TierMax* __restrict__ tmax) {
+                             const uint32_t* __restrict__ tier_long_ok, const uint32_t* __restrict__ tier_est_cap,
+                             uint32_t* __restrict__ lists, TierMax* __restrict__ tmax) {
     uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (w >= n_win) return;
     const WinStat s = st[w];
     const bool is_long = win[w].wtype == 1;
     int t = 0;
-    while (t < n_tiers - 1 && (s.max_len > tier_lcap[t] || (is_long && !tier_long_ok[t]))) ++t;
+    // (sum_len of a LONG window counts the round-2 backbone bound as well: about twice the bases)
+    const uint32_t est = s.max_len + (uint32_t)(((uint64_t)s.sum_len * (is_long ? 8u : 15u)) / 1000u);
+    while (t < n_tiers - 1 &&
+           (s.max_len > tier_lcap[t] || (is_long && !tier_long_ok[t]) || est > tier_est_cap[t]))
+        ++t;
     const uint32_t k = atomicAdd(&tmax[t].count, 1u);
     lists[(uint64_t)t * n_win + k] = (uint32_t)w;
 }
@@ -206,28 +211,35 @@ __global__ void widen_kernel(const uint32_t* __restrict__ len, uint64_t* __restr
 // Tier table
 // ---------------------------------------------------------------------------------------
 struct Tier {
-    bool smem_graph, one_tile, long_ok, from_bounds, compact;
+    bool smem_graph, one_tile, long_ok, from_bounds;
     int ncap, ecap, acap, scap, lcap;
     int warps_per_block, blocks_per_sm;
+    uint32_t est_cap;   // static routing: windows whose estimated node count exceeds this start in a later tier
+    int next;           // tier that re-runs the windows overflowing this one (skips tiers that cannot help)
 };
 
 // Tc : SHORT windows whose sequences fit one 128-column tile and whose DAG stays small (the
 //      30 x 120 headline shape at ~1 % read error: 187 nodes on average, 209 at most in 3000
 //      windows): DAG in 8.3 KB of shared memory, 27 warps/SM (3 CTAs x 9 warps, <= 72 registers),
-//      previous DP row carried in registers.
+//      the last three DP rows carried in registers.
 // T0 : same, larger DAG capacities, 18 warps/SM.  Windows that overflow Tc at run time land here.
-// T0b: SHORT windows up to 255 columns (two tiles), same DAG capacities, 18 warps/SM.
+// Tw : one tile, DAG sized for windows with many reads (100-200 x 120 bp), 10 warps/SM.
+// Static routing skips tiers a window is unlikely to fit: est = longest sequence + 1.5 % of all bases
+// (every base of a ~1 %-error read opens a new node with about that probability); a wrong guess only
+// costs the run-time overflow path.
+// T0b: SHORT windows up to 255 columns (two tiles), 12 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 // The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
-// (poa_kernel.cuh: fixed_caps); they are repeated here only as documentation and checked at start-up.
+// (poa_kernel.cuh: fixed_caps); they are repeated here as documentation and checked at start-up.
 const Tier kTiers[] = {
-    {true, true, false, false, true, 212, 328, 112, 212, 127, 9, 3},
-    {true, true, false, false, false, 320, 576, 128, 320, 127, 9, 2},
-    {true, false, false, false, false, 320, 576, 128, 320, 255, 9, 2},
-    {true, false, true, false, false, 1024, 2048, 384, 1024, 1023, 4, 1},
-    {false, false, true, true, false, 8192, 16384, 2048, 8192, 4095, 4, 1},
-    {false, false, true, true, false, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1},
+    {true, true, false, false, 212, 328, 212, 640, 127, 9, 3, 201, 1},
+    {true, true, false, false, 320, 576, 304, 1024, 127, 8, 2, 300, 2},
+    {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 4},
+    {true, false, false, false, 384, 768, 256, 1536, 255, 6, 2, 364, 4},
+    {true, false, true, false, 1024, 2048, 512, 4096, 1023, 5, 1, 972, 5},
+    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 6},
+    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 7},
 };
 const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 
@@ -248,7 +260,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
     if (n_win == 0) return HYPO_OK;
     if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
     // control block: [0..kNumTiers) TierMax, then queue counters
-    const size_t ctrl_bytes = sizeof(TierMax) * (kNumTiers + 1) + 64 * sizeof(uint32_t);
+    const size_t ctrl_bytes = sizeof(TierMax) * (kNumTiers + 1) + (64 + kNumFailReasons) * sizeof(uint32_t);
     CUDA_TRY(g.ctrl.reserve(ctrl_bytes));
     CUDA_TRY(g.lists.reserve(sizeof(uint32_t) * ((uint64_t)kNumTiers * n_win + (n_win + 1) * 2 + 64)));
     CUDA_TRY(cudaMemsetAsync(g.ctrl.p, 0, ctrl_bytes, stream));
@@ -258,17 +270,22 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
     uint32_t* d_ovf[2] = {d_lists + (uint64_t)kNumTiers * n_win, d_lists + (uint64_t)kNumTiers * n_win + (n_win + 1)};
     uint32_t* d_tier_lcap = d_queue + 16;
     uint32_t* d_tier_long = d_queue + 32;
+    uint32_t* d_tier_seq = d_queue + 48;
+    uint32_t* d_fail = d_queue + 64;
 
-    uint32_t h_lcap[16] = {0}, h_long[16] = {0};
+    uint32_t h_lcap[16] = {0}, h_long[16] = {0}, h_seq[16] = {0};
     for (int t = 0; t < kNumTiers; ++t) {
         h_lcap[t] = (uint32_t)kTiers[t].lcap;
         h_long[t] = kTiers[t].long_ok;
+        h_seq[t] = kTiers[t].est_cap;
     }
     CUDA_TRY(cudaMemcpyAsync(d_tier_lcap, h_lcap, sizeof(h_lcap), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_tier_long, h_long, sizeof(h_long), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_tier_seq, h_seq, sizeof(h_seq), cudaMemcpyHostToDevice, stream));
     const int tb = 256;
     route_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_stats, n_win, kNumTiers,
-                                                                     d_tier_lcap, d_tier_long, d_lists, d_tmax);
+                                                                     d_tier_lcap, d_tier_long, d_tier_seq, d_lists,
+                                                                     d_tmax);
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
 
@@ -279,24 +296,20 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
     uint32_t routed[16];
     for (int t = 0; t < kNumTiers; ++t) routed[t] = h_tmax[t].count;
 
-    uint32_t carry = 0;          // windows that overflowed the previous tier
-    int ovf_buf = 0;             // d_ovf[ovf_buf] receives this tier's overflow, [ovf_buf^1] holds the carry
+    // Windows that overflow tier t at run time are appended to the list of tier kTiers[t].next
+    // (always a later one), behind its routed windows: every list holds each window at most once.
+    uint32_t pend[16] = {0};
     for (int t = 0; t < kNumTiers; ++t) {
         const Tier& T = kTiers[t];
         uint32_t* d_work = d_lists + (uint64_t)t * n_win;
-        uint32_t n_work = routed[t];
-        if (carry) {   // carried windows join this tier's list (routed counts + carry <= n_win)
-            CUDA_TRY(cudaMemcpyAsync(d_work + n_work, d_ovf[ovf_buf ^ 1] + 1, sizeof(uint32_t) * carry,
-                                     cudaMemcpyDeviceToDevice, stream));
-            n_work += carry;
-            carry = 0;
-        }
+        const uint32_t n_work = routed[t] + pend[t];
         if (n_work == 0) continue;
-        uint32_t* d_over = d_ovf[ovf_buf];
+        uint32_t* d_over = d_ovf[0];
         CUDA_TRY(cudaMemsetAsync(d_over, 0, sizeof(uint32_t), stream));
 
         Caps caps;
         caps.ncap = T.ncap; caps.ecap = T.ecap; caps.acap = T.acap; caps.scap = T.scap; caps.lcap = T.lcap;
+        caps.alslots = t < kNumFixedTiers ? fixed_caps(t).alslots : kAlSlotsMax;
         bool need_paths = false;
         uint32_t sum_raw = 0, n_seq = 0;
         if (T.from_bounds || T.long_ok) {
@@ -357,6 +370,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         P.queue = d_queue + t;
         P.out = d_out; P.out_pos = d_out_pos; P.out_len = d_out_len;
         P.overflow = d_over;
+        P.fail_hist = d_fail;
         P.H = (int16_t*)g.H.p; P.h_slot = h_slot;
         P.gws = (uint8_t*)g.gws.p; P.g_slot = g_slot;
         P.paths = need_paths ? (uint16_t*)g.paths.p : nullptr; P.p_slot = p_slot;
@@ -376,12 +390,19 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
             g.poa_launches += 1;
             g.tier_windows[t] += n_work;
         }
-        carry = *h_ovf_count;
-        ovf_buf ^= 1;
+        const uint32_t over = *h_ovf_count;
+        if (over != 0) {
+            const int nxt = T.next;
+            if (nxt >= kNumTiers)
+                return fail(HYPO_E_CAPACITY, "%u window(s) exceed every device capacity tier (graph > 65534 nodes or "
+                                             "scores outside the 16-bit DP range)", over);
+            CUDA_TRY(cudaMemcpyAsync(d_lists + (uint64_t)nxt * n_win + routed[nxt] + pend[nxt], d_over + 1,
+                                     sizeof(uint32_t) * over, cudaMemcpyDeviceToDevice, stream));
+            pend[nxt] += over;
+        }
     }
-    if (carry != 0)
-        return fail(HYPO_E_CAPACITY, "%u window(s) exceed every device capacity tier (graph > 65534 nodes or "
-                                     "scores outside the 16-bit DP range)", carry);
+    CUDA_TRY(cudaMemcpyAsync(g.fail_hist, d_fail, sizeof(g.fail_hist), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
     return HYPO_OK;
 }
 
@@ -581,6 +602,11 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
     if (poa_kernel_ms) *poa_kernel_ms = g.poa_ms;
     if (poa_launches) *poa_launches = g.poa_launches;
     if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = g.tier_windows[t];
+    return HYPO_OK;
+}
+
+int hypo_gpu_last_fail_hist(uint32_t reasons[16]) {
+    if (reasons) for (int k = 0; k < kNumFailReasons; ++k) reasons[k] = g.fail_hist[k];
     return HYPO_OK;
 }
 

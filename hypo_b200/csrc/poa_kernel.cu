@@ -39,6 +39,7 @@ struct Graph {
     uint16_t* pred;
     uint16_t* cons;
     int n_nodes, n_edges, n_al, n_seq;
+    int als;              // slots per aligned-list block
 };
 
 // What persists per warp between the phases (kept in local memory; the phases are separate
@@ -52,7 +53,16 @@ struct GState {
     ArenaLayout L;
     int n_nodes, n_edges, n_al, n_seq;
     bool exact;          // r2n/n2r currently hold spoa's exact DFS order (not just a valid one)
+    uint32_t* fail_hist; // diagnostics: why windows were abandoned (may be null)
 };
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Records why the window is being abandoned in this tier; always returns false.
+__device__ __noinline__ bool give_up(const GState& st, int why) {
+    if (lane_id() == 0 && st.fail_hist) atomicAdd(st.fail_hist + why, 1u);
+    return false;
+}
 
 template <bool kSmem>
 __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout& L) {
@@ -86,6 +96,7 @@ __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout&
     g.pred = (uint16_t*)(base + L.pred);
     g.cons = (uint16_t*)(base + L.cons);
     g.n_nodes = st.n_nodes; g.n_edges = st.n_edges; g.n_al = st.n_al; g.n_seq = st.n_seq;
+    g.als = L.alslots;
     return g;
 }
 
@@ -115,8 +126,6 @@ __device__ __forceinline__ Caps tier_caps(const Caps& dyn) {
 struct Scores {
     int m, n, g;
 };
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ------------------------------------------------------------------------------------------
 // Sequence decode (PackedSeq<2>/<4>::unpack, reference src/PackedSeq.cpp:231-262 with the bit
@@ -701,7 +710,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
     if (first < 0) { first = len; last = len - 1; }   // empty alignment: whole read is a chain (:174-182)
     const int head_n = first, tail_n = len - 1 - last;
     const int base = g.n_nodes;
-    if (base + head_n + tail_n > caps.ncap) return false;
+    if (base + head_n + tail_n > caps.ncap) return give_up(st, kFailNodes);
 
     // head chain [0, first) and tail chain (last, len): fresh nodes, allocated FIRST (:194-200)
 #pragma unroll 1
@@ -739,7 +748,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
                     const int cnt = g.al_cnt[x];
 #pragma unroll 1
                     for (int k = 0; k < cnt; ++k) {
-                        int a = g.al_pool[blk * kAlSlots + k];
+                        int a = g.al_pool[blk * g.als + k];
                         if ((g.ninfo[a] & 7) == code) { res = a; need_new = false; break; }
                     }
                 }
@@ -747,7 +756,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
         }
         const unsigned newmask = __ballot_sync(kFull, need_new);
         const int n_new = __popc(newmask);
-        if (n_nodes + n_new > caps.ncap) return false;
+        if (n_nodes + n_new > caps.ncap) return give_up(st, kFailNodes);
         if (need_new) res = n_nodes + __popc(newmask & lt_mask);
         n_nodes += n_new;
         // aligned-list blocks: the new node needs one; so does x if it had none
@@ -755,9 +764,9 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
         const bool x_needs_blk = link && g.al_blk[x] == kNone;
         const unsigned m1 = __ballot_sync(kFull, link);
         const unsigned m2 = __ballot_sync(kFull, x_needs_blk);
-        if (n_al + __popc(m1) + __popc(m2) > caps.acap) return false;
+        if (n_al + __popc(m1) + __popc(m2) > caps.acap) return give_up(st, kFailAligned);
         // cannot happen (clique letters are distinct, <= 7 letters); checked uniformly anyway
-        if (__any_sync(kFull, link && g.al_cnt[x] + 1 > kAlSlots)) return false;
+        if (__any_sync(kFull, link && g.al_cnt[x] + 1 > g.als)) return give_up(st, kFailClique);
         if (need_new) init_node(g, res, code);
         if (link) {
             const int yb = n_al + __popc(m1 & lt_mask);
@@ -771,16 +780,16 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
             // y.list = x.list + [x]; every a in x.list gets y appended; x.list += y (:228-240)
 #pragma unroll 1
             for (int k = 0; k < cnt; ++k) {
-                const int a = g.al_pool[xb * kAlSlots + k];
-                g.al_pool[yb * kAlSlots + k] = (uint16_t)a;
+                const int a = g.al_pool[xb * g.als + k];
+                g.al_pool[yb * g.als + k] = (uint16_t)a;
                 const int ab = g.al_blk[a];
                 const int ac = g.al_cnt[a];
-                g.al_pool[ab * kAlSlots + ac] = (uint16_t)res;
+                g.al_pool[ab * g.als + ac] = (uint16_t)res;
                 g.al_cnt[a] = (uint8_t)(ac + 1);
             }
-            g.al_pool[yb * kAlSlots + cnt] = (uint16_t)x;
+            g.al_pool[yb * g.als + cnt] = (uint16_t)x;
             g.al_cnt[res] = (uint8_t)(cnt + 1);
-            g.al_pool[xb * kAlSlots + cnt] = (uint16_t)res;
+            g.al_pool[xb * g.als + cnt] = (uint16_t)res;
             g.al_cnt[x] = (uint8_t)(cnt + 1);
         }
         n_al += __popc(m1) + __popc(m2);
@@ -817,7 +826,7 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
             }
         }
         const unsigned em = __ballot_sync(kFull, need_edge);
-        if (n_edges + __popc(em) > caps.ecap || __any_sync(kFull, sat)) return false;
+        if (n_edges + __popc(em) > caps.ecap || __any_sync(kFull, sat)) return give_up(st, kFailEdges);
         if (need_edge) {
             const int e = n_edges + __popc(em & lt_mask);
             g.e_src[e] = (uint16_t)src;
@@ -870,7 +879,7 @@ struct SortCtx {
     const uint16_t* al_blk;
     const uint16_t* al_pool;
     uint16_t* list;      // [0] = n, [1..n] = nodes in emission order
-    int i0, id, lane, round;
+    int i0, id, lane, round, als;
     unsigned emit_mask;  // lanes whose replay succeeded in an earlier pass
     bool use_claims;
 };
@@ -909,7 +918,7 @@ __device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
     const int ublk = c.al_blk[u];
 #pragma unroll 1
     for (int k = 0; k < mu; ++k) {
-        const int b = c.al_pool[ublk * kAlSlots + k];
+        const int b = c.al_pool[ublk * c.als + k];
         if (c.mark[b] != 0 || s_ok(c, b)) return false;
 #pragma unroll 1
         for (int e = c.in_head[b]; e != kNone; e = c.e_next[e])
@@ -939,7 +948,7 @@ __device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
     if (!s_push(c, u)) return false;
 #pragma unroll 1
     for (int k = 0; k < mu; ++k)
-        if (!s_push(c, c.al_pool[ublk * kAlSlots + k])) return false;
+        if (!s_push(c, c.al_pool[ublk * c.als + k])) return false;
     return true;
 }
 
@@ -954,7 +963,7 @@ __device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
     // targets: aligned nodes last-to-first (only their sources are explored), then the node itself
 #pragma unroll 1
     for (int t = nm - 1; t >= -1; --t) {
-        const int x = t >= 0 ? (int)c.al_pool[blk * kAlSlots + t] : id;
+        const int x = t >= 0 ? (int)c.al_pool[blk * c.als + t] : id;
         if (t >= 0 && (c.mark[x] != 0 || s_ok(c, x))) return 2;
         unsigned long long und = 0ull;   // up to three 16-bit node ids
         int n_und = 0;
@@ -975,7 +984,7 @@ __device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
     if (!s_push(c, id)) return 2;
 #pragma unroll 1
     for (int k = 0; k < nm; ++k)
-        if (!s_push(c, c.al_pool[blk * kAlSlots + k])) return 2;
+        if (!s_push(c, c.al_pool[blk * c.als + k])) return 2;
     return 1;
 }
 
@@ -1019,7 +1028,7 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
             if (check) {
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
-                    const int a = g.al_pool[blk * kAlSlots + k];
+                    const int a = g.al_pool[blk * g.als + k];
                     const int ma = g.mark[a];
                     if ((ma & 3) != 2) {
                         if (sp >= caps.scap) return false;
@@ -1034,7 +1043,7 @@ __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int r
                 if (check) {
                     g.r2n[nr++] = (uint16_t)v;
 #pragma unroll 1
-                    for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * kAlSlots + k];
+                    for (int k = 0; k < cnt; ++k) g.r2n[nr++] = g.al_pool[blk * g.als + k];
                 }
             } else {
                 g.mark[v] = (uint8_t)((mv & 4) | 1);
@@ -1070,7 +1079,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps_dyn) {
         int status = (id < n && (g.mark[id] & 3) != 2) ? 2 : 0;
         SortCtx c;
         c.mark = g.mark; c.al_cnt = g.al_cnt; c.claim = claim; c.in_head = g.in_head; c.e_next = g.e_next;
-        c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool;
+        c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool; c.als = g.als;
         c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
         c.emit_mask = 0u;
 #pragma unroll 1
@@ -1132,7 +1141,7 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps_dyn) {
             if (lane == 0 && (g.mark[i0 + cut] & 3) != 2) ok = dfs_from(g, caps, i0 + cut, nr) ? 1 : 0;
             ok = __shfl_sync(kFull, ok, 0);
             nr = __shfl_sync(kFull, nr, 0);
-            if (!ok) return false;
+            if (!ok) return give_up(st, kFailStack);
             i0 += cut + 1;
             __syncwarp();
         } else {
@@ -1186,7 +1195,7 @@ __device__ __noinline__ void order_update(const GState& st, int len, int nb) {
                 const int blk = g.al_blk[v];
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
-                    const int m = g.al_pool[blk * kAlSlots + k];
+                    const int m = g.al_pool[blk * g.als + k];
                     if (m < nb) { const int r = g.n2r[m]; mn = min(mn, r); mx = max(mx, r); }
                 }
                 colmin = mn;
@@ -1403,7 +1412,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
-    if (len > caps.lcap) return false;
+    if (len > caps.lcap) return give_up(st, kFailLen);
     uint8_t* dst = g.seq + (s.head ? 1 : 0);
     if (s.bytes) {
         if (s.nb == 2) decode2(s.bytes, s.len, dst); else decode4(s.bytes, s.len, dst);
@@ -1433,7 +1442,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
         const int cols = tiles * kTileCols;
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
-        if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return false;
+        if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return give_up(st, kFailRange);
         EndCell ec = kOneTile ? dp_fill_one<kSmem, kTier>(st, H, len, s.type, sc)
                               : dp_fill_tiles<kSmem, kTier>(st, H, len, tiles, s.type, sc);
         if (ec.tie && !st.exact) {
@@ -1565,7 +1574,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         SeqSrc s;
         s.head = false; s.tail = false; s.type = kNW;
         auto add = [&](const SeqSrc& q) -> bool {
-            if (used + (uint32_t)q.len > pcap) return false;
+            if (used + (uint32_t)q.len > pcap) return give_up(g, kFailPaths);
             if (lane == 0) pstart[g.n_seq] = used;
             const bool ok = add_sequence<kSmem, kOneTile, kTier>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
@@ -1666,6 +1675,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     g.sbase = kSmem ? (uint32_t)warp_in_cta * arena_bytes : 0u;
     g.gbase = kSmem ? nullptr : (P.gws + (size_t)gwarp * P.g_slot);
     g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
+    g.fail_hist = P.fail_hist;
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 
@@ -1685,7 +1695,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         } else if (n >= 2) {
             if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier>(g, P, caps, H, w, out);
             else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier>(g, P, caps, H, w, out, paths, P.p_slot);
-            else res = -2;
+            else { give_up(g, kFailNoLong); res = -2; }
         } else {
             res = -1;
         }
@@ -1723,8 +1733,9 @@ cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile
     switch (tier) {
         case 0: k = poa_kernel<true, true, false, 3, 0>; break;    // Tc
         case 1: k = poa_kernel<true, true, false, 2, 1>; break;    // T0
-        case 2: k = poa_kernel<true, false, true, 2, 2>; break;    // T0b
-        case 3: k = poa_kernel<true, false, true, 2, 3>; break;    // T1
+        case 2: k = poa_kernel<true, true, false, 2, 2>; break;    // Tw
+        case 3: k = poa_kernel<true, false, true, 2, 3>; break;    // T0b
+        case 4: k = poa_kernel<true, false, true, 2, 4>; break;    // T1
         default:                                                   // bound-driven tiers, DAG in global memory
             if (smem_graph) return cudaErrorInvalidConfiguration;
             k = one_tile ? poa_kernel<false, true, false, 2, -1> : poa_kernel<false, false, true, 2, -1>;

@@ -46,13 +46,27 @@ constexpr int kTileCols = 32 * 2 * kNR;      // 128 DP columns per tile
 constexpr uint16_t kNone = 0xFFFF;
 constexpr int kNegInf = -30000;              // "minus infinity" that survives one int16 add
 constexpr uint32_t kNegInf2 = 0x8AD08AD0u;   // (kNegInf, kNegInf) packed
-constexpr int kAlSlots = 6;                  // clique <= 7 letters (J O A C G T N) => <= 6 peers
+constexpr int kAlSlotsMax = 6;               // clique <= 7 letters (J O A C G T N) => <= 6 peers
 constexpr int kNumCodes = 7;                 // A C G T N J O
 constexpr int kCodeJ = 5, kCodeO = 6;
 constexpr int kMaxH16 = 29000;               // int16 safety bound for |H^|
 constexpr int kBulkList = 10;                // per-lane emission list of the bulk topological sort
 
 enum AlignType { kNW = 0, kLOV = 1, kROV = 2 };
+
+// Why a window was abandoned in a tier (diagnostic histogram, hypo_gpu_last_fail_hist).
+enum FailReason {
+    kFailLen = 1,        // a sequence is longer than the tier's columns
+    kFailRange = 2,      // scores x size could leave the 16-bit DP range
+    kFailNodes = 3,      // node capacity
+    kFailAligned = 4,    // aligned-list blocks
+    kFailClique = 5,     // a clique with more than 7 members (cannot happen for 7 letters)
+    kFailEdges = 6,      // edge capacity or in-degree > 254
+    kFailStack = 7,      // DFS stack of the exact topological sort
+    kFailPaths = 8,      // LONG: per-sequence node paths
+    kFailNoLong = 9,     // LONG window in a tier compiled without the LONG driver
+    kNumFailReasons = 16
+};
 
 // Capacities of one tier (one kernel launch).
 struct Caps {
@@ -62,6 +76,9 @@ struct Caps {
     int scap;      // DFS stack entries
     int lcap;      // sequence length incl. markers
     int tiles;     // ceil((lcap+1)/kTileCols)
+    int alslots;   // slots per aligned-list block: a clique of more than alslots+1 nodes overflows the
+                   // tier (6 always suffices; the small tiers trade slots for blocks: cliques beyond
+                   // A/C/G/T need N or a marker letter aligned to bases)
 };
 
 struct Params {
@@ -75,6 +92,7 @@ struct Params {
     const uint64_t* out_pos;     // where window w writes
     uint32_t* out_len;           // consensus length of window w
     uint32_t* overflow;          // [0] = count, [1..] = window ids that exceeded this tier
+    uint32_t* fail_hist;         // [kNumFailReasons] why windows left a tier (diagnostics; may be null)
     int16_t* H;                  // DP workspace, one slot per warp
     uint64_t h_slot;             // elements per slot
     uint8_t* gws;                // tiers L: graph workspace, one slot per warp
@@ -99,7 +117,7 @@ struct ArenaLayout {
     uint32_t r2n;       // u16 rank -> node
     // edges
     uint32_t e_src, e_w, e_next;   // u16 each
-    uint32_t al_pool;   // u16 [acap][kAlSlots]
+    uint32_t al_pool;   // u16 [acap][alslots]
     // rows (rebuilt by build_rows after every change of the order; dead while the order is being
     // changed and once the last read has been aligned, so the sort / order-update / epilogue
     // scratch aliases this region)
@@ -119,6 +137,7 @@ struct ArenaLayout {
     uint32_t colseq;    // u8  [tiles*128] letter code of DP column j (= seq[j-1]); 7 = matches nothing
     uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
     uint32_t total;
+    int alslots;
 };
 
 struct LayoutCursor {
@@ -143,7 +162,8 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     L.e_src = k.take(2u * c.ecap);
     L.e_w = k.take(2u * c.ecap);
     L.e_next = k.take(2u * c.ecap);
-    L.al_pool = k.take(2u * kAlSlots * c.acap);
+    L.al_pool = k.take(2u * (uint32_t)c.alslots * c.acap);
+    L.alslots = c.alslots;
     const uint32_t rows0 = k.o;
     L.rowinfo = k.take(4u * (c.ncap + 4));
     L.prows = k.take(2u * c.ecap);
@@ -176,13 +196,15 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
 
 // Capacities of the shared-memory tiers are compile-time constants (the kernels fold every arena
 // offset into an immediate); tiers >= kNumFixedTiers take theirs from Params at run time.
-constexpr int kNumFixedTiers = 4;
+constexpr int kNumFixedTiers = 5;
 __host__ __device__ constexpr Caps fixed_caps(int tier) {
-    //                 ncap  ecap  acap  scap  lcap  tiles
-    return tier == 0 ? Caps{212, 328, 112, 212, 127, 1}      // Tc : compact, 27 warps / SM
-         : tier == 1 ? Caps{320, 576, 128, 320, 127, 1}      // T0 : one tile
-         : tier == 2 ? Caps{320, 576, 128, 320, 255, 2}      // T0b: two tiles
-                     : Caps{1024, 2048, 384, 1024, 1023, 8}; // T1 : LONG windows, medium DAG
+    // (scap, the DFS stack of the exact sort, aliases the row records and costs no extra memory)
+    //                 ncap  ecap  acap  scap  lcap  tiles alslots
+    return tier == 0 ? Caps{212, 328, 212, 640, 127, 1, 3}      // Tc : compact, 27 warps / SM
+         : tier == 1 ? Caps{320, 576, 304, 1024, 127, 1, 4}     // T0 : one tile
+         : tier == 2 ? Caps{512, 1024, 384, 2048, 127, 1, 6}    // Tw : one tile, many reads per window
+         : tier == 3 ? Caps{384, 768, 256, 1536, 255, 2, 6}     // T0b: two tiles
+                     : Caps{1024, 2048, 512, 4096, 1023, 8, 6}; // T1 : LONG windows, medium DAG
 }
 
 }  // namespace hypo_b200

@@ -20,6 +20,7 @@ ABI_SYMBOLS = (
     "hypo_gpu_out_bound",
     "hypo_gpu_consensus_batch",
     "hypo_gpu_consensus_batch_device",
+    "hypo_gpu_last_fail_hist",
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
     "hypo_gpu_launch_count",
@@ -139,3 +140,10 @@ def last_timing() -> Tuple[float, int, List[int]]:
     tiers = (C.c_uint32 * 8)()
     lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
     return float(ms.value), int(n.value), [int(x) for x in tiers]
+
+
+def last_fail_hist() -> List[int]:
+    """Why windows were abandoned in a capacity tier during the last batch call (by FailReason)."""
+    h = (C.c_uint32 * 16)()
+    lib().hypo_gpu_last_fail_hist(h)
+    return [int(x) for x in h]

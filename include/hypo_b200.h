@@ -150,6 +150,15 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
  */
 int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[8]);
 
+/*
+ * Diagnostic hook: how many times windows were abandoned in a capacity tier during the most recent
+ * batch call, by reason (index: 1 sequence longer than the tier's columns, 2 16-bit DP range,
+ * 3 node capacity, 4 aligned-list blocks, 5 clique size, 6 edge capacity / in-degree, 7 DFS stack,
+ * 8 LONG path slot, 9 LONG window in a SHORT-only tier).  Every abandoned window is re-run in a
+ * larger tier; this only explains the tier histogram of hypo_gpu_last_timing.
+ */
+int hypo_gpu_last_fail_hist(uint32_t reasons[16]);
+
 /* Number of kernel launches issued by this library since hypo_gpu_init. */
 uint64_t hypo_gpu_launch_count(void);
 
