@@ -32,6 +32,7 @@ struct ScoreParams {
 enum class WindowType : UINT8 { SHORT, LONG };
 
 class WindowBatch;
+class WindowStream;
 
 class Window {
 public:
@@ -104,6 +105,7 @@ public:
 
     friend std::ostream& operator<<(std::ostream&, const Window&);
     friend class WindowBatch;
+    friend class WindowStream;
 
 private:
     bool accept(const PackedSeq<2>& ps) const {

@@ -6,7 +6,9 @@
 #include <omp.h>
 
 #include <cstdint>
+#include <chrono>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -14,6 +16,7 @@
 #include "../../include/hypo_b200.h"
 #include "Window.hpp"
 #include "WindowBatch.hpp"
+#include "WindowStream.hpp"
 
 namespace {
 
@@ -183,6 +186,103 @@ int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win,
     }
     out_off[n_win] = pos;
     return HYPO_OK;
+}
+
+// ---- window streams in the reference's inspect-file format (WindowStream.hpp) ---------------------
+
+// Writes a flat batch as one contig's inspect file: every window preceded by a short strong region,
+// as the pipeline interleaves them; `cons`/`cons_off` are the consensus strings to record.
+int hypo_host_inspect_write(const char* path, const char* contig, const HypoWindowDesc* win, uint64_t n_win,
+                            const HypoArmDesc* arms, const uint8_t* packed, const char* cons,
+                            const uint64_t* cons_off) {
+    using namespace hypo;
+    WindowStream ws;
+    ws.contig = contig ? contig : "ctg";
+    uint64_t pos = 0;
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        const std::string sr = "ACGTTGCA";
+        ws.add_plain("SR", pos, sr);
+        pos += sr.size();
+        const bool lng = d.wtype == HYPO_WINDOW_LONG;
+        PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        std::unique_ptr<Window> wp(new Window(draft, 0, d.draft_len, lng ? WindowType::LONG : WindowType::SHORT));
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) wp->add_internal(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) wp->add_prefix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) wp->add_suffix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_empty; ++i) wp->add_empty();
+        ws.add_window(std::move(wp), lng ? "LNG" : "OTH", pos, std::string(cons + cons_off[w], cons + cons_off[w + 1]));
+        pos += d.draft_len;
+    }
+    std::ofstream os(path);
+    if (!os.is_open()) return HYPO_E_ARG;
+    ws.write(os, true);
+    return os.good() ? HYPO_OK : HYPO_E_ARG;
+}
+
+// Parses an inspect file.  Returns an opaque handle (nullptr on error, message in err[0..err_cap)).
+void* hypo_host_inspect_open(const char* path, char* err, uint64_t err_cap) {
+    using namespace hypo;
+    std::ifstream in(path);
+    std::string msg;
+    std::unique_ptr<WindowStream> ws(new WindowStream);
+    if (!in.is_open()) msg = std::string("cannot open ") + path;
+    else if (ws->read(in, &msg)) return ws.release();
+    if (err && err_cap) { strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+    return nullptr;
+}
+
+void hypo_host_inspect_close(void* h) { delete static_cast<hypo::WindowStream*>(h); }
+
+// counts[0..5] = regions, windows, arms, packed bytes (as the batch packer lays them out),
+// recorded consensus bytes, polished bp
+void hypo_host_inspect_sizes(void* h, uint64_t counts[6]) {
+    using namespace hypo;
+    WindowStream& ws = *static_cast<WindowStream*>(h);
+    WindowBatch b;
+    for (auto& w : ws.windows) b.add(w.get());
+    uint64_t cb = 0;
+    for (auto& c : ws.recorded) cb += c.size();
+    counts[0] = ws.regions.size(); counts[1] = ws.windows.size(); counts[2] = b.arm_desc().size();
+    counts[3] = b.packed().size(); counts[4] = cb; counts[5] = ws.polished_bp();
+}
+
+// The stream's windows as the flat batch of the C ABI plus the recorded consensus strings.
+void hypo_host_inspect_fill(void* h, HypoWindowDesc* win, HypoArmDesc* arms, uint8_t* packed, char* cons,
+                            uint64_t* cons_off) {
+    using namespace hypo;
+    WindowStream& ws = *static_cast<WindowStream*>(h);
+    WindowBatch b;
+    for (auto& w : ws.windows) b.add(w.get());
+    memcpy(win, b.win_desc().data(), b.win_desc().size() * sizeof(HypoWindowDesc));
+    memcpy(arms, b.arm_desc().data(), b.arm_desc().size() * sizeof(HypoArmDesc));
+    memcpy(packed, b.packed().data(), b.packed().size());
+    uint64_t pos = 0;
+    for (size_t i = 0; i < ws.recorded.size(); ++i) {
+        cons_off[i] = pos;
+        memcpy(cons + pos, ws.recorded[i].data(), ws.recorded[i].size());
+        pos += ws.recorded[i].size();
+    }
+    cons_off[ws.recorded.size()] = pos;
+}
+
+// Replays the stream on the device: one generate_consensus_batch over all windows.  Returns the number
+// of windows whose consensus differs from the recorded one (-1: not initialised); *seconds = wall
+// time of the batch call; if out_path is given the stream is written back with the NEW consensus.
+int64_t hypo_host_inspect_replay(void* h, const int8_t scores[6], int device, double* seconds, const char* out_path) {
+    using namespace hypo;
+    WindowStream& ws = *static_cast<WindowStream*>(h);
+    ScoreParams sp{scores[0], scores[1], scores[2], scores[3], scores[4], scores[5]};
+    Window::prepare_for_poa(sp, 1, device);
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t bad = ws.replay();
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (out_path && *out_path) {
+        std::ofstream os(out_path);
+        if (os.is_open()) ws.write(os, false);
+    }
+    return (int64_t)bad;
 }
 
 }  // extern "C"

@@ -33,6 +33,20 @@ def lib():
         L.hypo_host_run.restype = C.c_int
         L.hypo_host_run.argtypes = [C.POINTER(C.c_int8), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_void_p]
+        L.hypo_host_inspect_write.restype = C.c_int
+        L.hypo_host_inspect_write.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        L.hypo_host_inspect_open.restype = C.c_void_p
+        L.hypo_host_inspect_open.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+        L.hypo_host_inspect_close.restype = None
+        L.hypo_host_inspect_close.argtypes = [C.c_void_p]
+        L.hypo_host_inspect_sizes.restype = None
+        L.hypo_host_inspect_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.hypo_host_inspect_fill.restype = None
+        L.hypo_host_inspect_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hypo_host_inspect_replay.restype = C.c_int64
+        L.hypo_host_inspect_replay.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.POINTER(C.c_double),
+                                               C.c_char_p]
         _lib = L
     return _lib
 
@@ -70,3 +84,60 @@ def host_run(batch: WindowBatch, scores: Sequence[int] = (5, -4, -8, 3, -5, -4),
     if rc != 0:
         raise HypoGpuError(rc, "hypo_host_run failed")
     return split_consensus(out, off)
+
+
+# ---- window streams in the reference's inspect-file format (host/WindowStream.hpp) -------------------
+
+def write_inspect(path: str, batch: WindowBatch, consensus: Sequence[str], contig: str = "ctg") -> None:
+    """Stores a batch and the consensus strings to record in the format of the reference's
+    Contig::generate_inspect_file (reference src/Contig.cpp:368-453, src/Window.cpp:63-84)."""
+    blob = "".join(consensus).encode()
+    off = np.zeros(batch.n_win + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in consensus])
+    buf = np.frombuffer(blob + b"\0", np.uint8).copy()
+    rc = lib().hypo_host_inspect_write(path.encode(), contig.encode(), batch.win.ctypes.data, batch.n_win,
+                                       batch.arms.ctypes.data, batch.packed.ctypes.data, buf.ctypes.data,
+                                       off.ctypes.data)
+    if rc != 0:
+        raise OSError(f"cannot write {path}")
+
+
+class InspectStream:
+    """A parsed inspect file: its windows as a flat batch, the recorded consensus strings, and a
+    replay through the Window mirror's public API (one C-ABI call on the device)."""
+
+    def __init__(self, path: str):
+        err = C.create_string_buffer(512)
+        self._h = lib().hypo_host_inspect_open(path.encode(), err, 512)
+        if not self._h:
+            raise ValueError(err.value.decode())
+        counts = (C.c_uint64 * 6)()
+        lib().hypo_host_inspect_sizes(self._h, counts)
+        self.n_regions, self.n_windows, n_arms, n_bytes, n_cons, self.polished_bp = [int(x) for x in counts]
+        win = np.zeros(self.n_windows, WIN_DTYPE)
+        arms = np.zeros(n_arms, ARM_DTYPE)
+        packed = np.zeros(n_bytes + 16, np.uint8)
+        cons = np.zeros(n_cons + 1, np.uint8)
+        off = np.zeros(self.n_windows + 1, np.uint64)
+        lib().hypo_host_inspect_fill(self._h, win.ctypes.data, arms.ctypes.data, packed.ctypes.data,
+                                     cons.ctypes.data, off.ctypes.data)
+        self.batch = WindowBatch(win, arms, packed, {"source": path})
+        self.recorded = split_consensus(cons, off)
+
+    def replay(self, scores: Sequence[int] = (5, -4, -8, 3, -5, -4), device: int = 0, out_path: str = ""):
+        """Returns (windows whose consensus differs from the recorded one, seconds of the batch call)."""
+        sec = C.c_double(0)
+        sc = (C.c_int8 * 6)(*[int(x) for x in scores])
+        bad = lib().hypo_host_inspect_replay(self._h, sc, device, C.byref(sec), out_path.encode())
+        return int(bad), float(sec.value)
+
+    def close(self):
+        if self._h:
+            lib().hypo_host_inspect_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -171,6 +172,44 @@ int hypo_ref_spoa_consensus(int8_t m, int8_t n, int8_t g, const char* seqs,
     std::memcpy(out, c.data(), c.size());
     *out_len = c.size();
     return HYPO_OK;
+}
+
+// Golden window streams: runs the reference on a batch and dumps every window with the REFERENCE'S
+// OWN Window::operator<< (reference src/Window.cpp:63-84), framed the way
+// Contig::generate_inspect_file frames it (reference src/Contig.cpp:373-451: ">name", "#regions",
+// "==========(beg-end)<TAB>TYPE<TAB>" before each window; strong regions with zero counters and the
+// sequence twice).  Used by tests/golden/make_golden.py to produce tests/golden/inspect_ref.txt.gz.
+int hypo_ref_inspect_dump(const char* path, const char* contig, const int8_t scores[6],
+                          const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms,
+                          const uint8_t* packed) {
+    ensure_engines(scores, 1);
+    std::ofstream ofs(path);
+    if (!ofs.is_open()) return HYPO_E_ARG;
+    ofs << ">" << contig << std::endl;
+    ofs << "#" << 2 * n_win << std::endl;
+    uint64_t curr = 0;
+    const std::string sr = "ACGTTGCA";
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        ofs << "==========(" << curr << "-" << curr + sr.size() - 1 << ")\t" << "SR" << "\t" << 0 << "\t" << 0
+            << "\t" << 0 << "\t" << 0 << std::endl;
+        ofs << "++\t" << sr << std::endl;
+        ofs << "++\t" << sr << std::endl;
+        curr += sr.size();
+        hypo::PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        const bool lng = d.wtype == HYPO_WINDOW_LONG;
+        hypo::Window W(draft, 0, d.draft_len, lng ? hypo::WindowType::LONG : hypo::WindowType::SHORT);
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) W.add_internal(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) W.add_prefix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) W.add_suffix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_empty; ++i) W.add_empty();
+        W.generate_consensus(0);
+        ofs << "==========(" << curr << "-" << curr + W.get_window_len() - 1 << ")\t" << (lng ? "LNG" : "OTH") << "\t";
+        ofs << W;
+        curr += W.get_window_len();
+    }
+    return ofs.good() ? HYPO_OK : HYPO_E_ARG;
 }
 
 int hypo_ref_max_threads(void) { return omp_get_max_threads(); }

@@ -16,7 +16,14 @@ neither travels to the GPU box.
       the consensus produced by the compiled, UNMODIFIED reference (default flags => SISD).
       LONG windows only contain the arms the reference's insert-time Filter accepted.
 
-Usage:  make -C oracle ref && python tests/golden/make_golden.py
+  inspect_ref.txt.gz
+      A window stream in the reference's dump format (Contig::generate_inspect_file, reference
+      src/Contig.cpp:368-453): every window printed by the reference's own Window::operator<<
+      (src/Window.cpp:63-84) after the reference computed its consensus (oracle/ref_driver.cpp:
+      hypo_ref_inspect_dump).  Input and expected output of hypo_b200/host/WindowStream and
+      tools/replay_inspect.py.
+
+Usage:  make -C oracle ref && python tests/golden/make_golden.py [inspect]
 """
 import gzip
 import json
@@ -89,13 +96,43 @@ def window_fixture():
             "groups": groups}
 
 
+def inspect_fixture():
+    import ctypes as C
+    import tempfile
+    from tests.oracle_util import ref_lib
+    rng = np.random.default_rng(20261018)
+    specs = list(edge_case_windows())
+    for kind in ("internal", "backbone", "prefix", "suffix", "mixed"):
+        specs += [random_window(rng, length=int(rng.integers(5, 110)), n_arms=int(rng.integers(3, 36)), kind=kind,
+                                err=float(rng.choice([0.01, 0.05]))) for _ in range(10)]
+    specs += [random_window(rng, length=int(rng.integers(120, 300)), n_arms=int(rng.integers(4, 12)),
+                            kind=str(rng.choice(["internal", "mixed"])), wtype=WINDOW_LONG) for _ in range(6)]
+    batch = build_batch(specs)
+    lib = ref_lib(False)
+    sc = (C.c_int8 * 6)(*DEFAULT_SCORES)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "inspect_ctg.txt")
+        rc = lib.hypo_ref_inspect_dump(path.encode(), b"ctg_golden", sc, batch.win.ctypes.data_as(C.c_void_p),
+                                       C.c_uint64(batch.n_win), batch.arms.ctypes.data_as(C.c_void_p),
+                                       batch.packed.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        text = open(path, "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, "inspect_ref.txt.gz"), "wb", mtime=0) as f:
+        f.write(text)
+    return batch.n_win, len(text)
+
+
 def dump(name, obj):
     with gzip.GzipFile(os.path.join(HERE, name), "wb", mtime=0) as f:
         f.write(json.dumps(obj, separators=(",", ":")).encode())
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "inspect":
+        print("inspect stream: %d windows, %d bytes" % inspect_fixture())
+        sys.exit(0)
     dump("spoa_global_consensus.json.gz", spoa_fixture())
     wf = window_fixture()
     dump("windows.json.gz", wf)
     print("windows:", sum(len(g["windows"]) for g in wf["groups"]))
+    print("inspect stream: %d windows, %d bytes" % inspect_fixture())

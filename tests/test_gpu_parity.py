@@ -130,3 +130,29 @@ def test_large_random_parity_stresses_concurrent_sort():
         b = synth_batch(seed, **kw)
         want, _ = oracle_consensus(b)
         _assert_same(native.consensus(b), want, b, f"large/{kw}")
+
+
+def test_many_read_windows_take_the_wide_tier():
+    """100-200 reads per window: routed past the compact tiers by the node estimate (or abandoned
+    there and re-run), bit-exact either way; the diagnostics explain every abandonment."""
+    from hypo_b200.hostlib import synth_batch
+    for seed, kw in ((41, dict(n_win=160, length=100, n_arms=100, kind="internal", err=0.01)),
+                     (42, dict(n_win=120, length=50, n_arms=200, kind="mixed", err=0.02)),
+                     (43, dict(n_win=300, length=120, n_arms=30, kind="internal", err=0.05))):
+        b = synth_batch(seed, **kw)
+        want, _ = oracle_consensus(b)
+        _assert_same(native.consensus(b), want, b, f"wide/{kw}")
+        _, _, tiers = native.last_timing()
+        reasons = native.last_fail_hist()
+        assert sum(tiers) >= b.n_win                      # every window ran, some in more than one tier
+        assert sum(reasons) == sum(tiers) - b.n_win       # one recorded reason per abandonment
+
+
+def test_clique_beyond_acgt_leaves_the_compact_tier():
+    """An N in a backbone draft aligned with all four bases makes a five-letter clique: more peers than
+    the compact tier's aligned-list blocks hold, so the window is re-run in a tier with wider blocks."""
+    arms = ["AAAAAAAAA", "AAAACAAAA", "AAAAGAAAA", "AAAATAAAA"]
+    specs = [WindowSpec("AAAANAAAA", [], arms * 2, arms * 2, 0, 0) for _ in range(8)]
+    b = build_batch(specs)
+    want, _ = oracle_consensus(b)
+    _assert_same(native.consensus(b), want, b, "five-letter clique")

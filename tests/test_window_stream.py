@@ -1,0 +1,83 @@
+"""Window streams in the reference's dump format (hypo_b200/host/WindowStream.hpp).
+
+The golden stream tests/golden/inspect_ref.txt.gz was printed by the reference's own
+Window::operator<< after the reference computed each consensus (tests/golden/make_golden.py)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from hypo_b200.batch import build_batch
+from hypo_b200.hostlib import InspectStream, write_inspect
+from hypo_b200.synth import edge_case_windows, random_batch
+from tests.oracle_util import DEFAULT_SCORES, oracle_consensus
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture()
+def golden_path(tmp_path):
+    p = tmp_path / "inspect_ctg_golden.txt"
+    p.write_bytes(gzip.open(os.path.join(HERE, "golden", "inspect_ref.txt.gz")).read())
+    return str(p)
+
+
+def test_reference_stream_parses_and_pins_the_oracle(golden_path):
+    s = InspectStream(golden_path)
+    assert s.n_regions == 154 and s.n_windows == 71
+    assert s.polished_bp == int(s.batch.win["draft_len"].sum())
+    got, _ = oracle_consensus(s.batch, DEFAULT_SCORES)
+    assert got == s.recorded          # the C restatement agrees with what the reference recorded
+    assert (s.batch.win["wtype"] == 1).sum() >= 6   # the LNG regions come back as LONG windows
+
+
+def test_write_read_round_trip(tmp_path):
+    b = build_batch(edge_case_windows())
+    b2 = random_batch(5, 40, kind="mixed", length=60, n_arms=14, err=0.04)
+    for k, batch in enumerate((b, b2)):
+        cons, _ = oracle_consensus(batch)
+        p = str(tmp_path / f"inspect_{k}.txt")
+        write_inspect(p, batch, cons, contig=f"ctg{k}")
+        s = InspectStream(p)
+        # windows without any arm and without empties are plain regions in the dump
+        keep = [w for w in range(batch.n_win)
+                if int(batch.win["n_internal"][w] + batch.win["n_pre"][w] + batch.win["n_suf"][w] + batch.win["n_empty"][w]) > 0]
+        assert s.n_windows == len(keep) and s.n_regions == 2 * batch.n_win
+        assert s.recorded == [cons[w] for w in keep]
+        ref = batch.select(np.array(keep))
+        for w in range(s.n_windows):
+            assert s.batch.spec(w) == ref.spec(w)
+
+
+def test_malformed_stream_is_rejected(tmp_path):
+    p = tmp_path / "bad.txt"
+    p.write_text(">c\n#1\n==========(0-3)\tOTH\t1\t0\t0\t0\n++\tACGT\n")
+    with pytest.raises(ValueError):
+        InspectStream(str(p))
+    p.write_text(">c\n#2\n==========(0-3)\tSR\t0\t0\t0\t0\n++\tACGT\n++\tACGT\n")
+    with pytest.raises(ValueError):
+        InspectStream(str(p))
+    with pytest.raises(ValueError):
+        InspectStream(str(tmp_path / "missing.txt"))
+
+
+@pytest.mark.gpu
+def test_replay_reference_stream_on_the_gpu(golden_path, tmp_path):
+    s = InspectStream(golden_path)
+    out = str(tmp_path / "replayed.txt")
+    bad, sec = s.replay(DEFAULT_SCORES, 0, out)
+    assert bad == 0 and sec > 0
+    # written back with the GPU consensus, the stream is byte-identical to the reference's dump
+    assert open(out, "rb").read() == open(golden_path, "rb").read()
+
+
+@pytest.mark.gpu
+def test_replay_detects_a_wrong_recorded_consensus(tmp_path):
+    batch = random_batch(9, 32, kind="internal", length=50, n_arms=10)
+    cons, _ = oracle_consensus(batch)
+    cons[3] = cons[3] + "A"
+    p = str(tmp_path / "tampered.txt")
+    write_inspect(p, batch, cons)
+    bad, _ = InspectStream(p).replay(DEFAULT_SCORES, 0)
+    assert bad == 1
