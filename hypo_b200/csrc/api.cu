@@ -227,7 +227,7 @@ struct Tier {
 // Static routing skips tiers a window is unlikely to fit: est = longest sequence + 1.5 % of all bases
 // (every base of a ~1 %-error read opens a new node with about that probability); a wrong guess only
 // costs the run-time overflow path.
-// T0b: SHORT windows up to 255 columns (two tiles), 12 warps/SM.
+// T0b: windows up to 255 columns (two tiles; SHORT and LONG), 12 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 // The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
@@ -236,7 +236,7 @@ const Tier kTiers[] = {
     {true, true, false, false, 212, 328, 212, 640, 127, 9, 3, 201, 1},
     {true, true, false, false, 320, 576, 304, 1024, 127, 8, 2, 300, 2},
     {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 4},
-    {true, false, false, false, 384, 768, 256, 1536, 255, 6, 2, 364, 4},
+    {true, false, true, false, 384, 768, 256, 1536, 255, 6, 2, 364, 4},
     {true, false, true, false, 1024, 2048, 512, 4096, 1023, 5, 1, 972, 5},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 6},
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 7},
@@ -350,7 +350,8 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         int blocks = g.sms * bps;
         uint64_t warps = (uint64_t)blocks * wpb;
         if (warps > n_work) { blocks = (int)((n_work + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
-        const uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 63) & ~63ull;   // + dummy rows
+        // matrix rows (+ spare) and, behind them, the two boundary arrays of the multi-tile fill
+        const uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
         // keep the DP workspace bounded: shrink the grid if the slots would exceed ~24 GB
         while (warps * h_slot * 2 > (24ull << 30) && blocks > 1) { blocks = (blocks + 1) / 2; warps = (uint64_t)blocks * wpb; }
         CUDA_TRY(g.H.reserve(warps * h_slot * sizeof(int16_t)));

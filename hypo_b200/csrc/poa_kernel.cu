@@ -314,66 +314,72 @@ __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __res
     return ec;
 }
 
-// One-tile fill (sequences of at most 127 symbols).  The last three rows stay in registers, each
-// with its exclusive prefix max, which is exactly the value the lane to the left holds in its last
-// column: rows whose predecessors all lie within three ranks (rowinfo bits 28-30; 97 % of the rows
-// of the 30 x 120 shape) touch neither shared memory, nor the matrix, nor the shuffle unit before
-// the scan.  The loop is unrolled by three so that the roles of the three register sets rotate
-// without moves; build_rows pads the row records with harmless dummy rows to a multiple of three.
+// The fill works one 128-column tile at a time, all rows of a tile before the next tile (cell (i, j)
+// only needs columns <= j).  The last three rows of the tile stay in registers, each with its
+// exclusive prefix max, which is exactly the value the lane to the left holds in its last column:
+// rows whose predecessors all lie within three ranks (rowinfo bits 28-30; 97 % of the rows of the
+// 30 x 120 shape) touch neither shared memory, nor the matrix, nor the shuffle unit before the scan.
+// Tiles after the first one are seeded through lane 0: its "lane to the left" is column 128t-1 of
+// the same row, which the previous tile's pass left in a per-row boundary array (rows are
+// non-decreasing after the horizontal pass, so that one value is also the prefix max of everything
+// to the left).
+// (Unrolling the row loop by three to rotate the three register sets without moves removes 13 % of
+// the kernel's instructions but no longer fits the L0 instruction cache: measured 10 % slower.)
 struct RowRegs {
     uint32_t x[kNR];   // the lane's four columns
-    uint32_t left;     // last column of the lane to the left, in both halves (kNegInf2 on lane 0)
+    uint32_t left;     // last column of the lane to the left, in both halves
+};
+
+struct DpConst {
+    uint32_t g2, mm2, nn2, let4, neg2;
+    uint32_t lane0;      // non-zero on lane 0
+    uint32_t row0_left;  // `left` of the virtual row 0: -inf on lane 0 of the first tile, else 0
+    uint32_t xinit0;     // initial value of the lane's first register (ROV pins column 0 to 0)
+    unsigned stride;     // int16 elements per matrix row
 };
 
 // Rare rows with a predecessor further back (or none at all): predecessor rows come from the matrix.
 // (inlined: a call inside the row loop costs 2 % even though it is almost never taken)
-#ifdef HYPO_FAR_NOINLINE
-#define HYPO_FAR_ATTR __noinline__
-#else
-#define HYPO_FAR_ATTR __forceinline__
-#endif
-template <bool kSmem, int kTier>
-__device__ HYPO_FAR_ATTR uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint32_t info, int rk,
-                                        const int16_t* __restrict__ Hl, uint32_t p1a, uint32_t p1b,
-                                        uint32_t l1, uint32_t pf0, uint32_t pf1, uint32_t g2,
-                                        uint32_t row0_left, uint32_t xinit0) {
+template <bool kSmem, bool kMulti>
+__device__ __forceinline__ uint2 relax_far(typename Mem<kSmem>::addr_t prows, uint32_t info, int rk,
+                                           const int16_t* __restrict__ Hl, const RowRegs& d1, const uint32_t (&pf)[kNR],
+                                           const DpConst& c, const int16_t* __restrict__ bnd_prev) {
     typedef Mem<kSmem> M;
-    uint32_t x[kNR] = {xinit0, kNegInf2};
-    const uint32_t pf[kNR] = {pf0, pf1};
+    uint32_t x[kNR] = {c.xinit0, c.neg2};
     const int np = (info >> 16) & 0xff;
     if (np == 0) {
         // no predecessor: virtual row 0 (reference :300-301)
         const uint32_t p[kNR] = {0u, 0u};
-        relax(x, p, row0_left, pf, g2);
+        relax(x, p, c.row0_left, pf, c.g2);
     } else {
         typename M::addr_t pa = prows + 2u * (info & 0xffffu);
 #pragma unroll 1
         for (int k = 0; k < np; ++k, pa += 2) {
             const unsigned prow = M::ld16(pa);
             if (prow == (unsigned)rk) {
-                const uint32_t p[kNR] = {p1a, p1b};
-                relax(x, p, l1, pf, g2);
+                relax(x, d1.x, d1.left, pf, c.g2);
             } else {
-                const uint2 q = ldg64(Hl + prow * (unsigned)kTileCols);
+                const uint2 q = ldg64(Hl + prow * (kMulti ? c.stride : (unsigned)kTileCols));
                 const uint32_t p[kNR] = {q.x, q.y};
                 uint32_t left = __shfl_up_sync(kFull, q.y, 1);
-                left = row0_left ? kNegInf2 : left;
-                relax(x, p, left, pf, g2);
+                if (c.lane0) {
+                    left = c.neg2;
+                    if (kMulti && bnd_prev) left = bcast16(bnd_prev[prow]);
+                }
+                relax(x, p, left, pf, c.g2);
             }
         }
     }
     return make_uint2(x[0], x[1]);
 }
 
-struct DpConst {
-    uint32_t g2, mm2, nn2, let4, row0_left, neg2, xinit0;
-};
-
-// One DP row: d1/d2/d3 hold the rows 1/2/3 ranks back; the new row replaces d3.
-template <bool kSmem, int kTier>
+// One DP row: d1/d2/d3 hold the rows 1/2/3 ranks back; the new row replaces d3.  `seed2` is what
+// lane 0 feeds into the exclusive prefix max: -inf in the first tile, the row's boundary value after.
+template <bool kSmem, bool kMulti>
 __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1, const RowRegs& d2, RowRegs& d3,
                                        const DpConst& c, typename Mem<kSmem>::addr_t prows,
-                                       const int16_t* __restrict__ Hl, int16_t*& Hrow) {
+                                       const int16_t* __restrict__ Hl, int16_t*& Hrow, uint32_t seed2,
+                                       const int16_t* __restrict__ bnd_prev, int16_t* __restrict__ bnd_next) {
     uint32_t pf[kNR];
     profile_regs(c.let4, (info >> 24) & 7u, c.mm2, c.nn2, pf);
     // first column: NW/LOV follow the vertical rule (done by relax with diag = -inf); ROV pins it to
@@ -388,143 +394,78 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
         if (near & 2u) relax(x, d2.x, d2.left, pf, c.g2);
         if (near & 4u) relax(x, d3.x, d3.left, pf, c.g2);
     } else {
-        const uint2 q = relax_far<kSmem, kTier>(prows, info, rk, Hl, d1.x[0], d1.x[1], d1.left, pf[0], pf[1], c.g2,
-                                         c.row0_left, c.xinit0);
+        const uint2 q = relax_far<kSmem, kMulti>(prows, info, rk, Hl, d1, pf, c, bnd_prev);
         x[0] = q.x; x[1] = q.y;
     }
-    const uint32_t cb = warp_excl_max(scan_inlane(x, c.neg2), c.row0_left, c.neg2);
+    const uint32_t cb = warp_excl_max(scan_inlane(x, c.neg2), c.lane0, seed2);
     d3.x[0] = __vmaxs2(x[0], cb);
     d3.x[1] = __vmaxs2(x[1], cb);
-    d3.left = cb;   // == last column of the lane to the left (kNegInf for lane 0)
-    Hrow += kTileCols;
+    d3.left = cb;   // == last column of the lane to the left (lane 0: the seed)
+    Hrow += kMulti ? c.stride : (unsigned)kTileCols;
     stg64(Hrow, d3.x[0], d3.x[1]);
+    if (kMulti && bnd_next && lane_id() == 31) bnd_next[rk + 1] = (int16_t)hi16(d3.x[1]);
 }
 
-template <bool kSmem, int kTier>
-__device__ __noinline__ EndCell dp_fill_one(const GState& st, int16_t* __restrict__ H, int len, int type,
-                                            Scores sc) {
+// `bnd`: two boundary arrays of (n + 2) int16 each behind the matrix (multi-tile tiers only).
+template <bool kSmem, int kTier, bool kMulti>
+__device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restrict__ H, int16_t* __restrict__ bnd,
+                                        int bnd_len, int len, int tiles, int type, Scores sc) {
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
+    const int n = g.n_nodes;
+    const int ntiles = kMulti ? tiles : 1;
+    typedef Mem<kSmem> M;
     // loop constants are made opaque so that ptxas keeps them in registers instead of
     // re-deriving them in every row
     DpConst c;
     c.g2 = opaque(bcast16(sc.g));
     c.mm2 = opaque(bcast16(sc.m - sc.g));
     c.nn2 = opaque(bcast16(sc.n - sc.g));
-    c.let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + lane * 4));
-    c.row0_left = opaque(lane == 0 ? kNegInf2 : 0u);
     c.neg2 = opaque(kNegInf2);
-    c.xinit0 = opaque((type == kROV && lane == 0) ? (kNegInf2 & 0xffff0000u) : kNegInf2);
-    const int16_t* Hl = opaque_ptr(H + lane * 4);
-    const int n = g.n_nodes;
-    typedef Mem<kSmem> M;
-    typename M::addr_t ri = M::addr(g.rowinfo);
+    c.lane0 = opaque(lane == 0 ? 1u : 0u);
+    c.stride = (unsigned)ntiles * kTileCols;
     const typename M::addr_t prows = M::addr(g.prows);
+    if (kMulti && lane == 0) { bnd[0] = 0; bnd[bnd_len] = 0; }   // virtual row 0: H^[0][j] = 0
 
-    // row 0: H^[0][j] = 0
-    int16_t* Hrow = opaque_ptr(H + lane * 4);
-    stg64(Hrow, 0u, 0u);
-    RowRegs A, B, C;
-    A.x[0] = A.x[1] = 0u; A.left = c.row0_left;
-    B = A; C = A;
+#pragma unroll 1
+    for (int t = 0; t < ntiles; ++t) {
+        const unsigned toff = (unsigned)t * kTileCols;
+        c.let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + toff + lane * 4));
+        c.row0_left = opaque((lane == 0 && t == 0) ? kNegInf2 : 0u);
+        c.xinit0 = opaque((type == kROV && lane == 0 && t == 0) ? (kNegInf2 & 0xffff0000u) : kNegInf2);
+        const int16_t* Hl = opaque_ptr(H + toff + lane * 4);
+        const int16_t* bnd_prev = (kMulti && t > 0) ? bnd + ((t - 1) & 1) * bnd_len : nullptr;
+        int16_t* bnd_next = (kMulti && t + 1 < ntiles) ? bnd + (t & 1) * bnd_len : nullptr;
+        typename M::addr_t ri = M::addr(g.rowinfo);
 
-    uint32_t info = M::ld32(ri);
-#ifdef HYPO_DP_UNROLL3
-    // Rotating the roles of the three register sets by unrolling saves nine moves per row, but the
-    // tripled loop body no longer fits the L0 instruction cache next to the other phases (measured:
-    // -13 % instructions, +10 % time), so the rolled loop below is the default.
-#pragma unroll 1
-    for (int rk = 0; rk < n; rk += 3) {
-        // three rows per trip (records n .. n+2 are dummies), the next trip's first record ahead
-        const uint32_t i0 = info, i1 = M::ld32(ri + 4), i2 = M::ld32(ri + 8);
-        info = M::ld32(ri + 12);
-        ri += 12;
-        dp_row<kSmem, kTier>(i0, rk, A, B, C, c, prows, Hl, Hrow);       // new row -> C
-        dp_row<kSmem, kTier>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow);   // new row -> B
-        dp_row<kSmem, kTier>(i2, rk + 2, B, C, A, c, prows, Hl, Hrow);   // new row -> A
-    }
-#else
-#pragma unroll 1
-    for (int rk = 0; rk < n; ++rk) {
-        const uint32_t i0 = info;
-        ri += 4;
-        info = M::ld32(ri);   // one row ahead (the array has spare entries)
-        dp_row<kSmem, kTier>(i0, rk, A, B, C, c, prows, Hl, Hrow);   // new row -> C
-        const RowRegs t = C;
-        C = B; B = A; A = t;
-    }
-#endif
-    __syncwarp();
-    return end_cell(g, H, n, kTileCols, len, type);
-}
+        // row 0: H^[0][j] = 0
+        int16_t* Hrow = opaque_ptr(H + toff + lane * 4);
+        stg64(Hrow, 0u, 0u);
+        RowRegs A, B, C;
+        A.x[0] = A.x[1] = 0u; A.left = c.row0_left;
+        B = A; C = A;
 
-// Multi-tile fill: rows of up to `tiles` 128-column tiles, every predecessor row read back from the
-// matrix; `carry` threads the prefix max across the tiles of a row.
-template <bool kSmem, int kTier>
-__device__ __noinline__ EndCell dp_fill_tiles(const GState& st, int16_t* __restrict__ H, int len, int tiles,
-                                              int type, Scores sc) {
-    const Graph g = make_graph<kSmem, kTier>(st);
-    const int lane = lane_id();
-    const int cols = tiles * kTileCols;
-    const uint32_t g2 = bcast16(sc.g);
-    const uint32_t mm2 = bcast16(sc.m - sc.g), nn2 = bcast16(sc.n - sc.g);
-    int16_t* Hl = H + lane * 4;
-    const int n = g.n_nodes;
-
-    // row 0: H^[0][j] = 0
+        uint32_t info = M::ld32(ri);
+        uint32_t seed = (kMulti && bnd_prev) ? bcast16(bnd_prev[1]) : c.neg2;
 #pragma unroll 1
-    for (int t = 0; t < tiles; ++t)
-        *reinterpret_cast<uint2*>(Hl + t * kTileCols) = make_uint2(0u, 0u);
-    __syncwarp();
-
-    uint32_t info_next = g.rowinfo[0];
-#pragma unroll 1
-    for (int rk = 0; rk < n; ++rk) {
-        const uint32_t info = info_next;
-        info_next = g.rowinfo[rk + 1];   // one row ahead (the array has a spare entry)
-        const int ps = info & 0xffff;
-        const int pe = ps + ((info >> 16) & 0xff);
-        const uint32_t code = (info >> 24) & 7u;
-        const unsigned rowoff = (unsigned)(rk + 1) * (unsigned)cols;
-        uint32_t carry = kNegInf2;   // prefix max of the tiles to the left, in both halves
-#pragma unroll 1
-        for (int t = 0; t < tiles; ++t) {
-            const unsigned toff = (unsigned)t * kTileCols;
-            uint32_t x[kNR] = {kNegInf2, kNegInf2};
-            uint32_t pf[kNR];
-            profile_regs(*reinterpret_cast<const uint32_t*>(g.colseq + toff + lane * 4), code, mm2, nn2, pf);
-            if (ps == pe) {
-                // no predecessor: virtual row 0 (reference :300-301)
-                const uint32_t p[kNR] = {0u, 0u};
-                const uint32_t left = (lane == 0 && t == 0) ? kNegInf2 : 0u;
-                relax(x, p, left, pf, g2);
-            } else {
-#pragma unroll 1
-                for (int k = ps; k < pe; ++k) {
-                    const unsigned prow = g.prows[k];
-                    const uint2 q = *reinterpret_cast<const uint2*>(Hl + prow * (unsigned)cols + toff);
-                    const uint32_t p[kNR] = {q.x, q.y};
-                    uint32_t left = __shfl_up_sync(kFull, q.y, 1);
-                    if (lane == 0) {
-                        if (t == 0) left = kNegInf2;
-                        else left = (uint32_t)(uint16_t)H[prow * (unsigned)cols + toff - 1] << 16;
-                    }
-                    relax(x, p, left, pf, g2);
-                }
-            }
-            if (type == kROV && t == 0 && lane == 0) x[0] = (x[0] & 0xffff0000u);
-            const uint32_t tot2 = scan_inlane(x, kNegInf2);
-            const uint32_t cb = __vmaxs2(warp_excl_max(tot2, lane == 0 ? kNegInf2 : 0u, kNegInf2), carry);
-#pragma unroll
-            for (int r = 0; r < kNR; ++r) x[r] = __vmaxs2(x[r], cb);
-            carry = __shfl_sync(kFull, __vmaxs2(cb, tot2), 31);
-            *reinterpret_cast<uint2*>(Hl + rowoff + toff) = make_uint2(x[0], x[1]);
+        for (int rk = 0; rk < n; ++rk) {
+            const uint32_t i0 = info, s0 = seed;
+            ri += 4;
+            info = M::ld32(ri);   // one row ahead (the array has spare entries)
+            if (kMulti && bnd_prev) seed = bcast16(bnd_prev[rk + 2]);
+            dp_row<kSmem, kMulti>(i0, rk, A, B, C, c, prows, Hl, Hrow, s0, bnd_prev, bnd_next);   // new row -> C
+            const RowRegs r = C;
+            C = B; B = A; A = r;
         }
-        __syncwarp();   // lane 0 reads lane 31's column of earlier rows (tile boundary)
+        __syncwarp();   // the boundary values of this tile are read by every lane in the next one
     }
-    __syncwarp();
-    return end_cell(g, H, n, cols, len, type);
+    return end_cell(g, H, n, (int)c.stride, len, type);
 }
+// Emitted here (not at its first use) so that the hottest loop of the compact tier sits at the front
+// of the kernel's code: with 27 warps in different phases the placement of the row loop relative
+// to the other per-read phases decides how well the instruction caches hold (measured: 5 %).
+template __device__ EndCell dp_fill_row<true, 0, false>(const GState&, int16_t* __restrict__, int16_t* __restrict__, int,
+                                                    int, int, int, Scores);
 
 // ------------------------------------------------------------------------------------------
 // Traceback (reference sisd_alignment_engine.cpp:344-437).
@@ -540,7 +481,7 @@ struct AlnSpan {
 };
 
 template <bool kSmem, int kTier>
-__device__ __noinline__ AlnSpan traceback(const GState& st, const int16_t* __restrict__ H, int cols,
+__device__ __noinline__ AlnSpan traceback_dp(const GState& st, const int16_t* __restrict__ H, int cols,
                                           EndCell ec, int type, Scores sc, int max_steps) {
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
@@ -1295,7 +1236,7 @@ __device__ __noinline__ void build_rows(const GState& st) {
         }
         base += total;
     }
-    // dummy records n .. n+2 (the one-tile fill works in trips of three rows) + the one read ahead
+    // spare records behind the last row (the fill reads one record ahead)
     if (lane < 4) g.rowinfo[n + lane] = 1u << kRowNearShift;
     if (lane == 0) { g.fp[0] = 0; g.fp4[0] = 0; }
     __syncwarp();
@@ -1443,17 +1384,18 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
         if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return give_up(st, kFailRange);
-        EndCell ec = kOneTile ? dp_fill_one<kSmem, kTier>(st, H, len, s.type, sc)
-                              : dp_fill_tiles<kSmem, kTier>(st, H, len, tiles, s.type, sc);
+        // boundary arrays of the multi-tile fill live behind the matrix slot
+        const int bnd_len = caps.ncap + 4;
+        int16_t* bnd = H + (size_t)(caps.ncap + 4) * (size_t)(caps.tiles * kTileCols);
+        EndCell ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
         if (ec.tie && !st.exact) {
             // the reference breaks this tie by rank in ITS order: derive it and redo the fill
             if (!topo_sort<kSmem, kTier>(st, caps)) return false;
             st.exact = true;
             build_rows<kSmem, kTier>(st);
-            ec = kOneTile ? dp_fill_one<kSmem, kTier>(st, H, len, s.type, sc)
-                          : dp_fill_tiles<kSmem, kTier>(st, H, len, tiles, s.type, sc);
+            ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
         }
-        span = traceback<kSmem, kTier>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
+        span = traceback_dp<kSmem, kTier>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
         // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
         // written back: without this every DP row ends up in HBM (1 TB per million windows) just
         // to be overwritten by the next read.
