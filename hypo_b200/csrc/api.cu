@@ -236,8 +236,8 @@ const Tier kTiers[] = {
     {true, true, false, false, 212, 328, 212, 640, 127, 9, 3, 201, 1},
     {true, true, false, false, 320, 576, 304, 1024, 127, 8, 2, 300, 2},
     {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 4},
-    {true, false, true, false, 384, 768, 256, 1536, 255, 6, 2, 364, 4},
-    {true, false, true, false, 1024, 2048, 512, 4096, 1023, 5, 1, 972, 5},
+    {true, false, true, false, 384, 768, 384, 1536, 255, 6, 2, 364, 4},
+    {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 5},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 6},
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 7},
 };

@@ -203,8 +203,8 @@ __host__ __device__ constexpr Caps fixed_caps(int tier) {
     return tier == 0 ? Caps{212, 328, 212, 640, 127, 1, 3}      // Tc : compact, 27 warps / SM
          : tier == 1 ? Caps{320, 576, 304, 1024, 127, 1, 4}     // T0 : one tile
          : tier == 2 ? Caps{512, 1024, 384, 2048, 127, 1, 6}    // Tw : one tile, many reads per window
-         : tier == 3 ? Caps{384, 768, 256, 1536, 255, 2, 6}     // T0b: two tiles
-                     : Caps{1024, 2048, 512, 4096, 1023, 8, 6}; // T1 : LONG windows, medium DAG
+         : tier == 3 ? Caps{384, 768, 384, 1536, 255, 2, 6}     // T0b: two tiles
+                     : Caps{1024, 1920, 1024, 4096, 1023, 8, 4}; // T1 : LONG windows, medium DAG
 }
 
 }  // namespace hypo_b200
