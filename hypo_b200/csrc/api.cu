@@ -88,6 +88,8 @@ struct Ctx {
     int smem_optin = 0;
     int8_t scores[6];
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host-buffer entry point: H2D of the batch's tail
+    cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
     uint64_t launches = 0;
     DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
     DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp;
@@ -253,10 +255,13 @@ int check_scores(const int8_t s[6]) {
 // bound[w] bytes at d_out + d_out_pos[w].
 int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t n_arms,
                const uint8_t* d_packed, uint64_t packed_bytes, char* d_out, const uint64_t* d_out_pos,
-               uint32_t* d_out_len, const WinStat* d_stats, cudaStream_t stream) {
-    g.poa_ms = 0.f;
-    g.poa_launches = 0;
-    memset(g.tier_windows, 0, sizeof(g.tier_windows));
+               uint32_t* d_out_len, const WinStat* d_stats, cudaStream_t stream, bool accumulate = false) {
+    if (!accumulate) {
+        g.poa_ms = 0.f;
+        g.poa_launches = 0;
+        memset(g.tier_windows, 0, sizeof(g.tier_windows));
+        memset(g.fail_hist, 0, sizeof(g.fail_hist));
+    }
     if (n_win == 0) return HYPO_OK;
     if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
     // control block: [0..kNumTiers) TierMax, then queue counters
@@ -402,25 +407,34 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
             pend[nxt] += over;
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(g.fail_hist, d_fail, sizeof(g.fail_hist), cudaMemcpyDeviceToHost, stream));
+    uint32_t* h_fail = (uint32_t*)((char*)g.pinned_ctrl + 2560);
+    CUDA_TRY(cudaMemcpyAsync(h_fail, d_fail, sizeof(g.fail_hist), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int k = 0; k < kNumFailReasons; ++k) g.fail_hist[k] += h_fail[k];
     return HYPO_OK;
 }
 
+// Per-window static facts and output bounds of windows [0, n_win) of d_win into d_stats / d_bound.
+// n_arms / packed_bytes are the limits the descriptors are validated against (`quiet`: a violation is
+// reported as HYPO_E_ARG without a message: the pipelined path uses it to detect an input whose head
+// windows reference data of the tail).
 int prepare_stats(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t n_arms,
-                  uint64_t packed_bytes, uint64_t* d_bound, cudaStream_t stream) {
-    CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 64));
-    uint32_t* d_bad = (uint32_t*)((char*)g.stats.p + sizeof(WinStat) * n_win);
+                  uint64_t packed_bytes, WinStat* d_stats, uint64_t* d_bound, cudaStream_t stream,
+                  bool quiet = false) {
+    uint32_t* d_bad = (uint32_t*)((char*)g.stats.p + g.stats.cap - 64);
     CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), stream));
     const int tb = 128;
     classify_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_arms, n_win, n_arms, packed_bytes,
-                                                                        (WinStat*)g.stats.p, d_bound, d_bad);
+                                                                        d_stats, d_bound, d_bad);
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     uint32_t* h_bad = (uint32_t*)((char*)g.pinned_ctrl + 2048);
     CUDA_TRY(cudaMemcpyAsync(h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    if (*h_bad) return fail(HYPO_E_ARG, "%u window descriptor(s) reference arms/bytes out of range", *h_bad);
+    if (*h_bad) {
+        if (quiet) return HYPO_E_ARG;
+        return fail(HYPO_E_ARG, "%u window descriptor(s) reference arms/bytes out of range", *h_bad);
+    }
     return HYPO_OK;
 }
 
@@ -452,6 +466,9 @@ int hypo_gpu_init(const int8_t scores[6], int device) {
         return fail(HYPO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     if (!g.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    if (!g.ev_head) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_head, cudaEventDisableTiming));
+    if (!g.ev_tail) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_tail, cudaEventDisableTiming));
     if (!g.pinned_ctrl) CUDA_TRY(cudaHostAlloc(&g.pinned_ctrl, 4096, cudaHostAllocDefault));
     if (!g.ev0) CUDA_TRY(cudaEventCreate(&g.ev0));
     if (!g.ev1) CUDA_TRY(cudaEventCreate(&g.ev1));
@@ -492,13 +509,20 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
     cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
     if (n_win == 0) return HYPO_OK;
     CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
+    CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
     if (int rc = prepare_stats((const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, n_arms, packed_bytes,
-                               (uint64_t*)g.out_off.p, s))
+                               (WinStat*)g.stats.p, (uint64_t*)g.out_off.p, s))
         return rc;
     return run_device((const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, n_arms, d_packed, packed_bytes, d_out,
                       d_out_pos, d_out_len, (const WinStat*)g.stats.p, s);
 }
 
+// Host-buffer entry point.  The input is copied in two parts on a second stream: a head of the windows
+// (with the arms and packed bytes they reference) and the tail; the POA kernels of the head run while the
+// tail is still crossing PCIe, which hides most of the H2D time behind compute.  This relies on the
+// batch being laid out in window order (what hypo::WindowBatch and every sane packer produce); the head's
+// descriptors are validated on the device against the head's limits, and an input that is not laid out
+// that way silently takes the single-copy path instead.
 int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
                              const uint8_t* packed, uint64_t packed_bytes, char* out, uint64_t out_cap,
                              uint64_t* out_off) {
@@ -514,43 +538,127 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     CUDA_TRY(g.win.reserve(sizeof(WinDesc) * n_win));
     CUDA_TRY(g.arms.reserve(sizeof(ArmDesc) * std::max<uint64_t>(n_arms, 1)));
     CUDA_TRY(g.packed.reserve(packed_bytes + 16));
-    CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
-    if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
-    if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
-
-    // per-window bounds -> scratch positions (exclusive scan on the device)
     CUDA_TRY(g.out_pos.reserve(sizeof(uint64_t) * (n_win + 1)));
     CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
     CUDA_TRY(g.out_len.reserve(sizeof(uint32_t) * n_win));
+    CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
+    const WinDesc* d_win = (const WinDesc*)g.win.p;
+    const ArmDesc* d_arms = (const ArmDesc*)g.arms.p;
+    const uint8_t* d_packed = (const uint8_t*)g.packed.p;
     uint64_t* d_bound = (uint64_t*)g.out_off.p;   // reused as the compact offsets later
-    CUDA_TRY(cudaMemsetAsync((char*)g.out_off.p + sizeof(uint64_t) * n_win, 0, sizeof(uint64_t), s));
-    if (int rc = prepare_stats((const WinDesc*)g.win.p, n_win, (const ArmDesc*)g.arms.p, n_arms, packed_bytes, d_bound, s))
-        return rc;
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_bound, (uint64_t*)g.out_pos.p, n_win + 1, s));
-    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes));
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, (uint64_t*)g.out_pos.p, n_win + 1, s));
-    ++g.launches;
+    uint64_t* d_pos = (uint64_t*)g.out_pos.p;
+    WinStat* d_stats = (WinStat*)g.stats.p;
     uint64_t* h64 = (uint64_t*)((char*)g.pinned_ctrl + 3072);
-    CUDA_TRY(cudaMemcpyAsync(h64, (uint64_t*)g.out_pos.p + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    const uint64_t scratch_bytes = *h64;
-    CUDA_TRY(g.out_scratch.reserve(scratch_bytes + 16));
-    CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = g.cub_tmp.cap;
 
-    if (int rc = run_device((const WinDesc*)g.win.p, n_win, (const ArmDesc*)g.arms.p, n_arms, (const uint8_t*)g.packed.p,
-                            packed_bytes, (char*)g.out_scratch.p, (const uint64_t*)g.out_pos.p, (uint32_t*)g.out_len.p,
-                            (const WinStat*)g.stats.p, s))
-        return rc;
+    // ---- split: head = first ~1/8 of the windows -------------------------------------------------
+    uint64_t w_s = 0, a_s = 0, b_s = 0;
+    bool piped = n_win >= 65536 && n_arms > 0 && packed_bytes > 0;
+    if (piped) {
+        w_s = std::max<uint64_t>(32768, n_win / 8);
+        a_s = win[w_s].first_arm;
+        piped = a_s <= n_arms;
+        if (piped) {
+            b_s = std::min<uint64_t>(win[w_s].draft_off, a_s < n_arms ? arms[a_s].off : packed_bytes);
+            piped = b_s <= packed_bytes;
+        }
+    }
+    // an upper bound of the windows' scratch need that does not require looking at the arms: a window
+    // may write up to 2 * sum(len + 2) + 2 * draft_len + 4 bytes (classify_kernel; the factor 2 is the
+    // LONG round-2 backbone), and every base occupies at least 2 bits of the slab
+    const uint64_t scratch_cap = 8 * packed_bytes + 4 * n_arms + 8 * n_win + 64;
+
+    if (piped) {
+        CUDA_TRY(g.out_scratch.reserve(scratch_cap + 16));
+        cudaStream_t c = g.copy_stream;
+        CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * w_s, cudaMemcpyHostToDevice, c));
+        if (a_s) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * a_s, cudaMemcpyHostToDevice, c));
+        if (b_s) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, b_s, cudaMemcpyHostToDevice, c));
+        CUDA_TRY(cudaEventRecord(g.ev_head, c));
+        CUDA_TRY(cudaMemcpyAsync((WinDesc*)g.win.p + w_s, win + w_s, sizeof(WinDesc) * (n_win - w_s), cudaMemcpyHostToDevice, c));
+        if (n_arms > a_s)
+            CUDA_TRY(cudaMemcpyAsync((ArmDesc*)g.arms.p + a_s, arms + a_s, sizeof(ArmDesc) * (n_arms - a_s), cudaMemcpyHostToDevice, c));
+        if (packed_bytes > b_s)
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)g.packed.p + b_s, packed + b_s, packed_bytes - b_s, cudaMemcpyHostToDevice, c));
+        CUDA_TRY(cudaEventRecord(g.ev_tail, c));
+
+        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_head, 0));
+        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+        // head descriptors must only reference what has arrived: limits a_s / b_s
+        const int rc_head = prepare_stats(d_win, w_s, d_arms, a_s, b_s, d_stats, d_bound, s, /*quiet=*/true);
+        if (rc_head == HYPO_E_ARG) {
+            piped = false;   // not laid out in window order (or really invalid): single-copy path decides
+            CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
+        } else if (rc_head != HYPO_OK) {
+            return rc_head;
+        }
+    }
+
+    if (piped) {
+        // ---- head: positions, kernels (the tail is still being copied) ----------------------------
+        CUDA_TRY(cudaMemsetAsync(d_bound + w_s, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, w_s + 1, s));
+        ++g.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + w_s, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const uint64_t head_bytes = *h64;
+        if (head_bytes > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
+        if (int rc = run_device(d_win, w_s, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p, d_pos,
+                                (uint32_t*)g.out_len.p, d_stats, s))
+            return rc;
+        // ---- tail -----------------------------------------------------------------------------------
+        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
+        const uint64_t n_tail = n_win - w_s;
+        if (int rc = prepare_stats(d_win + w_s, n_tail, d_arms, n_arms, packed_bytes, d_stats + w_s, d_bound + w_s, s))
+            return rc;
+        CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveScan(g.cub_tmp.p, tmp_bytes, d_bound + w_s, d_pos + w_s, cuda::std::plus<>{},
+                                                (uint64_t)head_bytes, n_tail + 1, s));
+        ++g.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (*h64 > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
+        if (int rc = run_device(d_win + w_s, n_tail, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p,
+                                d_pos + w_s, (uint32_t*)g.out_len.p + w_s, d_stats + w_s, s, /*accumulate=*/true))
+            return rc;
+    } else {
+        // ---- single copy --------------------------------------------------------------------------
+        if (n_win < 65536 || !(n_arms > 0 && packed_bytes > 0) || w_s == 0) {
+            CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
+            if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
+            if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
+        } else {
+            // the split was attempted and abandoned: make sure everything has arrived
+            CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+            if (a_s > n_arms || b_s > packed_bytes) {   // nothing was copied yet (bad split point)
+                CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
+                if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
+                if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
+            }
+        }
+        CUDA_TRY(cudaMemsetAsync((char*)g.out_off.p + sizeof(uint64_t) * n_win, 0, sizeof(uint64_t), s));
+        if (int rc = prepare_stats(d_win, n_win, d_arms, n_arms, packed_bytes, d_stats, d_bound, s)) return rc;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+        ++g.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(g.out_scratch.reserve(*h64 + 16));
+        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+        if (int rc = run_device(d_win, n_win, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p, d_pos,
+                                (uint32_t*)g.out_len.p, d_stats, s))
+            return rc;
+    }
 
     // compact on the device: lengths -> offsets -> gather; then one D2H of the exact bytes
     uint64_t* d_len64 = d_bound;
     const int tb = 256;
     widen_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, s>>>((const uint32_t*)g.out_len.p, d_len64, n_win);
     CUDA_TRY(cudaMemsetAsync(d_len64 + n_win, 0, sizeof(uint64_t), s));
-    uint64_t* d_off = (uint64_t*)g.out_pos.p;   // scratch positions are dead after the gather... keep separate
     CUDA_TRY(g.lists.reserve(sizeof(uint64_t) * (n_win + 1)));
-    d_off = (uint64_t*)g.lists.p;
+    uint64_t* d_off = (uint64_t*)g.lists.p;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
     CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -622,6 +730,11 @@ void hypo_gpu_shutdown(void) {
     g.pinned_ctrl = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
+    if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
+    g.copy_stream = nullptr;
+    if (g.ev_head) cudaEventDestroy(g.ev_head);
+    if (g.ev_tail) cudaEventDestroy(g.ev_tail);
+    g.ev_head = g.ev_tail = nullptr;
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
     g.ev0 = g.ev1 = nullptr;

@@ -69,3 +69,20 @@ def test_headline_shape_full_size_properties():
     raw = out.tobytes()
     got = [raw[int(off[i]):int(off[i + 1])].decode() for i in idx]
     assert got == want
+
+
+def test_pipelined_host_copy_and_its_fallback():
+    """>= 65536 windows: the host-buffer entry point copies a head of the batch first and runs it while
+    the tail is still being copied.  Same bytes as the oracle; a batch that is NOT laid out in window
+    order (permuted windows over a shared slab) silently takes the single-copy path - same result."""
+    import numpy as np
+    from hypo_b200 import native
+    from hypo_b200.hostlib import synth_batch
+    from tests.oracle_util import DEFAULT_SCORES, oracle_consensus
+    native.init(DEFAULT_SCORES, 0)
+    b = synth_batch(77, 70000, 14, 9, "mixed", 0.03)
+    want, _ = oracle_consensus(b)
+    assert native.consensus(b) == want
+    perm = np.random.default_rng(5).permutation(b.n_win)
+    got = native.consensus(b.select(perm))
+    assert got == [want[i] for i in perm]
