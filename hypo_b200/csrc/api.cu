@@ -571,9 +571,18 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     // LONG round-2 backbone), and every base occupies at least 2 bits of the slab
     const uint64_t scratch_cap = 8 * packed_bytes + 4 * n_arms + 8 * n_win + 64;
 
+    // the caller's host buffers must not be touched after this function returns, on any path
+    struct CopyGuard {
+        cudaStream_t c;
+        bool armed = false;
+        ~CopyGuard() { if (armed) cudaStreamSynchronize(c); }
+    } guard{g.copy_stream};
+    bool copies_issued = false;
     if (piped) {
+        guard.armed = true;
         CUDA_TRY(g.out_scratch.reserve(scratch_cap + 16));
         cudaStream_t c = g.copy_stream;
+        copies_issued = true;
         CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * w_s, cudaMemcpyHostToDevice, c));
         if (a_s) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * a_s, cudaMemcpyHostToDevice, c));
         if (b_s) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, b_s, cudaMemcpyHostToDevice, c));
@@ -626,18 +635,13 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
             return rc;
     } else {
         // ---- single copy --------------------------------------------------------------------------
-        if (n_win < 65536 || !(n_arms > 0 && packed_bytes > 0) || w_s == 0) {
+        if (copies_issued) {
+            // the split was attempted and abandoned: everything is on its way on the copy stream
+            CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+        } else {
             CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
             if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
             if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
-        } else {
-            // the split was attempted and abandoned: make sure everything has arrived
-            CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
-            if (a_s > n_arms || b_s > packed_bytes) {   // nothing was copied yet (bad split point)
-                CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
-                if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
-                if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
-            }
         }
         CUDA_TRY(cudaMemsetAsync((char*)g.out_off.p + sizeof(uint64_t) * n_win, 0, sizeof(uint64_t), s));
         if (int rc = prepare_stats(d_win, n_win, d_arms, n_arms, packed_bytes, d_stats, d_bound, s)) return rc;
