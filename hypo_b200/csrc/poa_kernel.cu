@@ -447,6 +447,23 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
 
         uint32_t info = M::ld32(ri);
         uint32_t seed = (kMulti && bnd_prev) ? bcast16(bnd_prev[1]) : c.neg2;
+#ifndef HYPO_DP_ROLLED
+        // two rows per trip (measured +0.8 % over the rolled loop; three per trip overflows the L0
+        // instruction cache) (a spare record / matrix row pads an odd row count): the register sets
+        // are rotated once per pair
+#pragma unroll 1
+        for (int rk = 0; rk < n; rk += 2) {
+            const uint32_t i0 = info, i1 = M::ld32(ri + 4), s0 = seed;
+            uint32_t s1 = c.neg2;
+            ri += 8;
+            info = M::ld32(ri);
+            if (kMulti && bnd_prev) { s1 = bcast16(bnd_prev[rk + 2]); seed = bcast16(bnd_prev[rk + 3]); }
+            dp_row<kSmem, kMulti>(i0, rk, A, B, C, c, prows, Hl, Hrow, s0, bnd_prev, bnd_next);       // new row -> C
+            dp_row<kSmem, kMulti>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow, s1, bnd_prev, bnd_next);   // new row -> B
+            const RowRegs r = A;
+            A = B; B = C; C = r;
+        }
+#else
 #pragma unroll 1
         for (int rk = 0; rk < n; ++rk) {
             const uint32_t i0 = info, s0 = seed;
@@ -457,6 +474,7 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
             const RowRegs r = C;
             C = B; B = A; A = r;
         }
+#endif
         __syncwarp();   // the boundary values of this tile are read by every lane in the next one
     }
     return end_cell(g, H, n, (int)c.stride, len, type);
