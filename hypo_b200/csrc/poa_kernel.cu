@@ -1303,15 +1303,20 @@ __device__ __forceinline__ int branch_completion(const Graph& g, int rank) {
     return max_id;
 }
 
+// With `exact_order` false the ranks are only SOME valid clique-contiguous topological order.  The
+// per-node part of the traversal (scores, chosen predecessor) only looks at in-edges in stored order
+// and at predecessor scores, so it is the same under every valid order; the rank order itself decides
+// (a) which node wins when several reach the maximal score and (b) everything branch_completion does.
+// In either case the function returns -1 and the caller re-derives spoa's exact order first.
 template <bool kSmem, int kTier>
-__device__ __noinline__ int heaviest_bundle(const GState& st) {
+__device__ __noinline__ int heaviest_bundle(const GState& st, bool exact_order) {
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
     int len = 0;
     __syncwarp();
     if (lane == 0) {
-        int best = 0;
+        int best = 0, ties = 0;
 #pragma unroll 1
         for (int i = 0; i < n; ++i) g.score[i] = -1;
 #pragma unroll 1
@@ -1327,19 +1332,25 @@ __device__ __noinline__ int heaviest_bundle(const GState& st) {
             if (pv != kNone) sv += g.score[pv];
             g.score[v] = sv;
             g.pred[v] = (uint16_t)pv;
-            if (g.score[best] < sv) best = v;
+            const int sb = g.score[best];
+            if (sb < sv) { best = v; ties = 1; }
+            else if (sb == sv) ++ties;
         }
+        if (!exact_order && (ties > 1 || (g.ninfo[best] & 8))) best = -1;
         int guard = 0;
 #pragma unroll 1
-        while ((g.ninfo[best] & 8) && guard++ <= n) best = branch_completion(g, g.n2r[best]);
+        while (best >= 0 && (g.ninfo[best] & 8) && guard++ <= n) best = branch_completion(g, g.n2r[best]);
         // backtrack (reversed in place afterwards)
-        int k = 0;
+        int k = -1;
+        if (best >= 0) {
+            k = 0;
 #pragma unroll 1
-        while (g.pred[best] != kNone && k < n) { g.cons[k++] = (uint16_t)best; best = g.pred[best]; }
-        g.cons[k++] = (uint16_t)best;
+            while (g.pred[best] != kNone && k < n) { g.cons[k++] = (uint16_t)best; best = g.pred[best]; }
+            g.cons[k++] = (uint16_t)best;
 #pragma unroll 1
-        for (int a = 0, b = k - 1; a < b; ++a, --b) {
-            uint16_t t = g.cons[a]; g.cons[a] = g.cons[b]; g.cons[b] = t;
+            for (int a = 0, b = k - 1; a < b; ++a, --b) {
+                uint16_t t = g.cons[a]; g.cons[a] = g.cons[b]; g.cons[b] = t;
+            }
         }
         len = k;
     }
@@ -1490,11 +1501,14 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
         if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
     }
-    if (!g.exact) {   // the consensus needs spoa's exact rank order
+    // The heaviest bundle rarely depends on WHICH valid order the ranks are in; only then is spoa's
+    // exact order derived first.
+    int nc = heaviest_bundle<kSmem, kTier>(g, g.exact);
+    if (nc < 0) {
         if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
         g.exact = true;
+        nc = heaviest_bundle<kSmem, kTier>(g, true);
     }
-    const int nc = heaviest_bundle<kSmem, kTier>(g);
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
     const int n = nc >= 2 ? nc - 2 : 0;
     const Graph v = make_graph<kSmem, kTier>(g);
@@ -1561,7 +1575,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
             if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
             g.exact = true;
         }
-        const int nc = heaviest_bundle<kSmem, kTier>(g);
+        const int nc = heaviest_bundle<kSmem, kTier>(g, true);
         const Graph gv = make_graph<kSmem, kTier>(g);
         // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
         uint16_t* msa = gv.n2r;
