@@ -1315,25 +1315,48 @@ __device__ __noinline__ int heaviest_bundle(const GState& st, bool exact_order) 
     const int n = g.n_nodes;
     int len = 0;
     __syncwarp();
-    if (lane == 0) {
-        int best = 0, ties = 0;
+    // Phase 1, one node per lane: the heaviest in-edge.  Which of several equally heavy in-edges wins
+    // depends on the predecessors' path scores, so such nodes are only marked (kTiePred) and resolved
+    // in the serial pass; g.cons temporarily holds the winning weight.
+    constexpr int kTiePred = 0xFFFE;
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) g.score[i] = -1;
+    for (int v = lane; v < n; v += 32) {
+        int wmax = -1, pv = kNone, cnt = 0;
+#pragma unroll 1
+        for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+            const int w = g.e_w[e];
+            if (w > wmax) { wmax = w; pv = g.e_src[e]; cnt = 1; }
+            else if (w == wmax) ++cnt;
+        }
+        g.score[v] = -1;
+        g.pred[v] = (uint16_t)(cnt > 1 ? kTiePred : pv);
+        g.cons[v] = (uint16_t)wmax;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // Phase 2, serial in rank order: path scores (reference graph.cpp:616-634)
+        int best = 0, ties = 0, sb = -1;   // sb == g.score[best]
 #pragma unroll 1
         for (int r = 0; r < n; ++r) {
             const int v = g.r2n[r];
-            int sv = -1, pv = kNone;
+            int pv = g.pred[v];
+            int sv = -1;
+            if (pv == kTiePred) {
+                pv = kNone;
 #pragma unroll 1
-            for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
-                const int s = g.e_src[e];
-                const int w = g.e_w[e];
-                if (sv < w || (sv == w && g.score[pv] <= g.score[s])) { sv = w; pv = s; }
+                for (int e = g.in_head[v]; e != kNone; e = g.e_next[e]) {
+                    const int s = g.e_src[e];
+                    const int w = g.e_w[e];
+                    if (sv < w || (sv == w && g.score[pv] <= g.score[s])) { sv = w; pv = s; }
+                }
+                g.pred[v] = (uint16_t)pv;
+                sv += g.score[pv];
+            } else if (pv != kNone) {
+                sv = (int)g.cons[v] + g.score[pv];
             }
-            if (pv != kNone) sv += g.score[pv];
             g.score[v] = sv;
-            g.pred[v] = (uint16_t)pv;
-            const int sb = g.score[best];
-            if (sb < sv) { best = v; ties = 1; }
+            if (v == best) sb = sv;   // node 0 competes with its real score once it has been visited
+            if (sb < sv) { best = v; sb = sv; ties = 1; }
             else if (sb == sv) ++ties;
         }
         if (!exact_order && (ties > 1 || (g.ninfo[best] & 8))) best = -1;
