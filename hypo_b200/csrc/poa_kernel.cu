@@ -38,8 +38,9 @@ struct Graph {
     int32_t* score;       // epilogue
     uint16_t* pred;
     uint16_t* cons;
-    int n_nodes, n_edges, n_al, n_seq;
+    int n_nodes, n_edges, n_al, n_seq;   // snapshot of *ws taken by make_graph
     int als;              // slots per aligned-list block
+    struct WarpState* ws; // the live counts (in the arena)
 };
 
 // What persists per warp between the phases (kept in local memory; the phases are separate
@@ -47,12 +48,18 @@ struct Graph {
 // arena is, its layout, and the element counts.  Every phase rebuilds its typed view with
 // make_graph<kSmem>, which lets the compiler see that shared-memory tiers address __shared__
 // (LDS/STS with 32-bit addresses) instead of falling back to generic loads.
+// Element counts of the window a warp is building.  They live in the arena (shared memory for the
+// shared-memory tiers) so that the phases - separate functions - exchange them without going through
+// per-thread local memory.
+struct WarpState {
+    int n_nodes, n_edges, n_al, n_seq;
+    int exact;           // r2n/n2r currently hold spoa's exact DFS order (not just a valid one)
+    int pad[3];
+};
+
 struct GState {
     uint8_t* gbase;      // tiers L: this warp's arena in global memory
-    uint32_t sbase;      // tiers S: byte offset of this warp's arena in dynamic shared memory
-    ArenaLayout L;
-    int n_nodes, n_edges, n_al, n_seq;
-    bool exact;          // r2n/n2r currently hold spoa's exact DFS order (not just a valid one)
+    ArenaLayout L;       // tiers with run-time capacities only
     uint32_t* fail_hist; // diagnostics: why windows were abandoned (may be null)
 };
 
@@ -67,8 +74,9 @@ __device__ __noinline__ bool give_up(const GState& st, int why) {
 template <bool kSmem>
 __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout& L) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* base = kSmem ? (smem + st.sbase) : st.gbase;
+    uint8_t* base = kSmem ? (smem + (threadIdx.x >> 5) * L.total) : st.gbase;
     Graph g;
+    g.ws = (WarpState*)(base + L.state);
     g.ninfo = base + L.ninfo;
     g.al_cnt = base + L.al_cnt;
     g.in_deg = base + L.in_deg;
@@ -95,7 +103,7 @@ __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout&
     g.score = (int32_t*)(base + L.score);
     g.pred = (uint16_t*)(base + L.pred);
     g.cons = (uint16_t*)(base + L.cons);
-    g.n_nodes = st.n_nodes; g.n_edges = st.n_edges; g.n_al = st.n_al; g.n_seq = st.n_seq;
+    g.n_nodes = g.ws->n_nodes; g.n_edges = g.ws->n_edges; g.n_al = g.ws->n_al; g.n_seq = g.ws->n_seq;
     g.als = L.alslots;
     return g;
 }
@@ -109,6 +117,17 @@ __device__ __forceinline__ Graph make_graph(const GState& st) {
         return bind_graph<kSmem>(st, L);
     } else {
         return bind_graph<kSmem>(st, st.L);
+    }
+}
+
+template <bool kSmem, int kTier>
+__device__ __forceinline__ WarpState* warp_state(const GState& st) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    if constexpr (kTier >= 0) {
+        constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
+        return (WarpState*)((kSmem ? (smem + (threadIdx.x >> 5) * L.total) : st.gbase) + L.state);
+    } else {
+        return (WarpState*)((kSmem ? (smem + (threadIdx.x >> 5) * st.L.total) : st.gbase) + st.L.state);
     }
 }
 
@@ -797,10 +816,12 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
         }
         n_edges += __popc(em);
     }
-    st.n_nodes = n_nodes;
-    st.n_al = n_al;
-    st.n_edges = n_edges;
-    st.n_seq = g.n_seq + 1;
+    if (lane == 0) {
+        g.ws->n_nodes = n_nodes;
+        g.ws->n_al = n_al;
+        g.ws->n_edges = n_edges;
+        g.ws->n_seq = g.n_seq + 1;
+    }
     __syncwarp();
     return true;
 }
@@ -1430,44 +1451,48 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
 
     AlnSpan span;
     span.first = -1; span.last = -1;
-    if (st.n_nodes > 0) {   // reference sisd_alignment_engine.cpp:249-251
+    WarpState* const ws = g.ws;
+    const int nodes_before = g.n_nodes, edges_before = g.n_edges;
+    if (nodes_before > 0) {   // reference sisd_alignment_engine.cpp:249-251
         const int tiles = kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols;
         const int cols = tiles * kTileCols;
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
-        if (S * (st.n_nodes + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return give_up(st, kFailRange);
+        if (S * (nodes_before + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return give_up(st, kFailRange);
         // boundary arrays of the multi-tile fill live behind the matrix slot
         const int bnd_len = caps.ncap + 4;
         int16_t* bnd = H + (size_t)(caps.ncap + 4) * (size_t)(caps.tiles * kTileCols);
         EndCell ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
-        if (ec.tie && !st.exact) {
+        if (ec.tie && !ws->exact) {
             // the reference breaks this tie by rank in ITS order: derive it and redo the fill
             if (!topo_sort<kSmem, kTier>(st, caps)) return false;
-            st.exact = true;
+            if (lane == 0) ws->exact = 1;
+            __syncwarp();
             build_rows<kSmem, kTier>(st);
             ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
         }
-        span = traceback_dp<kSmem, kTier>(st, H, cols, ec, s.type, sc, st.n_nodes + len + 4);
+        span = traceback_dp<kSmem, kTier>(st, H, cols, ec, s.type, sc, nodes_before + len + 4);
         // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
         // written back: without this every DP row ends up in HBM (1 TB per million windows) just
         // to be overwritten by the next read.
         {
-            const unsigned lines = (unsigned)(st.n_nodes + 1) * (unsigned)cols / 64u;   // 128-byte lines
+            const unsigned lines = (unsigned)(nodes_before + 1) * (unsigned)cols / 64u;   // 128-byte lines
             char* hb = reinterpret_cast<char*>(H);
 #pragma unroll 1
             for (unsigned l = lane; l < lines; l += 32)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(hb + (size_t)l * 128) : "memory");
         }
     }
-    const int nodes_before = st.n_nodes, edges_before = st.n_edges;
     if (!add_to_graph<kSmem, kTier>(st, caps, len, span, path)) return false;
     // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence every
     // order, unchanged
-    if (st.n_nodes == nodes_before && st.n_edges == edges_before) return true;
+    const int nodes_after = ws->n_nodes;
+    if (nodes_after == nodes_before && ws->n_edges == edges_before) return true;
     // new nodes must be ranked; new edges alone keep the current order valid (they follow it),
     // but either may change what spoa's DFS would produce
-    if (st.n_nodes != nodes_before) order_update<kSmem, kTier>(st, len, nodes_before);
-    st.exact = false;
+    if (nodes_after != nodes_before) order_update<kSmem, kTier>(st, len, nodes_before);
+    if (lane == 0) ws->exact = 0;
+    __syncwarp();
     build_rows<kSmem, kTier>(st);
     return true;
 }
@@ -1494,8 +1519,9 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     added = __any_sync(kFull, added);
     if (!added) return -1;   // caller copies the draft (:150-152)
 
-    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
-    g.exact = true;
+    WarpState* const ws = warp_state<kSmem, kTier>(g);
+    if (lane == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; }
+    __syncwarp();
     SeqSrc s;
     s.ascii = nullptr;
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
@@ -1526,10 +1552,11 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     }
     // The heaviest bundle rarely depends on WHICH valid order the ranks are in; only then is spoa's
     // exact order derived first.
-    int nc = heaviest_bundle<kSmem, kTier>(g, g.exact);
+    int nc = heaviest_bundle<kSmem, kTier>(g, ws->exact != 0);
     if (nc < 0) {
         if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
-        g.exact = true;
+        if (lane == 0) ws->exact = 1;
+        __syncwarp();
         nc = heaviest_bundle<kSmem, kTier>(g, true);
     }
     // set_marked_consensus: strip first and last character (reference include/Window.hpp:144)
@@ -1565,14 +1592,16 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     int n_cons = 0;
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-        g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
-        g.exact = true;
+        WarpState* const ws = warp_state<kSmem, kTier>(g);
+        __syncwarp();
+        if (lane == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; }
+        __syncwarp();
         uint32_t used = 0;
         SeqSrc s;
         s.head = false; s.tail = false; s.type = kNW;
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return give_up(g, kFailPaths);
-            if (lane == 0) pstart[g.n_seq] = used;
+            if (lane == 0) pstart[ws->n_seq] = used;
             const bool ok = add_sequence<kSmem, kOneTile, kTier>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
             return ok;
@@ -1591,12 +1620,13 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
             s.bytes = P.packed + a[k].off; s.len = a[k].len;
             if (!add(s)) return -2;
         }
-        if (lane == 0) pstart[g.n_seq] = used;
+        if (lane == 0) pstart[ws->n_seq] = used;
         __syncwarp();
 
-        if (!g.exact) {   // consensus and MSA columns need spoa's exact rank order
+        if (!ws->exact) {   // consensus and MSA columns need spoa's exact rank order
             if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
-            g.exact = true;
+            if (lane == 0) ws->exact = 1;
+            __syncwarp();
         }
         const int nc = heaviest_bundle<kSmem, kTier>(g, true);
         const Graph gv = make_graph<kSmem, kTier>(g);
@@ -1669,9 +1699,8 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         g.L = arena_layout(caps);
         arena_bytes = g.L.total;
     }
-    g.sbase = kSmem ? (uint32_t)warp_in_cta * arena_bytes : 0u;
+    (void)arena_bytes;
     g.gbase = kSmem ? nullptr : (P.gws + (size_t)gwarp * P.g_slot);
-    g.n_nodes = g.n_edges = g.n_al = g.n_seq = 0;
     g.fail_hist = P.fail_hist;
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;

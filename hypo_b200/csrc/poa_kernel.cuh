@@ -107,6 +107,7 @@ __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & 
 
 // Per-warp graph arena.  Node arrays are indexed by node id, row arrays by rank (+1 = DP row).
 struct ArenaLayout {
+    uint32_t state;     // WarpState: element counts of the window being built (32 bytes)
     // nodes
     uint32_t ninfo;     // u8  letter code (bits 0-2) | has-out-edge (bit 3)
     uint32_t al_cnt;    // u8  number of aligned nodes
@@ -152,6 +153,7 @@ struct LayoutCursor {
 __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     ArenaLayout L{};
     LayoutCursor k{0};
+    L.state = k.take(32);
     L.ninfo = k.take(c.ncap);
     L.al_cnt = k.take(c.ncap);
     L.in_deg = k.take(c.ncap);
