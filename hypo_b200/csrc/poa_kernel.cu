@@ -300,35 +300,31 @@ constexpr int kRowNearShift = 28;
 __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __restrict__ H, int n, int cols,
                                             int len, int type) {
     const int lane = lane_id();
-    int best = INT_MIN, brow = 0x7fffffff;
+    // per lane: best score, its lowest row, and how many candidate rows reach it
+    int best = INT_MIN, brow = 0x7fffffff, cnt = 0;
 #pragma unroll 1
     for (int r = lane; r < n; r += 32) {
         const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
         if (cand) {
             const int v = (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len];
-            if (v > best) { best = v; brow = r + 1; }
+            if (v > best) { best = v; brow = r + 1; cnt = 1; }
+            else if (v == best) ++cnt;
         }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         const int ob = __shfl_xor_sync(kFull, best, d);
         const int orow = __shfl_xor_sync(kFull, brow, d);
-        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+        const int ocnt = __shfl_xor_sync(kFull, cnt, d);
+        if (ob > best) { best = ob; brow = orow; cnt = ocnt; }
+        else if (ob == best) { brow = min(brow, orow); cnt += ocnt; }
     }
     EndCell ec;
     const bool any = brow != 0x7fffffff;
     ec.row = any ? brow : 0;
     ec.col = any ? len : 0;
-    // does a second candidate reach the same score?  (only then does the exact order matter)
-    int same = 0;
-    if (any) {
-#pragma unroll 1
-        for (int r = lane; r < n; r += 32) {
-            const bool cand = (type == kLOV) || ((g.rowinfo[r] >> 27) & 1);
-            if (cand && (int)H[(unsigned)(r + 1) * (unsigned)cols + (unsigned)len] == best) ++same;
-        }
-    }
-    same = __reduce_add_sync(kFull, same);
+    // a second candidate with the same score?  (only then does the exact order matter)
+    const int same = any ? cnt : 0;
     ec.tie = same > 1;
     return ec;
 }
