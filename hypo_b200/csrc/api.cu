@@ -341,11 +341,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         const ArenaLayout L = arena_layout(caps);
 
         int wpb = T.warps_per_block;
-        int bps = T.blocks_per_sm;
-        if (t == 0) {   // developer knobs for occupancy experiments (not part of the ABI)
-            if (const char* e = getenv("HYPO_B200_T0_WPB")) wpb = std::max(1, atoi(e));
-            if (const char* e = getenv("HYPO_B200_T0_BPS")) bps = std::max(1, atoi(e));
-        }
+        const int bps = T.blocks_per_sm;
         size_t smem = 0;
         if (T.smem_graph) {
             smem = (size_t)L.total * wpb;

@@ -25,3 +25,24 @@ def test_synth_shapes():
     # consensus of clean-ish arms recovers a ~120 bp sequence
     cons, _ = oracle_consensus(b.select(np.arange(4)))
     assert all(100 < len(c) < 140 for c in cons)
+
+
+def test_concat_batches_and_pipeline_mix():
+    """bench.py's pipeline shape mix is a concatenation of fixed-shape batches: descriptors must be
+    re-based onto one arm table and one slab without changing any window."""
+    import argparse
+    import numpy as np
+    import bench
+    from hypo_b200.batch import concat_batches
+    from hypo_b200.synth import random_batch
+    a, b = random_batch(1, 5, length=20, n_arms=4), random_batch(2, 7, length=9, n_arms=6, kind="mixed")
+    c = concat_batches([a, b])
+    assert c.n_win == 12 and c.n_arms == a.n_arms + b.n_arms
+    assert [c.spec(i) for i in range(5)] == [a.spec(i) for i in range(5)]
+    assert [c.spec(5 + i) for i in range(7)] == [b.spec(i) for i in range(7)]
+    args = argparse.Namespace(mix="pipeline", windows=3000, err=0.01, length=120, arms=30, kind="internal")
+    m = bench.make_batch(args, 11)
+    assert abs(m.n_win - 3000) <= 40
+    assert 8 <= np.median(m.win["draft_len"]) <= 16 and m.win["draft_len"].max() <= 130
+    m2 = bench.make_batch(args, 11)
+    assert (m.win == m2.win).all() and (m.packed == m2.packed).all()   # seeded
