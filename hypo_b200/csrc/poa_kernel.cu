@@ -288,6 +288,7 @@ __device__ __forceinline__ uint32_t warp_excl_max(uint32_t tot2, uint32_t lane0_
 struct EndCell {
     int row;   // 0 if no candidate (reference clamps max_i=-1 to 0)
     int col;
+    int score; // H^ of that cell (0 for the clamped cell (0, 0))
     bool tie;  // two or more candidate rows share the best score (the rank order decides)
 };
 
@@ -323,6 +324,7 @@ __device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __res
     const bool any = brow != 0x7fffffff;
     ec.row = any ? brow : 0;
     ec.col = any ? len : 0;
+    ec.score = any ? best : 0;
     // a second candidate with the same score?  (only then does the exact order matter)
     const int same = any ? cnt : 0;
     ec.tie = same > 1;
@@ -522,7 +524,7 @@ __device__ __noinline__ AlnSpan traceback_dp(const GState& st, const int16_t* __
     AlnSpan span;
     span.first = -1; span.last = -1;
     const unsigned ucols = (unsigned)cols;
-    int hij = (int)H[(unsigned)i * ucols + (unsigned)j];
+    int hij = ec.score;   // == H[i][j], already known from the end-cell search
     const int mm = sc.m - sc.g, nn = sc.n - sc.g;
     int steps = 0;
     int chunk = 32;   // lanes used by the next speculative run: 8, 16 or 32
