@@ -506,10 +506,12 @@ template __device__ EndCell dp_fill_row<true, 0, false>(const GState&, int16_t* 
 // Traceback (reference sisd_alignment_engine.cpp:344-437).
 // Preference at every cell: diagonal via in-edge 0,1,..; vertical via in-edge 0,1,..; horizontal.
 // Because "diagonal through the FIRST in-edge" is tested first, a run of such moves can be
-// verified by 32 lanes at once: the chain of first-predecessor rows is walked serially in shared
-// memory (fp[]), then lane k tests the equality for step k and the longest all-true prefix is
-// committed.  Every other move takes the serial path (uniform across lanes, broadcast loads).
-// Lane 0 / the owning lanes record cur[pos] = aligned node (kNone for a read-only column).
+// verified by up to 32 lanes at once: lane k reaches the row of step k through the jump pointers
+// (fp4, then fp), tests the equality for its step, and the longest all-true prefix is committed; the
+// number of lanes used adapts to how long the last run was.  Every other move is a general step:
+// all candidates of the reference's preference list are fetched at once, one per lane, and the
+// lowest matching lane wins.  The owning lanes record cur[pos] = aligned node (kNone for a read-only
+// column).
 // ------------------------------------------------------------------------------------------
 struct AlnSpan {
     int first, last;

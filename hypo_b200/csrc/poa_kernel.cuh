@@ -3,21 +3,24 @@
 // One warp owns one weak-region window at a time and runs the whole of
 // hypo::Window::generate_consensus for it (reference src/Window.cpp:44-254):
 // for every read segment ("arm") in the reference's order it
-//   1. decodes the 2-bit PackedSeq bytes and builds the query profile,
+//   1. decodes the 2-bit PackedSeq bytes (the query profile is computed in registers, per row),
 //   2. fills the sequence-to-graph DP (spoa SISD linear-gap semantics,
 //      reference external/spoa/src/sisd_alignment_engine.cpp:263-342),
 //   3. walks the equality-driven traceback (:344-437),
 //   4. fuses the alignment into the DAG (reference external/spoa/src/graph.cpp:154-271),
-//   5. re-derives spoa's exact DFS topological order (:293-353),
+//   5. keeps a valid clique-contiguous topological order up to date; spoa's exact DFS order
+//      (:293-353) is re-derived only where the rank order can change the result,
 // and finally extracts the heaviest-bundle consensus (:610-705), for LONG windows
 // with the per-column support counts + curation (:533-568, src/Window.cpp:239-254).
 //
 // Data placement:
-//   * the growing DAG (SoA, 16-bit indices) lives in shared memory (tiers S) or in a
-//     global workspace (tiers L, for windows that overflow the shared-memory capacities);
-//   * the DP matrix lives in global memory and is sized to stay L2-resident; every warp
-//     keeps the previous row in registers so the common pred == previous-rank case never
-//     touches memory; rows are written once, coalesced, 8 bytes per lane;
+//   * the growing DAG (SoA, 16-bit indices) and the element counts live in shared memory (tiers S,
+//     layouts are compile-time constants) or in a global workspace (tiers L, for windows that
+//     overflow the shared-memory capacities);
+//   * the DP matrix lives in global memory, filled one 128-column tile at a time; every warp keeps
+//     the last three rows of the tile in registers, so rows whose predecessors lie within three
+//     ranks never touch memory before their store; rows are written once, coalesced, 8 bytes per
+//     lane, and dropped from L2 (discard.global.L2) once the read's traceback is done;
 //   * cells are 16-bit, two per register, updated with the sm_100 DPX instructions
 //     (VIADDMNMX.S16x2 / VIMNMX3.S16x2); the horizontal gap pass is a warp-shuffle
 //     prefix-max (the matrix is stored g-normalised, H^[i][j] = H[i][j] - j*g, which
