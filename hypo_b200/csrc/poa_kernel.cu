@@ -1041,11 +1041,32 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps_dyn) {
     const int lane = lane_id();
     const int n = g.n_nodes;
     uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
+    __syncwarp();   // the sort's scratch aliases the row records other lanes may still be reading
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) { g.mark[i] = 0; claim[i] = 0; }
     __syncwarp();
     uint16_t* list = g.lists + lane * kBulkList;
     int nr = 0, i0 = 0, round = 0;
+#ifndef HYPO_BULK_SORT
+    // DEFAULT: the reference's DFS, verbatim, on one lane.  The warp-parallel replay below (32 roots
+    // per round, unsynchronised claim table) is several times faster, but a randomised parity run
+    // found it to produce a different (still valid) order for about one LONG window in 10^6 - the
+    // outcome depends on how the lanes interleave - so it stays disabled until the claim protocol
+    // is made race-free.  Since the exact order is only derived where it can matter (end-cell ties,
+    // LONG windows, tied bundles), the serial sort costs nothing on the headline shape.
+    {
+        int ok = 1;
+        if (lane == 0) {
+#pragma unroll 1
+            for (int id = 0; id < n && ok; ++id)
+                if ((g.mark[id] & 3) != 2) ok = dfs_from(g, caps, id, nr) ? 1 : 0;
+        }
+        ok = __shfl_sync(kFull, ok, 0);
+        if (!ok) return give_up(st, kFailStack);
+        i0 = n;
+        __syncwarp();
+    }
+#endif
 #pragma unroll 1
     while (i0 < n) {
         if (++round == 2047) {   // claim encoding would wrap: start over with clean claims

@@ -156,3 +156,14 @@ def test_clique_beyond_acgt_leaves_the_compact_tier():
     b = build_batch(specs)
     want, _ = oracle_consensus(b)
     _assert_same(native.consensus(b), want, b, "five-letter clique")
+
+
+def test_regression_long_window_with_borderline_support():
+    """Found by tools/fuzz_parity.py: a LONG window whose first consensus base sits exactly on the
+    curation threshold; any deviation from spoa's exact topological order (MSA column ids) drops it.
+    Many copies, so that every warp slot of a CTA sees it."""
+    from tests.regression_specs import LONG_BORDERLINE_SUPPORT
+    b = build_batch([LONG_BORDERLINE_SUPPORT] * 48)
+    want, _ = oracle_consensus(b)
+    assert want[0] == "AGGGGGAACGGTGTCTCACCCTTACGGGCCTTTAACTTTCGGAAAAAT"
+    _assert_same(native.consensus(b), want, b, "long/borderline-support")
