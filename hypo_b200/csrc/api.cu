@@ -230,18 +230,21 @@ struct Tier {
 // (every base of a ~1 %-error read opens a new node with about that probability); a wrong guess only
 // costs the run-time overflow path.
 // T0b: windows up to 255 columns (two tiles; SHORT and LONG), 12 warps/SM.
-// T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory.
+// T1m: windows up to 511 columns (four tiles: the 500-bp windows of CCS reads and LONG windows) with
+//      up to 640 nodes, 8 warps/SM.
+// T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory, 5 warps/SM.
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
 // The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
 // (poa_kernel.cuh: fixed_caps); they are repeated here as documentation and checked at start-up.
 const Tier kTiers[] = {
     {true, true, false, false, 212, 328, 212, 640, 127, 9, 3, 201, 1},
     {true, true, false, false, 320, 576, 304, 1024, 127, 8, 2, 300, 2},
-    {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 4},
+    {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 5},
     {true, false, true, false, 384, 768, 384, 1536, 255, 6, 2, 364, 4},
-    {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 5},
-    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 6},
-    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 7},
+    {true, false, true, false, 640, 1152, 512, 2048, 511, 4, 2, 608, 5},
+    {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 6},
+    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 7},
+    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 8},
 };
 const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 
@@ -272,7 +275,10 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
     TierMax* d_tmax = (TierMax*)g.ctrl.p;
     uint32_t* d_queue = (uint32_t*)((char*)g.ctrl.p + sizeof(TierMax) * (kNumTiers + 1));
     uint32_t* d_lists = (uint32_t*)g.lists.p;
-    uint32_t* d_ovf[2] = {d_lists + (uint64_t)kNumTiers * n_win, d_lists + (uint64_t)kNumTiers * n_win + (n_win + 1)};
+    // behind the tier lists: the overflow list of the running launch, then the per-window size projections
+    uint32_t* d_over = d_lists + (uint64_t)kNumTiers * n_win;
+    uint32_t* d_need = d_over + (n_win + 1);
+    CUDA_TRY(cudaMemsetAsync(d_need, 0, sizeof(uint32_t) * n_win, stream));
     uint32_t* d_tier_lcap = d_queue + 16;
     uint32_t* d_tier_long = d_queue + 32;
     uint32_t* d_tier_seq = d_queue + 48;
@@ -309,7 +315,6 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         uint32_t* d_work = d_lists + (uint64_t)t * n_win;
         const uint32_t n_work = routed[t] + pend[t];
         if (n_work == 0) continue;
-        uint32_t* d_over = d_ovf[0];
         CUDA_TRY(cudaMemsetAsync(d_over, 0, sizeof(uint32_t), stream));
 
         Caps caps;
@@ -373,6 +378,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         P.out = d_out; P.out_pos = d_out_pos; P.out_len = d_out_len;
         P.overflow = d_over;
         P.fail_hist = d_fail;
+        P.need = d_need;
         P.H = (int16_t*)g.H.p; P.h_slot = h_slot;
         P.gws = (uint8_t*)g.gws.p; P.g_slot = g_slot;
         P.paths = need_paths ? (uint16_t*)g.paths.p : nullptr; P.p_slot = p_slot;

@@ -54,8 +54,16 @@ struct Graph {
 struct WarpState {
     int n_nodes, n_edges, n_al, n_seq;
     int exact;           // r2n/n2r currently hold spoa's exact DFS order (not just a valid one)
-    int pad[3];
+    int n_total;         // sequences this window (round) will add in all
+    uint32_t base;       // nodes | edges << 16 after the second sequence (growth is measured from here)
+    uint32_t need;       // projected final nodes | edges << 16 when the window was abandoned on projection
 };
+
+// Tiers that extrapolate a window's growth and abandon it early (add_sequence): the multi-tile ones with
+// compile-time capacities.  There a late overflow throws away the most work; the one-tile tiers' windows
+// are so small that the bookkeeping alone costs more than it saves (measured on the pipeline shape mix).
+template <bool kOneTile, int kTier>
+constexpr bool kProjects = kTier >= 0 && !kOneTile;
 
 struct GState {
     uint8_t* gbase;      // tiers L: this warp's arena in global memory
@@ -1474,6 +1482,29 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
     span.first = -1; span.last = -1;
     WarpState* const ws = g.ws;
     const int nodes_before = g.n_nodes, edges_before = g.n_edges;
+    // A DAG on course to outgrow this tier is handed on now, not after most of its reads have been
+    // aligned: growth per read since the second sequence, extrapolated over the reads to come.  The
+    // projection travels with the window (Params::need) so that later tiers it would not fit either
+    // pass it on without work.  Only where the window runs is affected, never its result.
+    if constexpr (kProjects<kOneTile, kTier>) {
+        if (g.n_seq == 2) {
+            if (lane == 0) ws->base = (uint32_t)nodes_before | ((uint32_t)edges_before << 16);
+        } else if (g.n_seq >= kProjectFrom) {
+            const uint32_t b = ws->base;
+            const int left = ws->n_total - g.n_seq, seen = g.n_seq - 2;
+            const int dn = nodes_before - (int)(b & 0xffffu), de = edges_before - (int)(b >> 16);
+            const int capn = caps.ncap + caps.ncap / 8, cape = caps.ecap + caps.ecap / 8;
+            // (growth slows as the DAG fills - later reads' errors coincide with nodes that exist - so
+            // only 3/4 of the linear extrapolation is held against the capacity)
+            if (3 * dn * left > 4 * (capn - nodes_before) * seen || 3 * de * left > 4 * (cape - edges_before) * seen) {
+                const int pn = nodes_before + 3 * dn * left / (4 * seen);
+                const int pe = edges_before + 3 * de * left / (4 * seen);
+                if (lane == 0) ws->need = (uint32_t)min(pn, 0xffff) | ((uint32_t)min(pe, 0xffff) << 16);
+                __syncwarp();
+                return give_up(st, kFailProjected);
+            }
+        }
+    }
     if (nodes_before > 0) {   // reference sisd_alignment_engine.cpp:249-251
         const int tiles = kOneTile ? 1 : (len + 1 + kTileCols - 1) / kTileCols;
         const int cols = tiles * kTileCols;
@@ -1530,18 +1561,28 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     const int n_arms = w.n_internal + w.n_pre + w.n_suf;
     // arms_added (reference :90,106,117,128)
     bool added = false;
+    int n_added = 0;
 #pragma unroll 1
     for (int k = lane; k < n_arms; k += 32) {
         const ArmDesc d = a[k];
-        added |= d.len > 0;
+        if constexpr (kProjects<kOneTile, kTier>) n_added += d.len > 0;
+        else added |= d.len > 0;
         // the reads' packed bytes are needed one read at a time: pull them into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + d.off));
     }
-    added = __any_sync(kFull, added);
+    if constexpr (kProjects<kOneTile, kTier>) {
+        n_added = __reduce_add_sync(kFull, n_added);
+        added = n_added != 0;
+    } else {
+        added = __any_sync(kFull, added);
+    }
     if (!added) return -1;   // caller copies the draft (:150-152)
 
     WarpState* const ws = warp_state<kSmem, kTier>(g);
-    if (lane == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; }
+    if (lane == 0) {
+        ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1;
+        if constexpr (kProjects<kOneTile, kTier>) { ws->n_total = n_added + (w.n_internal == 0); ws->base = 0; ws->need = 0; }
+    }
     __syncwarp();
     SeqSrc s;
     s.ascii = nullptr;
@@ -1597,11 +1638,11 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     const ArmDesc* a = P.arms + w.first_arm;
     const Scores sc = {P.lr_m, P.lr_n, P.lr_g};
     const int n_arms = w.n_internal + w.n_pre + w.n_suf;
-    bool added = false;
+    int n_added = 0;
 #pragma unroll 1
-    for (int k = lane; k < n_arms; k += 32) added |= a[k].len > 0;
-    added = __any_sync(kFull, added);
-    if (!added) return -1;
+    for (int k = lane; k < n_arms; k += 32) n_added += a[k].len > 0;
+    n_added = __reduce_add_sync(kFull, n_added);
+    if (n_added == 0) return -1;
     // (UINT)std::floor(_num_internal * _cThresh), float _cThresh = 0.4 (reference :28,245)
     const uint32_t thres = (uint32_t)floorf(__fmul_rn((float)w.n_internal, 0.4f));
 
@@ -1615,7 +1656,10 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     for (int round = 0; round < 2; ++round) {
         WarpState* const ws = warp_state<kSmem, kTier>(g);
         __syncwarp();
-        if (lane == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; }
+        if (lane == 0) {
+            ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1;
+            ws->n_total = n_added + 1; ws->base = 0; ws->need = 0;
+        }
         __syncwarp();
         uint32_t used = 0;
         SeqSrc s;
@@ -1737,8 +1781,18 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         char* out = P.out + P.out_pos[widx];
         const uint32_t n = w.n_internal + w.n_pre + w.n_suf;
         int res;
+        // projected size from a tier that abandoned the window (0 = none)
+        uint32_t need = 0;
+        bool pass_on = false;
+        if constexpr (kProjects<kOneTile, kTier>) {
+            if (P.need) need = P.need[widx];
+            pass_on = (int)(need & 0xffffu) > caps.ncap + caps.ncap / 8 || (int)(need >> 16) > caps.ecap + caps.ecap / 8;
+        }
         if (w.n_empty > n) {
             res = 0;   // reference src/Window.cpp:47-49
+        } else if (kProjects<kOneTile, kTier> && pass_on) {
+            give_up(g, kFailForwarded);
+            res = -2;
         } else if (n >= 2) {
             if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier>(g, P, caps, H, w, out);
             else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier>(g, P, caps, H, w, out, paths, P.p_slot);
@@ -1759,6 +1813,12 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
             if (res == -2) {
                 const uint32_t k = atomicAdd(P.overflow, 1u);
                 P.overflow[1 + k] = widx;
+                if constexpr (kProjects<kOneTile, kTier>) {
+                    // (run_short / run_long zero it when they start a window; non-zero = abandoned on projection)
+                    const uint32_t proj = pass_on ? 0u : warp_state<kSmem, kTier>(g)->need;
+                    if (P.need && proj != 0)
+                        P.need[widx] = max(proj & 0xffffu, need & 0xffffu) | (max(proj >> 16, need >> 16) << 16);
+                }
             } else {
                 P.out_len[widx] = (uint32_t)res;
             }
@@ -1782,7 +1842,8 @@ cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile
         case 1: k = poa_kernel<true, true, false, 2, 1>; break;    // T0
         case 2: k = poa_kernel<true, true, false, 2, 2>; break;    // Tw
         case 3: k = poa_kernel<true, false, true, 2, 3>; break;    // T0b
-        case 4: k = poa_kernel<true, false, true, 2, 4>; break;    // T1
+        case 4: k = poa_kernel<true, false, true, 2, 4>; break;    // T1m
+        case 5: k = poa_kernel<true, false, true, 2, 5>; break;    // T1
         default:                                                   // bound-driven tiers, DAG in global memory
             if (smem_graph) return cudaErrorInvalidConfiguration;
             k = one_tile ? poa_kernel<false, true, false, 2, -1> : poa_kernel<false, false, true, 2, -1>;

@@ -68,6 +68,8 @@ enum FailReason {
     kFailStack = 7,      // DFS stack of the exact topological sort
     kFailPaths = 8,      // LONG: per-sequence node paths
     kFailNoLong = 9,     // LONG window in a tier compiled without the LONG driver
+    kFailProjected = 10, // node / edge growth per read extrapolates beyond the tier: handed on early
+    kFailForwarded = 11, // an earlier tier's projection exceeds this tier as well: passed on without work
     kNumFailReasons = 16
 };
 
@@ -96,6 +98,8 @@ struct Params {
     uint32_t* out_len;           // consensus length of window w
     uint32_t* overflow;          // [0] = count, [1..] = window ids that exceeded this tier
     uint32_t* fail_hist;         // [kNumFailReasons] why windows left a tier (diagnostics; may be null)
+    uint32_t* need;              // per window: projected nodes | edges << 16 left by a tier that abandoned it
+                                 // on projection (0 = none; may be null)
     int16_t* H;                  // DP workspace, one slot per warp
     uint64_t h_slot;             // elements per slot
     uint8_t* gws;                // tiers L: graph workspace, one slot per warp
@@ -201,7 +205,9 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
 
 // Capacities of the shared-memory tiers are compile-time constants (the kernels fold every arena
 // offset into an immediate); tiers >= kNumFixedTiers take theirs from Params at run time.
-constexpr int kNumFixedTiers = 5;
+// Growth projection (add_sequence): from this many sequences in the graph on.
+constexpr int kProjectFrom = 6;
+constexpr int kNumFixedTiers = 6;
 __host__ __device__ constexpr Caps fixed_caps(int tier) {
     // (scap, the DFS stack of the exact sort, aliases the row records and costs no extra memory)
     //                 ncap  ecap  acap  scap  lcap  tiles alslots
@@ -209,7 +215,8 @@ __host__ __device__ constexpr Caps fixed_caps(int tier) {
          : tier == 1 ? Caps{320, 576, 304, 1024, 127, 1, 4}     // T0 : one tile
          : tier == 2 ? Caps{512, 1024, 384, 2048, 127, 1, 6}    // Tw : one tile, many reads per window
          : tier == 3 ? Caps{384, 768, 384, 1536, 255, 2, 6}     // T0b: two tiles
-                     : Caps{1024, 1920, 1024, 4096, 1023, 8, 4}; // T1 : LONG windows, medium DAG
+         : tier == 4 ? Caps{640, 1152, 512, 2048, 511, 4, 4}    // T1m: four tiles (500-bp windows), 8 warps / SM
+                     : Caps{1024, 1920, 1024, 4096, 1023, 8, 4}; // T1 : eight tiles, medium DAG
 }
 
 }  // namespace hypo_b200

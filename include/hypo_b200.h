@@ -154,8 +154,10 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
  * Diagnostic hook: how many times windows were abandoned in a capacity tier during the most recent
  * batch call, by reason (index: 1 sequence longer than the tier's columns, 2 16-bit DP range,
  * 3 node capacity, 4 aligned-list blocks, 5 clique size, 6 edge capacity / in-degree, 7 DFS stack,
- * 8 LONG path slot, 9 LONG window in a SHORT-only tier).  Every abandoned window is re-run in a
- * larger tier; this only explains the tier histogram of hypo_gpu_last_timing.
+ * 8 LONG path slot, 9 LONG window in a SHORT-only tier, 10 growth per read extrapolates beyond the
+ * tier (abandoned early), 11 passed on without work because an earlier tier's projection exceeds this
+ * tier too).  Every abandoned window is re-run in a larger tier; this only explains the tier histogram
+ * of hypo_gpu_last_timing.
  */
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]);
 

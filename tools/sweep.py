@@ -72,7 +72,7 @@ def main():
             "mbp_per_s_e2e": batch.polished_bp / 1e6 / dt, "windows_per_s": n / (k_ms / 1e3),
             "gcups": cells * n / 1e9 / (k_ms / 1e3),
             "hbm_gbs_algorithmic": alg / 1e9 / (k_ms / 1e3), "hbm_frac_of_measured_peak": alg / 1e9 / (k_ms / 1e3) / peak,
-            "tier_windows": tiers[:7], "abandoned_by_reason": native.last_fail_hist()[1:10],
+            "tier_windows": tiers[:8], "abandoned_by_reason": native.last_fail_hist()[1:12],
             "bit_exact_checked": k, "bit_exact": got == want,
         }
         print(json.dumps(line), flush=True)
