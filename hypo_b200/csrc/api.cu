@@ -233,7 +233,10 @@ struct Tier {
 // T1m: windows up to 511 columns (four tiles: the 500-bp windows of CCS reads and LONG windows) with
 //      up to 640 nodes, 8 warps/SM.
 // T1 : anything up to 1023 columns (LONG windows included) with a medium DAG in shared memory, 5 warps/SM.
-// T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped).
+// T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped); 16 and 8
+//      warps/SM - nothing but occupancy hides the latency of the DAG accesses (16 warps/SM run the
+//      30 x 500 bp, 5 %-error windows 2.8x faster than 4), the DP workspace permitting (the grid
+//      shrinks when the slots would exceed 24 GB).
 // The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
 // (poa_kernel.cuh: fixed_caps); they are repeated here as documentation and checked at start-up.
 const Tier kTiers[] = {
@@ -243,8 +246,8 @@ const Tier kTiers[] = {
     {true, false, true, false, 384, 768, 384, 1536, 255, 6, 2, 364, 4},
     {true, false, true, false, 640, 1152, 512, 2048, 511, 4, 2, 608, 5},
     {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 6},
-    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 1, 0xffffffffu, 7},
-    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 1, 0xffffffffu, 8},
+    {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 4, 0xffffffffu, 7},
+    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 8},
 };
 const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 
