@@ -171,7 +171,8 @@ __global__ void route_kernel(const WinDesc* __restrict__ win, const WinStat* __r
     // (sum_len of a LONG window counts the round-2 backbone bound as well: about twice the bases)
     const uint32_t est = s.max_len + (uint32_t)(((uint64_t)s.sum_len * (is_long ? 8u : 15u)) / 1000u);
     while (t < n_tiers - 1 &&
-           (s.max_len > tier_lcap[t] || (is_long && !tier_long_ok[t]) || est > tier_est_cap[t]))
+           (s.max_len > tier_lcap[t] || (is_long ? !(tier_long_ok[t] & 1u) : (tier_long_ok[t] & 2u) != 0) ||
+            est > tier_est_cap[t]))
         ++t;
     const uint32_t k = atomicAdd(&tmax[t].count, 1u);
     lists[(uint64_t)t * n_win + k] = (uint32_t)w;
@@ -242,7 +243,7 @@ struct Tier {
 const Tier kTiers[] = {
     {true, true, false, false, 212, 328, 212, 640, 127, 9, 3, 201, 1},
     {true, true, false, false, 320, 576, 304, 1024, 127, 8, 2, 300, 2},
-    {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 5},
+    {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 6},
     {true, false, true, false, 384, 768, 384, 1536, 255, 6, 2, 364, 4},
     {true, false, true, false, 640, 1152, 512, 2048, 511, 4, 2, 608, 5},
     {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 6},
@@ -250,6 +251,11 @@ const Tier kTiers[] = {
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 8},
 };
 const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
+// Static routing sends only LONG windows to T1: at 5 warps/SM it is slower than T2 at 16 for SHORT windows
+// (30 x 500 bp: 19 vs 36 Mbp/s), while a LONG window's bound-driven capacities in T2 (the round-2 backbone
+// is bounded by the node count) blow up the DP workspace and with it shrink the grid (5.7 vs 2.0 Mbp/s).
+// SHORT windows still reach T1 as the overflow successor of T1m.
+const int kLongOnlyTier = 5;
 
 int check_scores(const int8_t s[6]) {
     if (s[2] > 0 || s[5] > 0)
@@ -290,7 +296,7 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
     uint32_t h_lcap[16] = {0}, h_long[16] = {0}, h_seq[16] = {0};
     for (int t = 0; t < kNumTiers; ++t) {
         h_lcap[t] = (uint32_t)kTiers[t].lcap;
-        h_long[t] = kTiers[t].long_ok;
+        h_long[t] = (kTiers[t].long_ok ? 1u : 0u) | (t == kLongOnlyTier ? 2u : 0u);   // bit 0: LONG allowed, bit 1: SHORT not routed here
         h_seq[t] = kTiers[t].est_cap;
     }
     CUDA_TRY(cudaMemcpyAsync(d_tier_lcap, h_lcap, sizeof(h_lcap), cudaMemcpyHostToDevice, stream));

@@ -132,6 +132,27 @@ def test_large_random_parity_stresses_concurrent_sort():
         _assert_same(native.consensus(b), want, b, f"large/{kw}")
 
 
+def test_mid_size_windows_and_growth_projection():
+    """250-500 bp windows (CCS-sized SHORT windows, LONG windows): the four-tile tier; at 5 % read error
+    the DAG outgrows it, which the growth projection notices after a few reads (reason 10) - the window
+    moves on with its projection (reason 11 where a later tier cannot hold it either) and the result
+    stays bit-exact."""
+    from hypo_b200.hostlib import synth_batch
+    projected = 0
+    for seed, kw in ((51, dict(n_win=96, length=250, n_arms=30, kind="internal", err=0.01)),
+                     (52, dict(n_win=64, length=250, n_arms=30, kind="internal", err=0.05)),
+                     (53, dict(n_win=48, length=500, n_arms=12, kind="mixed", err=0.03)),
+                     (54, dict(n_win=32, length=400, n_arms=20, kind="internal", err=0.04, wtype=WINDOW_LONG))):
+        b = synth_batch(seed, **kw)
+        want, _ = oracle_consensus(b)
+        _assert_same(native.consensus(b), want, b, f"mid/{kw}")
+        _, _, tiers = native.last_timing()
+        reasons = native.last_fail_hist()
+        assert sum(reasons) == sum(tiers) - b.n_win
+        projected += reasons[10]
+    assert projected > 0
+
+
 def test_many_read_windows_take_the_wide_tier():
     """100-200 reads per window: routed past the compact tiers by the node estimate (or abandoned
     there and re-run), bit-exact either way; the diagnostics explain every abandonment."""
