@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <omp.h>
+
 #include "WindowBatch.hpp"
 
 namespace hypo {
@@ -45,52 +47,84 @@ std::ostream& operator<<(std::ostream& os, const Window& wnd) {
 }
 
 void WindowBatch::clear() {
-    _windows.clear(); _win.clear(); _arms.clear(); _packed.clear(); _bp = 0;
+    _windows.clear(); _win.clear(); _arms.clear(); _packed.reset(); _packed_bytes = 0; _n_packed = 0; _bp = 0;
 }
 
-void WindowBatch::reserve(size_t n_windows, size_t n_arms, size_t bytes) {
-    _windows.reserve(n_windows); _win.reserve(n_windows); _arms.reserve(n_arms); _packed.reserve(bytes);
-}
-
-uint64_t WindowBatch::put(const uint8_t* p, size_t n) {
-    const uint64_t off = _packed.size();
-    _packed.insert(_packed.end(), p, p + n);
-    return off;
+void WindowBatch::reserve(size_t n_windows, size_t /*n_arms*/, size_t /*bytes*/) {
+    _windows.reserve(n_windows);
 }
 
 void WindowBatch::add(Window* w) {
-    HypoWindowDesc d;
-    memset(&d, 0, sizeof(d));
-    d.draft_off = put(w->_draft.data(), w->_draft.data_size());
-    d.draft_len = (uint32_t)w->_draft.get_seq_size();
-    d.first_arm = _arms.size();
-    d.n_internal = (uint32_t)w->_internal_arms.size();
-    d.n_pre = (uint32_t)w->_pre_arms.size();
-    d.n_suf = (uint32_t)w->_suf_arms.size();
-    d.n_empty = w->_num_empty;
-    d.wtype = w->_wtype == WindowType::LONG ? HYPO_WINDOW_LONG : HYPO_WINDOW_SHORT;
-    for (const auto* v : {&w->_internal_arms, &w->_pre_arms, &w->_suf_arms})
-        for (const auto& a : *v) {
-            HypoArmDesc ad;
-            ad.off = put(a.data(), a.data_size());
-            ad.len = (uint32_t)a.get_seq_size();
-            ad.reserved = 0;
-            _arms.push_back(ad);
-        }
-    _win.push_back(d);
     _windows.push_back(w);
-    _bp += d.draft_len;
+    _bp += w->_draft.get_seq_size();
+}
+
+void WindowBatch::pack(int threads) {
+    const size_t n = _windows.size();
+    if (_n_packed == n) return;
+    if (threads <= 0) threads = omp_get_max_threads();
+    // pass 1: arms and bytes per window
+    std::vector<uint64_t> arm0(n + 1), byte0(n + 1);
+    arm0[0] = 0; byte0[0] = 0;
+#pragma omp parallel for schedule(static, 512) num_threads(threads)
+    for (size_t i = 0; i < n; ++i) {
+        const Window* w = _windows[i];
+        uint64_t bytes = w->_draft.data_size();
+        for (const auto* v : {&w->_internal_arms, &w->_pre_arms, &w->_suf_arms})
+            for (const auto& a : *v) bytes += a.data_size();
+        arm0[i + 1] = w->_internal_arms.size() + w->_pre_arms.size() + w->_suf_arms.size();
+        byte0[i + 1] = bytes;
+    }
+    for (size_t i = 0; i < n; ++i) { arm0[i + 1] += arm0[i]; byte0[i + 1] += byte0[i]; }
+    _win.resize(n);
+    _arms.resize(arm0[n]);
+    _packed_bytes = byte0[n];
+    _packed.reset(new uint8_t[_packed_bytes + 16]);
+    uint8_t* const slab = _packed.get();
+    // pass 2: every window fills its own slice (arms in container order: internal, prefix, suffix)
+#pragma omp parallel for schedule(static, 512) num_threads(threads)
+    for (size_t i = 0; i < n; ++i) {
+        const Window* w = _windows[i];
+        uint64_t pos = byte0[i];
+        HypoWindowDesc d;
+        memset(&d, 0, sizeof(d));
+        d.draft_off = pos;
+        d.draft_len = (uint32_t)w->_draft.get_seq_size();
+        memcpy(slab + pos, w->_draft.data(), w->_draft.data_size());
+        pos += w->_draft.data_size();
+        d.first_arm = arm0[i];
+        d.n_internal = (uint32_t)w->_internal_arms.size();
+        d.n_pre = (uint32_t)w->_pre_arms.size();
+        d.n_suf = (uint32_t)w->_suf_arms.size();
+        d.n_empty = w->_num_empty;
+        d.wtype = w->_wtype == WindowType::LONG ? HYPO_WINDOW_LONG : HYPO_WINDOW_SHORT;
+        HypoArmDesc* ad = _arms.data() + arm0[i];
+        for (const auto* v : {&w->_internal_arms, &w->_pre_arms, &w->_suf_arms})
+            for (const auto& a : *v) {
+                ad->off = pos;
+                ad->len = (uint32_t)a.get_seq_size();
+                ad->reserved = 0;
+                memcpy(slab + pos, a.data(), a.data_size());
+                pos += a.data_size();
+                ++ad;
+            }
+        _win[i] = d;
+    }
+    _n_packed = n;
 }
 
 void WindowBatch::run() {
     if (_windows.empty()) return;
+    pack();
     const uint64_t cap = hypo_gpu_out_bound(_win.data(), _win.size(), _arms.data(), _arms.size());
     _out.resize(cap + 16);
     _off.resize(_win.size() + 1);
-    if (hypo_gpu_consensus_batch(_win.data(), _win.size(), _arms.data(), _arms.size(), _packed.data(), _packed.size(),
+    if (hypo_gpu_consensus_batch(_win.data(), _win.size(), _arms.data(), _arms.size(), _packed.get(), _packed_bytes,
                                  _out.data(), _out.size(), _off.data()) != HYPO_OK)
         die("POA of windows");
-    for (size_t i = 0; i < _windows.size(); ++i)
+    const size_t n = _windows.size();
+#pragma omp parallel for schedule(static, 512)
+    for (size_t i = 0; i < n; ++i)
         _windows[i]->set_consensus(std::string(_out.data() + _off[i], _out.data() + _off[i + 1]));
 }
 

@@ -8,6 +8,7 @@
 // FFI call for the whole batch.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -16,29 +17,40 @@
 
 namespace hypo {
 
+// Packing is two passes over the windows, both OpenMP-parallel: sizes (arms and bytes per window), a
+// serial prefix sum, then every window copies its own bytes and writes its own descriptors at the
+// offsets the prefix sum assigned - the layout is the one a serial walk would produce, whatever the
+// thread count (a million 30-arm windows are 31 M small copies: ~1 s on one thread, which would be
+// twice the GPU's time for them).  The scatter of the consensus strings is parallel as well.
 class WindowBatch {
 public:
     void clear();
-    void reserve(size_t n_windows, size_t n_arms, size_t bytes);
-    // Appends a window; the Window must outlive run().
+    void reserve(size_t n_windows, size_t n_arms = 0, size_t bytes = 0);
+    // Appends a window (O(1), nothing is copied yet); the Window must outlive run().
     void add(Window* w);
     size_t size() const { return _windows.size(); }
-    // Sum of Window::get_window_len() — the numerator of the Mbp-polished/s metric.
+    // Sum of Window::get_window_len() - the numerator of the Mbp-polished/s metric.
     uint64_t polished_bp() const { return _bp; }
-    // One hypo_gpu_consensus_batch call + scatter into Window::_consensus.
+    // Flattens the windows added so far (idempotent; run() and the accessors call it).
+    // threads <= 0: all OpenMP threads.
+    void pack(int threads = 0);
+    // pack() + one hypo_gpu_consensus_batch call + scatter into Window::_consensus.
     // On failure prints "[Hypo::GPU] Error: ..." and exits(1), the reference's convention.
     void run();
 
-    const std::vector<HypoWindowDesc>& win_desc() const { return _win; }
-    const std::vector<HypoArmDesc>& arm_desc() const { return _arms; }
-    const std::vector<uint8_t>& packed() const { return _packed; }
+    const HypoWindowDesc* win_desc() { pack(); return _win.data(); }
+    const HypoArmDesc* arm_desc() { pack(); return _arms.data(); }
+    const uint8_t* packed() { pack(); return _packed.get(); }
+    size_t n_arms() { pack(); return _arms.size(); }
+    size_t packed_bytes() { pack(); return _packed_bytes; }
 
 private:
-    uint64_t put(const uint8_t* p, size_t n);
     std::vector<Window*> _windows;
     std::vector<HypoWindowDesc> _win;
     std::vector<HypoArmDesc> _arms;
-    std::vector<uint8_t> _packed;
+    std::unique_ptr<uint8_t[]> _packed;   // (not a vector: no zero-fill of a slab that is overwritten anyway)
+    size_t _packed_bytes = 0;
+    size_t _n_packed = 0;                 // windows covered by the buffers above
     std::vector<char> _out;
     std::vector<uint64_t> _off;
     uint64_t _bp = 0;

@@ -157,13 +157,16 @@ int hypo_synth_generate(uint64_t seed, uint64_t n_win, uint32_t len, uint32_t n_
 }
 
 // Drives the Window mirror through its public API.  Mirrors hypo_ref_consensus_batch.
-int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win, uint64_t n_win,
-                  const HypoArmDesc* arms, const uint8_t* packed, char* out, uint64_t out_cap, uint64_t* out_off) {
+}  // extern "C"
+
+namespace {
+// A flat batch rebuilt as hypo::Window objects through the public API (what the reference's pipeline does
+// while it walks the alignments).
+std::vector<std::unique_ptr<hypo::Window>> build_windows(const HypoWindowDesc* win, uint64_t n_win,
+                                                         const HypoArmDesc* arms, const uint8_t* packed) {
     using namespace hypo;
-    ScoreParams sp{scores[0], scores[1], scores[2], scores[3], scores[4], scores[5]};
-    Window::prepare_for_poa(sp, 1, device);
     std::vector<std::unique_ptr<Window>> ws(n_win);
-    std::vector<Window*> ptrs(n_win);
+#pragma omp parallel for schedule(static, 64)
     for (uint64_t w = 0; w < n_win; ++w) {
         const HypoWindowDesc& d = win[w];
         PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
@@ -173,8 +176,43 @@ int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win,
         for (uint32_t i = 0; i < d.n_pre; ++i, ++a) ws[w]->add_prefix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
         for (uint32_t i = 0; i < d.n_suf; ++i, ++a) ws[w]->add_suffix(PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
         for (uint32_t i = 0; i < d.n_empty; ++i) ws[w]->add_empty();
-        ptrs[w] = ws[w].get();
     }
+    return ws;
+}
+}  // namespace
+
+extern "C" {
+
+// CPU-only check and timing of the batch packer: flat batch -> hypo::Window objects -> WindowBatch::pack
+// with `threads` threads -> flat buffers again (win/arms/packed must be as large as the inputs).  The
+// packer writes the slab in container order (draft, internal, prefix, suffix arms); for a batch that is
+// laid out that way already the outputs equal the inputs byte for byte.  *seconds = time of pack() alone.
+int hypo_host_pack(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
+                   const uint8_t* packed, uint64_t packed_bytes, int threads, HypoWindowDesc* out_win,
+                   HypoArmDesc* out_arms, uint8_t* out_packed, double* seconds) {
+    using namespace hypo;
+    auto ws = build_windows(win, n_win, arms, packed);
+    WindowBatch b;
+    b.reserve(n_win);
+    for (auto& w : ws) b.add(w.get());
+    const double t0 = omp_get_wtime();
+    b.pack(threads);
+    if (seconds) *seconds = omp_get_wtime() - t0;
+    if (b.n_arms() != n_arms || b.packed_bytes() != packed_bytes) return HYPO_E_ARG;
+    memcpy(out_win, b.win_desc(), n_win * sizeof(HypoWindowDesc));
+    memcpy(out_arms, b.arm_desc(), n_arms * sizeof(HypoArmDesc));
+    memcpy(out_packed, b.packed(), packed_bytes);
+    return HYPO_OK;
+}
+
+int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win, uint64_t n_win,
+                  const HypoArmDesc* arms, const uint8_t* packed, char* out, uint64_t out_cap, uint64_t* out_off) {
+    using namespace hypo;
+    ScoreParams sp{scores[0], scores[1], scores[2], scores[3], scores[4], scores[5]};
+    Window::prepare_for_poa(sp, 1, device);
+    auto ws = build_windows(win, n_win, arms, packed);
+    std::vector<Window*> ptrs(n_win);
+    for (uint64_t w = 0; w < n_win; ++w) ptrs[w] = ws[w].get();
     Window::generate_consensus_batch(ptrs);
     uint64_t pos = 0;
     for (uint64_t w = 0; w < n_win; ++w) {
@@ -244,8 +282,8 @@ void hypo_host_inspect_sizes(void* h, uint64_t counts[6]) {
     for (auto& w : ws.windows) b.add(w.get());
     uint64_t cb = 0;
     for (auto& c : ws.recorded) cb += c.size();
-    counts[0] = ws.regions.size(); counts[1] = ws.windows.size(); counts[2] = b.arm_desc().size();
-    counts[3] = b.packed().size(); counts[4] = cb; counts[5] = ws.polished_bp();
+    counts[0] = ws.regions.size(); counts[1] = ws.windows.size(); counts[2] = b.n_arms();
+    counts[3] = b.packed_bytes(); counts[4] = cb; counts[5] = ws.polished_bp();
 }
 
 // The stream's windows as the flat batch of the C ABI plus the recorded consensus strings.
@@ -255,9 +293,9 @@ void hypo_host_inspect_fill(void* h, HypoWindowDesc* win, HypoArmDesc* arms, uin
     WindowStream& ws = *static_cast<WindowStream*>(h);
     WindowBatch b;
     for (auto& w : ws.windows) b.add(w.get());
-    memcpy(win, b.win_desc().data(), b.win_desc().size() * sizeof(HypoWindowDesc));
-    memcpy(arms, b.arm_desc().data(), b.arm_desc().size() * sizeof(HypoArmDesc));
-    memcpy(packed, b.packed().data(), b.packed().size());
+    memcpy(win, b.win_desc(), b.size() * sizeof(HypoWindowDesc));
+    memcpy(arms, b.arm_desc(), b.n_arms() * sizeof(HypoArmDesc));
+    memcpy(packed, b.packed(), b.packed_bytes());
     uint64_t pos = 0;
     for (size_t i = 0; i < ws.recorded.size(); ++i) {
         cons_off[i] = pos;

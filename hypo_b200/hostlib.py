@@ -30,6 +30,9 @@ def lib():
         L.hypo_synth_generate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_double,
                                           C.c_double, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.POINTER(C.c_uint64), C.c_int]
+        L.hypo_host_pack.restype = C.c_int
+        L.hypo_host_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.hypo_host_run.restype = C.c_int
         L.hypo_host_run.argtypes = [C.POINTER(C.c_int8), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_void_p]
@@ -84,6 +87,27 @@ def host_run(batch: WindowBatch, scores: Sequence[int] = (5, -4, -8, 3, -5, -4),
     if rc != 0:
         raise HypoGpuError(rc, "hypo_host_run failed")
     return split_consensus(out, off)
+
+
+def host_pack(batch: WindowBatch, threads: int = 0):
+    """CPU only: batch -> hypo::Window objects (public add_* API) -> the C++ batch packer with `threads`
+    OpenMP threads -> (win, arms, packed, seconds spent packing).  The packer lays the slab out in
+    container order (draft, internal, prefix, suffix arms, window after window); for a batch that already
+    is, the three arrays equal the batch's own byte for byte."""
+    L = lib()
+    # bytes in use (batches may carry slack behind the last sequence)
+    n_bytes = int(max((batch.arms["off"] + (batch.arms["len"] + 3) // 4).max(initial=0),
+                      (batch.win["draft_off"] + (batch.win["draft_len"] + 1) // 2).max(initial=0)))
+    win = np.zeros(batch.n_win, WIN_DTYPE)
+    arms = np.zeros(batch.n_arms, ARM_DTYPE)
+    packed = np.zeros(n_bytes, np.uint8)
+    sec = C.c_double(0.0)
+    rc = L.hypo_host_pack(batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data, batch.n_arms,
+                          batch.packed.ctypes.data, n_bytes, threads, win.ctypes.data, arms.ctypes.data,
+                          packed.ctypes.data, C.byref(sec))
+    if rc != 0:
+        raise HypoGpuError(rc, "hypo_host_pack: the packer's arm / byte counts differ from the batch's")
+    return win, arms, packed, float(sec.value)
 
 
 # ---- window streams in the reference's inspect-file format (host/WindowStream.hpp) -------------------

@@ -46,3 +46,41 @@ def test_concat_batches_and_pipeline_mix():
     assert 8 <= np.median(m.win["draft_len"]) <= 16 and m.win["draft_len"].max() <= 130
     m2 = bench.make_batch(args, 11)
     assert (m.win == m2.win).all() and (m.packed == m2.packed).all()   # seeded
+
+
+def test_batch_packer_round_trip_is_thread_independent():
+    """hypo::WindowBatch (the packer behind Window::generate_consensus_batch): windows built through the
+    public add_* API flatten to the batch they came from - same descriptors, same bytes per sequence, the
+    slab in container order - whatever the number of packing threads."""
+    from hypo_b200.hostlib import host_pack
+
+    def seqs(win, arms, packed):
+        out = [packed[int(w["draft_off"]): int(w["draft_off"]) + (int(w["draft_len"]) + 1) // 2].tobytes() for w in win]
+        out += [packed[int(a["off"]): int(a["off"]) + (int(a["len"]) + 3) // 4].tobytes() for a in arms]
+        return out
+
+    for b in (synth_batch(9, 700, 60, 14, "mixed"), synth_batch(10, 64, 300, 25, "internal", wtype=1)):
+        ref = None
+        for threads in (1, 3, 8):
+            win, arms, packed, _ = host_pack(b, threads)
+            for f in ("wtype", "n_internal", "n_pre", "n_suf", "n_empty", "draft_len", "first_arm"):
+                assert (win[f] == b.win[f]).all(), f
+            assert (arms["len"] == b.arms["len"]).all()
+            assert seqs(win, arms, packed) == seqs(b.win, b.arms, b.packed)
+            # container order, no gaps: draft, then the arms as listed
+            pos = 0
+            for w in win:
+                assert int(w["draft_off"]) == pos
+                pos += (int(w["draft_len"]) + 1) // 2
+                for a in arms[int(w["first_arm"]): int(w["first_arm"]) + int(w["n_internal"]) + int(w["n_pre"]) + int(w["n_suf"])]:
+                    assert int(a["off"]) == pos
+                    pos += (int(a["len"]) + 3) // 4
+            assert pos == packed.size
+            blob = win.tobytes() + arms.tobytes() + packed.tobytes()
+            assert ref is None or blob == ref
+            ref = blob
+    # a batch already in container order comes back byte for byte
+    b = synth_batch(11, 300, 120, 30, "internal")
+    win, arms, packed, _ = host_pack(b, 4)
+    assert win.tobytes() == b.win.tobytes() and arms.tobytes() == b.arms.tobytes()
+    assert packed.tobytes() == b.packed[:packed.size].tobytes()
