@@ -12,9 +12,11 @@
 #pragma once
 #include <functional>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
+#include "MinimizerFilter.hpp"
 #include "PackedSeq.hpp"
 
 namespace hypo {
@@ -61,9 +63,21 @@ public:
 
     // LONG windows run every arm through hypo::Filter::is_good at insert time in the
     // reference (include/Window.hpp:66-101).  The minimiser filter is upstream of the hot
-    // path and stays the maintainers' code; plug it in here (default: accept every arm).
+    // path; by default this mirror accepts every arm.  use_reference_long_filter(true) makes
+    // add_* behave like the reference's (MinimizerFilter.hpp, pinned against the compiled
+    // reference); set_long_arm_filter plugs in any other predicate.
     using ArmFilter = std::function<bool(const Window&, const PackedSeq<2>&)>;
     static void set_long_arm_filter(ArmFilter f) { _long_filter = std::move(f); }
+    static void use_reference_long_filter(bool on) {
+        if (!on) { _long_filter = nullptr; return; }
+        _long_filter = [](const Window& w, const PackedSeq<2>& ps) {
+            if (!w._ref_filter) {   // (the reference builds it in the constructor of a LONG window, :51)
+                w._ref_filter.reset(new MinimizerFilter());
+                w._ref_filter->init(w._draft.unpack());
+            }
+            return w._ref_filter->accepts(ps.unpack());
+        };
+    }
 
     void add_prefix(const PackedSeq<2>& ps) {
         if (!accept(ps)) return;
@@ -121,6 +135,7 @@ private:
     std::vector<PackedSeq<2>> _pre_arms;
     std::vector<PackedSeq<2>> _suf_arms;
     std::string _consensus;
+    mutable std::unique_ptr<MinimizerFilter> _ref_filter;   // LONG windows, use_reference_long_filter only
     static ArmFilter _long_filter;
 };
 

@@ -205,6 +205,36 @@ int hypo_host_pack(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc*
     return HYPO_OK;
 }
 
+// CPU only: which arms the Window mirror keeps when it filters the arms of LONG windows like the
+// reference's Window does (Window::use_reference_long_filter; reference include/Window.hpp:66-101,
+// include/Filter.hpp).  accepted[a] = 1/0 per arm descriptor; SHORT windows keep every arm.  Returns
+// HYPO_E_ARG if the windows built through add_* disagree with the filter applied arm by arm.
+int hypo_host_long_filter(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, const uint8_t* packed,
+                          uint8_t* accepted) {
+    using namespace hypo;
+    Window::use_reference_long_filter(true);
+    auto ws = build_windows(win, n_win, arms, packed);
+    Window::use_reference_long_filter(false);
+    int bad = 0;
+#pragma omp parallel for schedule(static, 64) reduction(+ : bad)
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        const uint64_t n = (uint64_t)d.n_internal + d.n_pre + d.n_suf;
+        MinimizerFilter f;
+        if (d.wtype == HYPO_WINDOW_LONG) f.init(unpack4(packed + d.draft_off, d.draft_len));
+        uint32_t kept[3] = {0, 0, 0};
+        for (uint64_t i = 0; i < n; ++i) {
+            const HypoArmDesc& a = arms[d.first_arm + i];
+            const bool ok = d.wtype != HYPO_WINDOW_LONG || f.accepts(unpack2(packed + a.off, a.len));
+            accepted[d.first_arm + i] = ok;
+            kept[i < d.n_internal ? 0 : i < (uint64_t)d.n_internal + d.n_pre ? 1 : 2] += ok;
+        }
+        bad += ws[w]->get_num_internal() != kept[0] + d.n_empty || ws[w]->get_num_pre() != kept[1] ||
+               ws[w]->get_num_suf() != kept[2];
+    }
+    return bad ? HYPO_E_ARG : HYPO_OK;
+}
+
 int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win, uint64_t n_win,
                   const HypoArmDesc* arms, const uint8_t* packed, char* out, uint64_t out_cap, uint64_t* out_off) {
     using namespace hypo;

@@ -33,6 +33,8 @@ def lib():
         L.hypo_host_pack.restype = C.c_int
         L.hypo_host_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.hypo_host_long_filter.restype = C.c_int
+        L.hypo_host_long_filter.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hypo_host_run.restype = C.c_int
         L.hypo_host_run.argtypes = [C.POINTER(C.c_int8), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_void_p]
@@ -87,6 +89,17 @@ def host_run(batch: WindowBatch, scores: Sequence[int] = (5, -4, -8, 3, -5, -4),
     if rc != 0:
         raise HypoGpuError(rc, "hypo_host_run failed")
     return split_consensus(out, off)
+
+
+def long_arm_filter(batch: WindowBatch) -> np.ndarray:
+    """CPU only: per arm, whether the Window mirror keeps it when it filters the arms of LONG windows like
+    the reference's Window (Window::use_reference_long_filter)."""
+    acc = np.zeros(max(batch.n_arms, 1), np.uint8)
+    rc = lib().hypo_host_long_filter(batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data,
+                                     batch.packed.ctypes.data, acc.ctypes.data)
+    if rc != 0:
+        raise HypoGpuError(rc, "hypo_host_long_filter: Window::add_* and the filter disagree")
+    return acc[: batch.n_arms].astype(bool)
 
 
 def host_pack(batch: WindowBatch, threads: int = 0):

@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-from hypo_b200.batch import WINDOW_LONG, build_batch  # noqa: E402
+from hypo_b200.batch import WINDOW_LONG, WindowSpec, build_batch  # noqa: E402
 from hypo_b200.synth import edge_case_windows, random_window  # noqa: E402
 from tests.oracle_util import DEFAULT_SCORES, drop_rejected_arms, ref_consensus, ref_spoa  # noqa: E402
 
@@ -122,12 +122,47 @@ def inspect_fixture():
     return batch.n_win, len(text)
 
 
+def long_filter_fixture():
+    """Which arms of LONG windows the reference's Window keeps (hypo::Filter::is_good, reference
+    include/Filter.hpp, applied by Window::add_* at include/Window.hpp:66-101): seeded LONG windows at
+    several error rates, the arms as strings, and the compiled reference's accept flag per arm."""
+    from tests.oracle_util import ref_consensus
+    rng = np.random.default_rng(20261019)
+    specs = []
+    for err in (0.02, 0.04, 0.06, 0.1):
+        for kind in ("internal", "mixed"):
+            specs += [random_window(rng, length=int(rng.integers(40, 320)), n_arms=int(rng.integers(4, 14)), kind=kind,
+                                    err=err, wtype=WINDOW_LONG) for _ in range(8)]
+    # a draft with N runs: a non-ACGT character restarts the k-mer but not the filter's minimizer window
+    tail = random_window(rng, length=150, n_arms=6, kind="internal", err=0.02, wtype=WINDOW_LONG)
+    d = list(tail.draft)
+    for p in (17, 18, 60, 95, 96, 97):
+        d[p] = "N"
+    specs.append(WindowSpec("".join(d), tail.internal, tail.pre, tail.suf, tail.n_empty, tail.wtype))
+    batch = build_batch(specs)
+    _, acc, _ = ref_consensus(batch)
+    wins = []
+    for w in range(batch.n_win):
+        s = batch.spec(w)
+        a0 = int(batch.win[w]["first_arm"])
+        n = len(s.internal) + len(s.pre) + len(s.suf)
+        wins.append({"draft": s.draft, "internal": s.internal, "pre": s.pre, "suf": s.suf,
+                     "accepted": [int(x) for x in acc[a0:a0 + n]]})
+    return {"generator_version": GENERATOR_VERSION, "oracle": "oracle/_ref/libhypo_ref.so", "windows": wins}
+
+
 def dump(name, obj):
     with gzip.GzipFile(os.path.join(HERE, name), "wb", mtime=0) as f:
         f.write(json.dumps(obj, separators=(",", ":")).encode())
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "filter":
+        lf = long_filter_fixture()
+        dump("long_filter.json.gz", lf)
+        flags = [x for w in lf["windows"] for x in w["accepted"]]
+        print("long filter: %d windows, %d arms, %d rejected" % (len(lf["windows"]), len(flags), flags.count(0)))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "inspect":
         print("inspect stream: %d windows, %d bytes" % inspect_fixture())
         sys.exit(0)
@@ -136,3 +171,4 @@ if __name__ == "__main__":
     dump("windows.json.gz", wf)
     print("windows:", sum(len(g["windows"]) for g in wf["groups"]))
     print("inspect stream: %d windows, %d bytes" % inspect_fixture())
+    dump("long_filter.json.gz", long_filter_fixture())

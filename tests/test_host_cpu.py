@@ -84,3 +84,35 @@ def test_batch_packer_round_trip_is_thread_independent():
     win, arms, packed, _ = host_pack(b, 4)
     assert win.tobytes() == b.win.tobytes() and arms.tobytes() == b.arms.tobytes()
     assert packed.tobytes() == b.packed[:packed.size].tobytes()
+
+
+def test_long_window_arm_filter_matches_reference_golden():
+    """Window::use_reference_long_filter: the mirror's add_* keeps exactly the arms the reference's Window
+    keeps for LONG windows (reference include/Window.hpp:66-101, include/Filter.hpp).  Golden flags from the
+    compiled reference (tests/golden/make_golden.py filter), both outcomes well represented."""
+    from hypo_b200.batch import WindowSpec, build_batch
+    from hypo_b200.hostlib import long_arm_filter
+    from tests.conftest import load_golden
+    g = load_golden("long_filter.json.gz")
+    specs = [WindowSpec(w["draft"], w["internal"], w["pre"], w["suf"], 0, 1) for w in g["windows"]]
+    want = np.array([x for w in g["windows"] for x in w["accepted"]], dtype=bool)
+    assert (~want).sum() > 100 and want.sum() > 100
+    got = long_arm_filter(build_batch(specs))
+    assert (got == want).all(), f"{int((got != want).sum())} of {want.size} arms decided differently"
+    # SHORT windows are never filtered
+    short = [WindowSpec(w["draft"], w["internal"], w["pre"], w["suf"], 0, 0) for w in g["windows"][:8]]
+    assert long_arm_filter(build_batch(short)).all()
+
+
+def test_long_window_arm_filter_vs_compiled_reference():
+    from hypo_b200.hostlib import long_arm_filter
+    from tests.oracle_util import ref_consensus, ref_lib
+    if ref_lib() is None:
+        import pytest
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    for seed, kw in ((21, dict(n_win=60, length=250, n_arms=20, kind="internal", err=0.08, wtype=1)),
+                     (22, dict(n_win=60, length=90, n_arms=12, kind="mixed", err=0.04, wtype=1)),
+                     (23, dict(n_win=40, length=30, n_arms=8, kind="prefix", err=0.02, wtype=1))):
+        b = synth_batch(seed, **kw)
+        _, acc, _ = ref_consensus(b)
+        assert (long_arm_filter(b) == acc).all(), kw
