@@ -205,6 +205,40 @@ int hypo_host_pack(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc*
     return HYPO_OK;
 }
 
+// CPU only: the PackedSeq mirror on the data-format side of the path - same contract as
+// hypo_ref_packedseq_probe (oracle/ref_driver.cpp), which answers with the reference's own class.
+int hypo_host_packedseq_probe(const uint8_t* hts, uint32_t seq_len, uint32_t offset, uint32_t left, uint32_t right,
+                              char* out2, char* out4, char* sub2, char* sub24, char* sub4, char* rng4) {
+    using namespace hypo;
+    int flags = 0;
+    PackedSeq<4> r4(seq_len, offset, hts);
+    const std::string s4 = r4.unpack();
+    memcpy(out4, s4.data(), s4.size());
+    PackedSeq<2> r2(seq_len, offset, hts);
+    if (r2.is_valid()) {
+        flags |= 1;
+        const std::string s2 = r2.unpack();
+        memcpy(out2, s2.data(), s2.size());
+        PackedSeq<2> p(r2, left, right);
+        const std::string t = p.unpack();
+        memcpy(sub2, t.data(), t.size());
+    }
+    bool clean = true;
+    for (uint32_t i = left; i < right; ++i) clean = clean && r4.enc_base_at(i) < 4;
+    if (clean) {
+        flags |= 2;
+        PackedSeq<2> p(r4, left, right);
+        const std::string t = p.unpack();
+        memcpy(sub24, t.data(), t.size());
+    }
+    PackedSeq<4> q(r4, left, right);
+    const std::string u = q.unpack();
+    memcpy(sub4, u.data(), u.size());
+    const std::string v = r4.unpack(left, right);
+    memcpy(rng4, v.data(), v.size());
+    return flags;
+}
+
 // CPU only: which arms the Window mirror keeps when it filters the arms of LONG windows like the
 // reference's Window does (Window::use_reference_long_filter; reference include/Window.hpp:66-101,
 // include/Filter.hpp).  accepted[a] = 1/0 per arm descriptor; SHORT windows keep every arm.  Returns

@@ -212,6 +212,46 @@ int hypo_ref_inspect_dump(const char* path, const char* contig, const int8_t sco
     return ofs.good() ? HYPO_OK : HYPO_E_ARG;
 }
 
+// Behaviour of the reference's PackedSeq on the data-format side of the path (reference
+// src/PackedSeq.cpp:122-229): a read as htslib stores it (4-bit codes, two per byte) packed from `offset`,
+// and sub-ranges of packed sequences, as hypo::Alignment / hypo::Contig build arms and window drafts.
+// Outputs (ASCII, caller-sized): out2 / out4 = the read as PackedSeq<2> / PackedSeq<4> (seq_len chars),
+// sub2 = PackedSeq<2>(read2, left, right), sub24 = PackedSeq<2>(read4, left, right), sub4 =
+// PackedSeq<4>(read4, left, right), rng4 = read4.unpack(left, right) (right-left chars each).
+// flags bit 0: PackedSeq<2> of the read is valid (out2 / sub2 filled); bit 1: [left, right) of the read holds
+// only A/C/G/T (sub24 filled - the reference exits on anything else).
+int hypo_ref_packedseq_probe(const uint8_t* hts, uint32_t seq_len, uint32_t offset, uint32_t left, uint32_t right,
+                             char* out2, char* out4, char* sub2, char* sub24, char* sub4, char* rng4) {
+    using namespace hypo;
+    int flags = 0;
+    PackedSeq<4> r4(seq_len, offset, hts);
+    const std::string s4 = r4.unpack();
+    memcpy(out4, s4.data(), s4.size());
+    PackedSeq<2> r2(seq_len, offset, hts);
+    if (r2.is_valid()) {
+        flags |= 1;
+        const std::string s2 = r2.unpack();
+        memcpy(out2, s2.data(), s2.size());
+        PackedSeq<2> p(r2, left, right);
+        const std::string t = p.unpack();
+        memcpy(sub2, t.data(), t.size());
+    }
+    bool clean = true;
+    for (uint32_t i = left; i < right; ++i) clean = clean && r4.enc_base_at(i) < 4;
+    if (clean) {
+        flags |= 2;
+        PackedSeq<2> p(r4, left, right);
+        const std::string t = p.unpack();
+        memcpy(sub24, t.data(), t.size());
+    }
+    PackedSeq<4> q(r4, left, right);
+    const std::string u = q.unpack();
+    memcpy(sub4, u.data(), u.size());
+    const std::string v = r4.unpack(left, right);
+    memcpy(rng4, v.data(), v.size());
+    return flags;
+}
+
 int hypo_ref_max_threads(void) { return omp_get_max_threads(); }
 
 // 1 if this build of the reference selected spoa's SIMD engine (built with

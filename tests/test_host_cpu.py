@@ -116,3 +116,52 @@ def test_long_window_arm_filter_vs_compiled_reference():
         b = synth_batch(seed, **kw)
         _, acc, _ = ref_consensus(b)
         assert (long_arm_filter(b) == acc).all(), kw
+
+
+def _packedseq_probe(lib, name, hts, seq_len, offset, left, right):
+    import ctypes as C
+    fn = getattr(lib, name)
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_char_p] * 6
+    bufs = [C.create_string_buffer(max(n, 1)) for n in (seq_len, seq_len) + (right - left,) * 4]
+    flags = fn(hts.ctypes.data, seq_len, offset, left, right, *bufs)
+    out = [b.raw[:n] for b, n in zip(bufs, (seq_len, seq_len) + (right - left,) * 4)]
+    if not flags & 1:
+        out[0] = out[2] = b""
+    if not flags & 2:
+        out[3] = b""
+    return flags, out
+
+
+def test_packedseq_mirror_vs_compiled_reference():
+    """Data formats on the input side of the path: a read as htslib stores it -> PackedSeq<2>/<4>, and
+    sub-ranges of packed sequences (how hypo::Alignment cuts arms and hypo::Contig cuts window drafts;
+    reference src/PackedSeq.cpp:122-229).  The mirror must answer like the reference's own class."""
+    import pytest
+    from hypo_b200 import hostlib
+    from tests.oracle_util import ref_lib
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    rng = np.random.default_rng(77)
+    codes = np.array([1, 2, 4, 8], np.uint8)   # A C G T in htslib's 4-bit alphabet
+    seen_invalid = seen_dirty = 0
+    for trial in range(300):
+        total = int(rng.integers(1, 90))
+        nib = codes[rng.integers(0, 4, size=total)]
+        if trial % 3 == 0:   # sprinkle N (15) and other ambiguity codes
+            k = rng.integers(0, total, size=max(1, total // 15))
+            nib[k] = rng.choice(np.array([15, 3, 5, 0], np.uint8), size=k.size)
+        if total & 1:
+            nib = np.append(nib, np.uint8(0))
+        hts = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8)
+        offset = int(rng.integers(0, total))
+        seq_len = int(rng.integers(1, total - offset + 1))
+        left = int(rng.integers(0, seq_len))
+        right = int(rng.integers(left + 1, seq_len + 1))   # (the reference cannot build an empty sub-range: bad_alloc)
+        want = _packedseq_probe(ref, "hypo_ref_packedseq_probe", hts, seq_len, offset, left, right)
+        got = _packedseq_probe(hostlib.lib(), "hypo_host_packedseq_probe", hts, seq_len, offset, left, right)
+        assert got == want, (trial, seq_len, offset, left, right)
+        seen_invalid += not want[0] & 1
+        seen_dirty += not want[0] & 2
+    assert seen_invalid > 10 and seen_dirty > 5
