@@ -3,9 +3,10 @@
 // Same public surface and bit layout as the reference class (reference
 // include/PackedSeq.hpp:84-158, src/PackedSeq.cpp:28-262) for everything the POA path and
 // its callers use: construction from a string / from an htslib 4-bit sequence / from a
-// sub-range of another PackedSeq, unpack, get_seq_size, enc_base_at, base_at, is_valid.
-// The k-mer search helpers (find_kmer, check_kmer, ...) belong to the windowing code, which
-// is out of scope, and are not mirrored.
+// sub-range of another PackedSeq, unpack, get_seq_size, enc_base_at, base_at, is_valid, and the k-mer
+// search helpers arm extraction uses to anchor a read segment on its window (find_kmer, check_kmer and
+// their canonical variants, reference src/PackedSeq.cpp:264-414).  tests/test_host_cpu.py pins all of it
+// against the reference's own class (compiled into oracle/_ref).
 //
 // One addition: data()/remainder() give read-only access to the packed bytes so the batch
 // packer can hand them to the device verbatim (the reference keeps _data private,
@@ -114,6 +115,63 @@ public:
         std::string s(right_ind - left_ind, 'N');
         for (size_t i = left_ind; i < right_ind; ++i) s[i - left_ind] = base_at(i);
         return s;
+    }
+
+    // ---- k-mer search (k-mers as 2-bit codes, first base in the highest bits; a non-ACGT base restarts) ----
+    // Is `target` one of the k-mers inside [left, right)?  `result` = start of the first (is_first) or of
+    // the last occurrence; untouched when there is none.
+    bool find_kmer(const UINT64 target, const UINT k, const size_t left_ind, const size_t right_ind, const bool is_first,
+                   size_t& result) const {
+        assert(right_ind <= _len && left_ind <= right_ind);
+        bool found = false;
+        const UINT64 mask = (1ULL << (2 * k)) - 1;
+        UINT64 fwd = 0;
+        UINT run = 0;
+        for (size_t i = left_ind; i < right_ind; ++i) {
+            const BYTE b = enc_base_at(i);
+            if (b > 3) { run = 0; fwd = 0; continue; }
+            fwd = ((fwd << 2) | b) & mask;
+            if (run < k) ++run;
+            if (run == k && fwd == target) {
+                result = i + 1 - k;
+                found = true;
+                if (is_first) break;
+            }
+        }
+        return found;
+    }
+    // Does the k-mer that starts at `ind` equal `target`?
+    bool check_kmer(const UINT64 target, const UINT k, const size_t ind) const {
+        size_t at;
+        return find_kmer(target, k, ind, ind + k, true, at);
+    }
+    // Same for canonical k-mers (the smaller of a k-mer and its reverse complement).  The reference
+    // computes these in 32-bit registers (k <= 16) and so does this.
+    bool find_canonical_kmer(const UINT64 target, const UINT k, const size_t left_ind, const size_t right_ind,
+                             const bool is_first, size_t& result) const {
+        assert(right_ind <= _len && left_ind <= right_ind);
+        bool found = false;
+        const UINT32 top = 2 * (k - 1);
+        const UINT32 mask = (UINT32)((1ULL << (2 * k)) - 1);
+        UINT32 fwd = 0, rev = 0;
+        UINT run = 0;
+        for (size_t i = left_ind; i < right_ind; ++i) {
+            const BYTE b = enc_base_at(i);
+            if (b > 3) { run = 0; continue; }   // (the registers keep their bits; k valid bases flush them)
+            ++run;
+            fwd = (UINT32)((fwd << 2ull | b) & mask);
+            rev = (UINT32)((rev >> 2ull) | (3ULL ^ b) << top);
+            if (run >= k && (fwd < rev ? fwd : rev) == target) {
+                result = i + 1 - k;
+                found = true;
+                if (is_first) break;
+            }
+        }
+        return found;
+    }
+    bool check_canonical_kmer(const UINT64 target, const UINT k, const size_t ind) const {
+        size_t at;
+        return find_canonical_kmer(target, k, ind, ind + k, true, at);
     }
 
     // read-only view of the packed bytes (device consumes them verbatim)

@@ -239,6 +239,30 @@ int hypo_host_packedseq_probe(const uint8_t* hts, uint32_t seq_len, uint32_t off
     return flags;
 }
 
+// CPU only: k-mer search of the PackedSeq mirror - same contract as hypo_ref_kmer_probe.
+int hypo_host_kmer_probe(const char* seq, uint32_t len, int nb, int mode, uint64_t target, uint32_t k, uint32_t left,
+                         uint32_t right, int is_first, uint64_t* result) {
+    using namespace hypo;
+    size_t at = (size_t)-1;
+    bool found;
+    const std::string s(seq, len);
+    if (nb == 2) {
+        PackedSeq<2> p(s);
+        found = mode == 0 ? p.find_kmer(target, k, left, right, is_first != 0, at)
+              : mode == 1 ? p.check_kmer(target, k, left)
+              : mode == 2 ? p.find_canonical_kmer(target, k, left, right, is_first != 0, at)
+                          : p.check_canonical_kmer(target, k, left);
+    } else {
+        PackedSeq<4> p(s);
+        found = mode == 0 ? p.find_kmer(target, k, left, right, is_first != 0, at)
+              : mode == 1 ? p.check_kmer(target, k, left)
+              : mode == 2 ? p.find_canonical_kmer(target, k, left, right, is_first != 0, at)
+                          : p.check_canonical_kmer(target, k, left);
+    }
+    *result = found ? (uint64_t)at : ~0ull;
+    return found ? 1 : 0;
+}
+
 // CPU only: which arms the Window mirror keeps when it filters the arms of LONG windows like the
 // reference's Window does (Window::use_reference_long_filter; reference include/Window.hpp:66-101,
 // include/Filter.hpp).  accepted[a] = 1/0 per arm descriptor; SHORT windows keep every arm.  Returns

@@ -252,6 +252,33 @@ int hypo_ref_packedseq_probe(const uint8_t* hts, uint32_t seq_len, uint32_t offs
     return flags;
 }
 
+// The reference's k-mer search on packed sequences (reference src/PackedSeq.cpp:264-414), used by arm
+// extraction to anchor read segments.  nb = 2 / 4: PackedSeq<2> / PackedSeq<4> built from `seq`;
+// mode 0 find_kmer, 1 check_kmer (at `left`), 2 find_canonical_kmer, 3 check_canonical_kmer.
+// Returns found; *result = position for the find modes (all ones when not found / check modes).
+int hypo_ref_kmer_probe(const char* seq, uint32_t len, int nb, int mode, uint64_t target, uint32_t k, uint32_t left,
+                        uint32_t right, int is_first, uint64_t* result) {
+    using namespace hypo;
+    size_t at = (size_t)-1;
+    bool found;
+    const std::string s(seq, len);
+    if (nb == 2) {
+        PackedSeq<2> p(s);
+        found = mode == 0 ? p.find_kmer(target, k, left, right, is_first != 0, at)
+              : mode == 1 ? p.check_kmer(target, k, left)
+              : mode == 2 ? p.find_canonical_kmer(target, k, left, right, is_first != 0, at)
+                          : p.check_canonical_kmer(target, k, left);
+    } else {
+        PackedSeq<4> p(s);
+        found = mode == 0 ? p.find_kmer(target, k, left, right, is_first != 0, at)
+              : mode == 1 ? p.check_kmer(target, k, left)
+              : mode == 2 ? p.find_canonical_kmer(target, k, left, right, is_first != 0, at)
+                          : p.check_canonical_kmer(target, k, left);
+    }
+    *result = found ? (uint64_t)at : ~0ull;
+    return found ? 1 : 0;
+}
+
 int hypo_ref_max_threads(void) { return omp_get_max_threads(); }
 
 // 1 if this build of the reference selected spoa's SIMD engine (built with

@@ -165,3 +165,65 @@ def test_packedseq_mirror_vs_compiled_reference():
         seen_invalid += not want[0] & 1
         seen_dirty += not want[0] & 2
     assert seen_invalid > 10 and seen_dirty > 5
+
+
+def test_packedseq_kmer_search_vs_compiled_reference():
+    """find_kmer / check_kmer / find_canonical_kmer / check_canonical_kmer of the mirror against the
+    reference's class (reference src/PackedSeq.cpp:264-414): first and last occurrence, N restarts the
+    k-mer, canonical k-mers in 32-bit registers."""
+    import ctypes as C
+    import pytest
+    from hypo_b200 import hostlib
+    from tests.oracle_util import ref_lib
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+
+    def probe(lib, name, *a):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                       C.POINTER(C.c_uint64)]
+        r = C.c_uint64(0)
+        return fn(*a, C.byref(r)), int(r.value)
+
+    def kmer(s, canonical):
+        f = 0
+        for ch in s:
+            f = f << 2 | "ACGT".index(ch)
+        if not canonical:
+            return f
+        r = 0
+        for ch in reversed(s):
+            r = r << 2 | 3 - "ACGT".index(ch)
+        return min(f, r)
+
+    rng = np.random.default_rng(5)
+    hits = 0
+    for trial in range(600):
+        n = int(rng.integers(8, 120))
+        nb = 2 if trial % 2 else 4
+        seq = "".join(rng.choice(list("ACGT"), size=n))
+        if trial % 5 == 0:   # low complexity: repeated k-mers, first != last occurrence
+            seq = (seq[:6] * 30)[:n]
+        if nb == 4 and trial % 3 == 0:
+            seq = list(seq)
+            for p in rng.integers(0, n, size=max(1, n // 12)):
+                seq[p] = "N"
+            seq = "".join(seq)
+        k = int(rng.integers(3, min(16, n) + 1))
+        mode = int(rng.integers(0, 4))
+        left = int(rng.integers(0, n - k + 1))
+        right = int(rng.integers(left, n + 1)) if mode in (0, 2) else left + k
+        src = int(rng.integers(0, n - k + 1))
+        word = seq[src:src + k]
+        if "N" in word or trial % 4 == 0:
+            target = int(rng.integers(0, 4 ** k))
+        else:
+            target = kmer(word, mode >= 2)
+        args = (seq.encode(), n, nb, mode, target, k, left, right, int(trial % 2))
+        want = probe(ref, "hypo_ref_kmer_probe", *args)
+        got = probe(hostlib.lib(), "hypo_host_kmer_probe", *args)
+        assert got == want, (trial, seq, args)
+        hits += want[0]
+    assert 60 < hits < 540
