@@ -239,6 +239,29 @@ int hypo_host_packedseq_probe(const uint8_t* hts, uint32_t seq_len, uint32_t off
     return flags;
 }
 
+// CPU only: the Window mirror's counters with the reference's LONG-window arm filter switched on - same
+// contract as hypo_ref_window_counts.
+void hypo_host_window_counts(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, const uint8_t* packed,
+                             uint32_t* counts) {
+    hypo::Window::use_reference_long_filter(true);
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        hypo::PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        hypo::Window W(draft, 0, d.draft_len, d.wtype == HYPO_WINDOW_LONG ? hypo::WindowType::LONG : hypo::WindowType::SHORT);
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) W.add_internal(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) W.add_prefix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) W.add_suffix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_empty; ++i) W.add_empty();
+        uint32_t* c = counts + 8 * w;
+        c[0] = W.get_num_pre(); c[1] = W.get_num_suf(); c[2] = W.get_num_internal(); c[3] = W.get_num_total();
+        c[4] = W.get_maxlen_pre(); c[5] = W.get_maxlen_suf(); c[6] = (uint32_t)W.get_window_len();
+        W.clear_pre_suf();
+        c[7] = W.get_num_total();
+    }
+    hypo::Window::use_reference_long_filter(false);
+}
+
 // CPU only: k-mer search of the PackedSeq mirror - same contract as hypo_ref_kmer_probe.
 int hypo_host_kmer_probe(const char* seq, uint32_t len, int nb, int mode, uint64_t target, uint32_t k, uint32_t left,
                          uint32_t right, int is_first, uint64_t* result) {

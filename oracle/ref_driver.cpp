@@ -279,6 +279,29 @@ int hypo_ref_kmer_probe(const char* seq, uint32_t len, int nb, int mode, uint64_
     return found ? 1 : 0;
 }
 
+// The bookkeeping side of the reference's Window (reference include/Window.hpp:61-120): what the
+// counters report after the arms of a batch went through add_* (LONG windows filter them), and after
+// clear_pre_suf.  counts[8 * w + ...] = num_pre, num_suf, num_internal (incl. empty), num_total,
+// maxlen_pre, maxlen_suf, window_len, num_total after clear_pre_suf.
+void hypo_ref_window_counts(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, const uint8_t* packed,
+                            uint32_t* counts) {
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const HypoWindowDesc& d = win[w];
+        hypo::PackedSeq<4> draft(unpack4(packed + d.draft_off, d.draft_len));
+        hypo::Window W(draft, 0, d.draft_len, d.wtype == HYPO_WINDOW_LONG ? hypo::WindowType::LONG : hypo::WindowType::SHORT);
+        uint64_t a = d.first_arm;
+        for (uint32_t i = 0; i < d.n_internal; ++i, ++a) W.add_internal(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_pre; ++i, ++a) W.add_prefix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_suf; ++i, ++a) W.add_suffix(hypo::PackedSeq<2>(unpack2(packed + arms[a].off, arms[a].len)));
+        for (uint32_t i = 0; i < d.n_empty; ++i) W.add_empty();
+        uint32_t* c = counts + 8 * w;
+        c[0] = W.get_num_pre(); c[1] = W.get_num_suf(); c[2] = W.get_num_internal(); c[3] = W.get_num_total();
+        c[4] = W.get_maxlen_pre(); c[5] = W.get_maxlen_suf(); c[6] = (uint32_t)W.get_window_len();
+        W.clear_pre_suf();
+        c[7] = W.get_num_total();
+    }
+}
+
 int hypo_ref_max_threads(void) { return omp_get_max_threads(); }
 
 // 1 if this build of the reference selected spoa's SIMD engine (built with

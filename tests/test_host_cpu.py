@@ -227,3 +227,28 @@ def test_packedseq_kmer_search_vs_compiled_reference():
         assert got == want, (trial, seq, args)
         hits += want[0]
     assert 60 < hits < 540
+
+
+def test_window_mirror_counters_vs_compiled_reference():
+    """add_* / add_empty / get_num_* / get_maxlen_* / get_window_len / clear_pre_suf of the Window mirror
+    against the reference's Window (reference include/Window.hpp:61-120), LONG windows filtered."""
+    import ctypes as C
+    import pytest
+    from hypo_b200 import hostlib
+    from hypo_b200.batch import build_batch
+    from hypo_b200.synth import edge_case_windows
+    from tests.oracle_util import ref_lib
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    for b in (build_batch(edge_case_windows()), synth_batch(31, 80, 70, 14, "mixed", err=0.03),
+              synth_batch(32, 60, 200, 16, "mixed", err=0.06, wtype=1), synth_batch(33, 40, 90, 10, "prefix", err=0.02, wtype=1)):
+        res = []
+        for lib, name in ((ref, "hypo_ref_window_counts"), (hostlib.lib(), "hypo_host_window_counts")):
+            fn = getattr(lib, name)
+            fn.restype = None
+            fn.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+            c = np.zeros(8 * b.n_win, np.uint32)
+            fn(b.win.ctypes.data, b.n_win, b.arms.ctypes.data, b.packed.ctypes.data, c.ctypes.data)
+            res.append(c.reshape(-1, 8))
+        assert (res[0] == res[1]).all()
