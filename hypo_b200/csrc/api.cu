@@ -341,7 +341,14 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
             sum_raw = h_tmax->sum_raw; n_seq = h_tmax->n_seq;
             need_paths = h_tmax->any_long != 0;
             if (T.from_bounds) {
-                caps.lcap = (int)std::min<uint32_t>(std::max<uint32_t>(h_tmax->bound_len, 1), (uint32_t)T.lcap);
+                uint32_t lc = std::min<uint32_t>(std::max<uint32_t>(h_tmax->bound_len, 1), (uint32_t)T.lcap);
+                // The only sequence that can be longer than the longest input is the round-2 backbone of a
+                // LONG window: bounded by the node count of round 1, in practice about as long as the draft.
+                // Sizing the columns (hence the DP slot, hence how many warps fit the workspace) for that
+                // bound starves the grid, so every bound-driven tier but the last sizes them for twice the
+                // longest input; a backbone beyond that leaves the tier with kFailLen and runs in the next.
+                if (t + 1 < kNumTiers) lc = std::min<uint32_t>(lc, std::max<uint32_t>(2 * h_tmax->max_len + 64, 1023));
+                caps.lcap = (int)lc;
                 const uint32_t nb = std::max<uint32_t>(h_tmax->sum_len + 2, 64);
                 caps.ncap = (int)std::min<uint32_t>(nb, (uint32_t)T.ncap);
                 caps.ecap = (int)std::min<uint32_t>(nb + 64, (uint32_t)T.ecap);
