@@ -26,6 +26,12 @@ int poa_oracle_spoa_consensus(int8_t m, int8_t n, int8_t g, const char* seqs,
 int poa_oracle_window_stats(const int8_t scores[6], const HypoWindowDesc* win,
                             const HypoArmDesc* arms, const uint8_t* packed, uint64_t stats[5]);
 
+/* How the window's DAG grows: growth[3*i..] = nodes, edges, cumulative DP cells after the i-th sequence
+ * (both rounds of a LONG window, one after the other); *n = entries written (at most cap).  Feeds
+ * tools/projection_sim.py, the offline model of the kernels' growth projection. */
+int poa_oracle_window_growth(const int8_t scores[6], const HypoWindowDesc* win, const HypoArmDesc* arms,
+                             const uint8_t* packed, uint64_t* growth, uint32_t cap, uint32_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -153,3 +153,17 @@ def oracle_stats(batch: WindowBatch, w: int, scores=DEFAULT_SCORES) -> np.ndarra
         _ptr(sc, C.POINTER(C.c_int8)), _ptr(one, C.c_void_p), _ptr(batch.arms, C.c_void_p),
         _ptr(batch.packed, _u8p), _ptr(st, _u64p))
     return st
+
+
+def oracle_growth(batch: WindowBatch, w: int, scores=DEFAULT_SCORES) -> np.ndarray:
+    """[n_sequences, 3] nodes, edges, cumulative DP cells after every sequence of window w (both rounds of a
+    LONG window, one after the other)."""
+    one = batch.win[w : w + 1]
+    cap = 2 * (int(one["n_internal"][0]) + int(one["n_pre"][0]) + int(one["n_suf"][0]) + 2)
+    g = np.zeros(3 * cap, np.uint64)
+    n = C.c_uint32(0)
+    sc = _scores(scores)
+    oracle_lib().poa_oracle_window_growth(
+        _ptr(sc, C.POINTER(C.c_int8)), _ptr(one, C.c_void_p), _ptr(batch.arms, C.c_void_p),
+        _ptr(batch.packed, _u8p), _ptr(g, _u64p), C.c_uint32(cap), C.byref(n))
+    return g[: 3 * n.value].reshape(-1, 3).astype(np.int64)

@@ -110,3 +110,22 @@ def test_bulk_toposort_simulation():
     env = dict(os.environ, POA_ORACLE_CHECK_BULK="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_growth_trace_is_consistent_with_window_stats():
+    """poa_oracle_window_growth (input of tools/projection_sim.py): one entry per added sequence, nodes and
+    edges never shrink within a round, and the last entry equals the final graph of poa_oracle_window_stats."""
+    from tests.oracle_util import oracle_growth, oracle_stats
+    b = random_batch(21, 6, kind="mixed", length=80, n_arms=12, err=0.04)
+    for w in range(b.n_win):
+        g = oracle_growth(b, w)
+        st = oracle_stats(b, w)
+        d = b.win[w]
+        assert len(g) == int(d["n_internal"]) + int(d["n_pre"]) + int(d["n_suf"]) + (int(d["n_internal"]) == 0)
+        assert (np.diff(g[:, 0]) >= 0).all() and (np.diff(g[:, 1]) >= 0).all() and (np.diff(g[:, 2]) > 0).all()
+        assert int(g[-1][0]) == int(st[0]) and int(g[-1][1]) == int(st[1]) and int(g[-1][2]) == int(st[2])
+    bl = random_batch(22, 3, wtype=WINDOW_LONG, length=150, n_arms=8)
+    for w in range(bl.n_win):
+        g = oracle_growth(bl, w)
+        assert len(g) == 2 * (8 + 1)          # draft / backbone + 8 reads, two rounds
+        assert int(g[-1][0]) == int(oracle_stats(bl, w)[0])
