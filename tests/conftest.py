@@ -29,3 +29,8 @@ def golden_windows():
 @pytest.fixture(scope="session")
 def golden_spoa():
     return load_golden("spoa_global_consensus.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_windows_large():
+    return load_golden("windows_large.json.gz")

@@ -96,6 +96,41 @@ def window_fixture():
             "groups": groups}
 
 
+def large_window_fixture():
+    """Windows of the sizes the multi-tile and global-memory capacity tiers run (250-500 bp, up to 100 reads,
+    1-6 % read error, SHORT and LONG), consensus by the compiled reference.  Kept in a file of its own."""
+    rng = np.random.default_rng(20261020)
+    groups = []
+
+    def add(name, specs, scores=DEFAULT_SCORES):
+        batch = build_batch(specs)
+        cons, acc, _ = ref_consensus(batch, scores)
+        if not acc.all():
+            batch = drop_rejected_arms(batch, acc)
+            cons, acc, _ = ref_consensus(batch, scores)
+            assert acc.all()
+        wins = []
+        for w in range(batch.n_win):
+            s = batch.spec(w)
+            wins.append({"draft": s.draft, "internal": list(s.internal), "pre": list(s.pre),
+                         "suf": list(s.suf), "n_empty": s.n_empty, "wtype": s.wtype,
+                         "consensus": cons[w]})
+        groups.append({"name": name, "scores": list(scores), "windows": wins})
+
+    add("short_250", [random_window(rng, length=250, n_arms=30, kind=str(rng.choice(["internal", "mixed"])),
+                                    err=float(rng.choice([0.01, 0.05]))) for _ in range(8)])
+    add("short_500", [random_window(rng, length=int(rng.integers(400, 500)), n_arms=int(rng.integers(8, 30)),
+                                    kind=str(rng.choice(["internal", "prefix", "suffix"])),
+                                    err=float(rng.choice([0.01, 0.03, 0.06]))) for _ in range(8)])
+    add("many_reads", [random_window(rng, length=int(rng.integers(60, 125)), n_arms=100, kind="mixed",
+                                     err=float(rng.choice([0.01, 0.04]))) for _ in range(4)])
+    add("long_300_500", [random_window(rng, length=int(rng.integers(300, 500)), n_arms=int(rng.integers(12, 30)),
+                                       kind="internal", wtype=WINDOW_LONG, err=float(rng.choice([0.01, 0.03])))
+                         for _ in range(8)])
+    return {"generator_version": GENERATOR_VERSION, "oracle": "oracle/_ref/libhypo_ref.so (SISD)",
+            "groups": groups}
+
+
 def inspect_fixture():
     import ctypes as C
     import tempfile
@@ -157,6 +192,11 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        lw = large_window_fixture()
+        dump("windows_large.json.gz", lw)
+        print("large windows:", sum(len(g["windows"]) for g in lw["groups"]))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "filter":
         lf = long_filter_fixture()
         dump("long_filter.json.gz", lf)
@@ -172,3 +212,4 @@ if __name__ == "__main__":
     print("windows:", sum(len(g["windows"]) for g in wf["groups"]))
     print("inspect stream: %d windows, %d bytes" % inspect_fixture())
     dump("long_filter.json.gz", long_filter_fixture())
+    dump("windows_large.json.gz", large_window_fixture())

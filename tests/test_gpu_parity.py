@@ -36,6 +36,15 @@ def test_golden_vectors_from_compiled_reference(golden_windows):
     native.init(DEFAULT_SCORES, 0)
 
 
+def test_golden_large_windows_from_compiled_reference(golden_windows_large):
+    """The multi-tile and global-memory tiers against consensus strings produced by the reference itself."""
+    for group in golden_windows_large["groups"]:
+        batch, expected = group_batch(group)
+        native.init(tuple(group["scores"]), 0)
+        _assert_same(native.consensus(batch), expected, batch, group["name"])
+    native.init(DEFAULT_SCORES, 0)
+
+
 def test_edge_cases():
     b = build_batch(edge_case_windows())
     want, _ = oracle_consensus(b)

@@ -28,6 +28,17 @@ def test_golden_windows(golden_windows):
     assert total >= 200
 
 
+def test_golden_large_windows(golden_windows_large):
+    """Reference-made golden vectors at the sizes of the larger capacity tiers (250-500 bp, 100 reads, LONG)."""
+    total = 0
+    for group in golden_windows_large["groups"]:
+        batch, expected = group_batch(group)
+        got, _ = oracle_consensus(batch, tuple(group["scores"]))
+        assert got == expected, group["name"]
+        total += len(expected)
+    assert total == 28
+
+
 def test_thread_count_independent():
     b = random_batch(11, 64, kind="mixed", length=50, n_arms=12)
     a, _ = oracle_consensus(b, threads=1)
