@@ -12,7 +12,7 @@ from tests.oracle_util import oracle_consensus, ref_consensus, drop_rejected_arm
 tot = bad = 0
 t0 = time.time()
 seed = 7000
-for rep in range(6):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
     for kw in (dict(n_win=400, length=250, n_arms=30, kind="internal", err=0.01),
                dict(n_win=300, length=250, n_arms=30, kind="mixed", err=0.05),
                dict(n_win=150, length=500, n_arms=30, kind="internal", err=0.03),
