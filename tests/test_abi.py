@@ -64,6 +64,22 @@ def test_batch_select_reindexes_arms():
     assert sub.spec(1).draft == "GG"
 
 
+def test_out_bound_is_host_arithmetic_and_covers_every_consensus():
+    """hypo_gpu_out_bound needs no device: it equals the Python mirror of the rule and is an upper bound of
+    what the path can emit for every window (checked with the oracle's consensus lengths)."""
+    from hypo_b200.synth import edge_case_windows, random_batch
+    from tests.oracle_util import oracle_consensus
+    lib = ctypes.CDLL(native.LIB_PATH)
+    lib.hypo_gpu_out_bound.restype = ctypes.c_uint64
+    lib.hypo_gpu_out_bound.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]
+    for b in (build_batch(edge_case_windows()), random_batch(3, 40, kind="mixed", length=60, n_arms=9, err=0.1),
+              random_batch(4, 10, kind="internal", length=200, n_arms=6, wtype=1)):
+        per = b.out_bound()
+        assert lib.hypo_gpu_out_bound(b.win.ctypes.data, b.n_win, b.arms.ctypes.data, b.n_arms) == int(per.sum())
+        cons, _ = oracle_consensus(b)
+        assert all(len(c) <= int(p) for c, p in zip(cons, per))
+
+
 def test_no_cpu_fallback_without_device():
     """On a box without a GPU the product path must raise, not silently compute on the CPU."""
     try:
