@@ -105,12 +105,14 @@ class WindowBatch:
         return int(self.win["draft_len"].astype(np.int64).sum())
 
     def out_bound(self) -> np.ndarray:
-        """Per-window upper bound of consensus bytes (same rule as hypo_gpu_out_bound)."""
+        """Per-window upper bound of the bytes a window may write (same rule as hypo_gpu_window_bounds):
+        SHORT sum(len) + 2 * arms + draft + 2; LONG 2 * sum(len) + draft + 2."""
         n_per = (self.win["n_internal"] + self.win["n_pre"] + self.win["n_suf"]).astype(np.int64)
         first = self.win["first_arm"].astype(np.int64)
-        csum = np.concatenate([[0], np.cumsum(self.arms["len"].astype(np.int64) + 2)])
+        csum = np.concatenate([[0], np.cumsum(self.arms["len"].astype(np.int64))])
         s = csum[first + n_per] - csum[first]
-        return np.maximum(self.win["draft_len"].astype(np.int64), s + self.win["draft_len"] + 2)
+        draft = self.win["draft_len"].astype(np.int64)
+        return np.where(self.win["wtype"] == WINDOW_LONG, 2 * s + draft + 2, s + 2 * n_per + draft + 2)
 
     def algorithmic_bytes(self, consensus_bytes: int) -> int:
         """Compulsory HBM traffic of one pass: every input byte read

@@ -1,25 +1,36 @@
 // api.cu — the C ABI of include/hypo_b200.h on top of the sm_100a kernels.
 //
 // Tiering: every window first runs in the fastest tier whose static limits
-// it satisfies; a window that overflows a capacity at run time is abandoned, appended to the
-// tier's overflow list on the device and re-run from scratch in the next tier.  The last tier
-// is sized from exact upper bounds, so nothing ever falls back to the CPU.
+// it satisfies; a window that overflows a capacity at run time is abandoned, appended ON THE DEVICE
+// to the list of the tier's successor and re-run from scratch there.  The last tier is sized from
+// exact upper bounds and fills reads beyond the 16-bit DP range with 32-bit cells, so nothing ever
+// falls back to the CPU and no window is refused for its scores or size.
+//
+// Devices: one context per GPU (streams, buffers, control blocks).  hypo_gpu_init drives one device,
+// hypo_gpu_init_multi drives G devices from ONE host process: the host-buffer entry point cuts the batch
+// into G contiguous window ranges of equal estimated cost, one host thread per device runs the same
+// single-device pipeline on its range, and the consensus bytes are gathered in window order - directly
+// per device, or through device 0 over NVLink (NCCL send/recv) when option "gather" is 2.
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hypo_b200.h"
 #include "poa_kernel.cuh"
 
 namespace hypo_b200 {
-cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile, int blocks,
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream);
 }
 
@@ -72,143 +83,15 @@ struct DevBuf {
 struct WinStat {
     uint32_t max_len;    // longest input sequence incl. markers (routing)
     uint32_t bound_len;  // upper bound of any sequence incl. the LONG round-2 backbone
-    uint32_t sum_len;    // sum of sequence lengths incl. markers (node upper bound)
+    uint32_t sum_len;    // sum of sequence lengths incl. markers (node upper bound), saturating
     uint32_t n_seq;      // sequences incl. draft/backbone
-    uint32_t sum_raw;    // LONG: draft + arms, for the path slot
+    uint32_t sum_raw;    // LONG: draft + arms + backbone bound, for the path slot (saturating)
 };
 
+constexpr int kMaxFields = 6;   // max_len, bound_len, sum_len, n_seq, sum_raw, any_long
 struct TierMax {
     uint32_t max_len, bound_len, sum_len, n_seq, sum_raw, any_long, count;
 };
-
-struct Ctx {
-    bool init = false;
-    int device = 0;
-    int sms = 0;
-    int smem_optin = 0;
-    int8_t scores[6];
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;          // host-buffer entry point: H2D of the batch's tail
-    cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
-    uint64_t launches = 0;
-    DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
-    DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp;
-    void* pinned_ctrl = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
-    uint32_t poa_launches = 0;
-    uint32_t tier_windows[8] = {0};
-    uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
-} g;
-
-std::mutex g_mu;
-
-// ---------------------------------------------------------------------------------------
-// Small helper kernels
-// ---------------------------------------------------------------------------------------
-
-// One thread per window: static facts + per-window output bound.
-__global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* __restrict__ arms,
-                                uint64_t n_win, uint64_t n_arms, uint64_t packed_bytes,
-                                WinStat* __restrict__ st, uint64_t* __restrict__ bound,
-                                uint32_t* __restrict__ bad) {
-    uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (w >= n_win) return;
-    const WinDesc d = win[w];
-    const uint64_t n = (uint64_t)d.n_internal + d.n_pre + d.n_suf;
-    bool ok = d.first_arm + n <= n_arms && d.wtype <= 1 &&
-              d.draft_off + (d.draft_len + 1) / 2 <= packed_bytes;
-    uint32_t max_len = 0, bound_len = 0, sum_len = 0, n_seq = 0, sum_raw = d.draft_len;
-    const uint32_t mark = d.wtype == 0 ? 2 : 0;
-    if (ok) {
-        for (uint64_t k = 0; k < n; ++k) {
-            const ArmDesc a = arms[d.first_arm + k];
-            if (a.off + (a.len + 3) / 4 > packed_bytes || a.reserved != 0) { ok = false; break; }
-            if (a.len == 0) continue;
-            const uint32_t l = a.len + mark;   // upper bound (prefix/suffix arms carry 1 marker)
-            max_len = max(max_len, l);
-            sum_len += l;
-            sum_raw += a.len;
-            ++n_seq;
-        }
-    }
-    // backbone / seq 0: draft (SHORT without internal arms, LONG round 1) or the previous
-    // consensus (LONG round 2, never longer than the node count of round 1)
-    const uint32_t dl = d.draft_len + mark;
-    if (d.wtype == 1) {
-        // round-2 backbone = curated round-1 consensus <= nodes of round 1 <= sum_len + draft
-        const uint32_t b = sum_len + d.draft_len;
-        max_len = max(max_len, d.draft_len);
-        bound_len = b;
-        sum_len += b;
-        sum_raw += b;   // generous: path slot must hold the round-2 backbone too
-        ++n_seq;
-    } else if (d.n_internal == 0) {
-        max_len = max(max_len, dl);
-        sum_len += dl;
-        ++n_seq;
-    }
-    if (!ok) atomicAdd(bad, 1u);
-    WinStat s;
-    s.max_len = max_len; s.bound_len = max(bound_len, max_len); s.sum_len = sum_len; s.n_seq = n_seq; s.sum_raw = sum_raw;
-    st[w] = s;
-    uint64_t b = (uint64_t)sum_len + 2;
-    if (b < d.draft_len) b = d.draft_len;
-    bound[w] = ok ? b : 0;
-}
-
-// Route windows to the first tier whose static limits they satisfy.
-// lists: [tier][n_win] window ids; counts[tier]; tmax[tier] running maxima.
-__global__ void route_kernel(const WinDesc* __restrict__ win, const WinStat* __restrict__ st,
-                             uint64_t n_win, int n_tiers, const uint32_t* __restrict__ tier_lcap,
-                             const uint32_t* __restrict__ tier_long_ok, const uint32_t* __restrict__ tier_est_cap,
-                             uint32_t* __restrict__ lists, TierMax* __restrict__ tmax) {
-    uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (w >= n_win) return;
-    const WinStat s = st[w];
-    const bool is_long = win[w].wtype == 1;
-    int t = 0;
-    // (sum_len of a LONG window counts the round-2 backbone bound as well: about twice the bases)
-    const uint32_t est = s.max_len + (uint32_t)(((uint64_t)s.sum_len * (is_long ? 8u : 15u)) / 1000u);
-    while (t < n_tiers - 1 &&
-           (s.max_len > tier_lcap[t] || (is_long ? !(tier_long_ok[t] & 1u) : (tier_long_ok[t] & 2u) != 0) ||
-            est > tier_est_cap[t]))
-        ++t;
-    const uint32_t k = atomicAdd(&tmax[t].count, 1u);
-    lists[(uint64_t)t * n_win + k] = (uint32_t)w;
-}
-
-// Running maxima over an explicit work list (used to size the bound-driven tiers).
-__global__ void listmax_kernel(const WinDesc* __restrict__ win, const WinStat* __restrict__ st,
-                               const uint32_t* __restrict__ list, uint32_t n, TierMax* __restrict__ tm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t w = list[i];
-    const WinStat s = st[w];
-    atomicMax(&tm->max_len, s.max_len);
-    atomicMax(&tm->bound_len, s.bound_len);
-    atomicMax(&tm->sum_len, s.sum_len);
-    atomicMax(&tm->n_seq, s.n_seq);
-    atomicMax(&tm->sum_raw, s.sum_raw);
-    if (win[w].wtype == 1) atomicMax(&tm->any_long, 1u);
-}
-
-// One warp per window: gather scratch consensus into the compact, window-ordered output.
-__global__ void gather_kernel(const char* __restrict__ scratch, const uint64_t* __restrict__ pos,
-                              const uint32_t* __restrict__ len, const uint64_t* __restrict__ off,
-                              char* __restrict__ dst, uint64_t n_win) {
-    const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_win) return;
-    const int lane = threadIdx.x & 31;
-    const char* s = scratch + pos[w];
-    char* d = dst + off[w];
-    for (uint32_t i = lane; i < len[w]; i += 32) d[i] = s[i];
-}
-
-__global__ void widen_kernel(const uint32_t* __restrict__ len, uint64_t* __restrict__ len64, uint64_t n) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) len64[i] = len[i];
-}
 
 // ---------------------------------------------------------------------------------------
 // Tier table
@@ -237,7 +120,8 @@ struct Tier {
 // T2/T3: DAG in global memory, capacities from the windows' exact upper bounds (T2 capped); 16 and 8
 //      warps/SM - nothing but occupancy hides the latency of the DAG accesses (16 warps/SM run the
 //      30 x 500 bp, 5 %-error windows 2.8x faster than 4), the DP workspace permitting (the grid
-//      shrinks when the slots would exceed 24 GB).
+//      shrinks when the slots would exceed 24 GB).  T3 is the tier that never refuses: reads whose
+//      scores x size leave the 16-bit DP range are filled with 32-bit cells there.
 // The capacities of the first kNumFixedTiers rows are compile-time constants of the kernels
 // (poa_kernel.cuh: fixed_caps); they are repeated here as documentation and checked at start-up.
 const Tier kTiers[] = {
@@ -250,12 +134,209 @@ const Tier kTiers[] = {
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 4, 0xffffffffu, 7},
     {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 8},
 };
-const int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
+constexpr int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 // Static routing sends only LONG windows to T1: at 5 warps/SM it is slower than T2 at 16 for SHORT windows
 // (30 x 500 bp: 19 vs 36 Mbp/s), while a LONG window's bound-driven capacities in T2 (the round-2 backbone
 // is bounded by the node count) blow up the DP workspace and with it shrink the grid (5.7 vs 2.0 Mbp/s).
 // SHORT windows still reach T1 as the overflow successor of T1m.
-const int kLongOnlyTier = 5;
+constexpr int kLongOnlyTier = 5;
+constexpr uint32_t kMaxSeqLen = 0x7ffffff0u;   // longer drafts / arms are malformed input (HYPO_E_ARG)
+
+// Device-side control block of one pass (zeroed before every pass).
+struct DevCtrl {
+    TierMax tmax[kNumTiers + 2];      // [t].count = length of tier t's list; the fields before it: maxima of
+                                      // the windows ROUTED there; [kNumTiers].count = windows no tier could
+                                      // hold; [kNumTiers + 1] = scratch of listmax_kernel
+    uint32_t queue[16];               // work-queue heads of the tier launches
+    uint32_t fail[kNumFailReasons];   // why windows were abandoned (diagnostics)
+    uint32_t bad;                     // malformed descriptors
+    uint32_t pad[3];
+};
+
+struct RouteCfg {
+    uint32_t lcap[kNumTiers], flags[kNumTiers], est_cap[kNumTiers];
+    int first_tier;
+};
+
+struct Options {
+    int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it)
+    int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
+    int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
+                          // 2 = NCCL send/recv to device 0 over NVLink, then one device-to-host copy
+};
+
+constexpr int kPasses = 2;   // head and tail of the pipelined host-buffer path
+
+struct Ctx {
+    int device = -1;
+    int sms = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host-buffer entry point: H2D of the batch's tail
+    cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
+    cudaEvent_t tev0[kPasses][kNumTiers] = {}, tev1[kPasses][kNumTiers] = {};
+    DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
+    DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp, gather;
+    void* pinned_ctrl = nullptr;                 // DevCtrl mirror + a few words
+    float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
+    uint32_t poa_launches = 0;
+    uint32_t tier_windows[8] = {0};
+    uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
+    std::string err;             // message of a failure on this device's worker thread
+};
+
+struct Global {
+    bool init = false;
+    int n_dev = 0;
+    Ctx* dev[HYPO_MAX_DEVICES] = {nullptr};
+    int8_t scores[6] = {0};
+    Options opt;
+    std::atomic<uint64_t> launches{0};
+    // NCCL (resolved at run time; only the multi-device gather uses it)
+    void* nccl_lib = nullptr;
+    void* comms[HYPO_MAX_DEVICES] = {nullptr};
+    bool comms_ready = false;
+} G;
+
+std::mutex g_mu;
+
+// ---------------------------------------------------------------------------------------
+// Small helper kernels
+// ---------------------------------------------------------------------------------------
+
+__host__ __device__ inline uint32_t sat32(uint64_t v) { return v > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)v; }
+
+// One thread per window: validation, static facts, per-window output bound, and the tier the window
+// starts in (appended to that tier's list; per-tier maxima of the routed windows for the launcher).
+// Descriptors are validated against the ranges the caller made resident: arms [a_lo, a_hi), bytes
+// [b_lo, b_hi) (`arms` / the kernels' `packed` are virtual bases: element 0 need not be resident).
+// All range arithmetic is 64-bit; lengths above kMaxSeqLen are malformed.
+__global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* __restrict__ arms,
+                                uint64_t n_win, uint64_t a_lo, uint64_t a_hi, uint64_t b_lo, uint64_t b_hi,
+                                WinStat* __restrict__ st, uint64_t* __restrict__ bound, RouteCfg cfg,
+                                uint32_t* __restrict__ lists, DevCtrl* __restrict__ ctrl) {
+    __shared__ uint32_t smax[kNumTiers][kMaxFields];
+    for (int i = threadIdx.x; i < kNumTiers * kMaxFields; i += blockDim.x) (&smax[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    int t = -1;
+    if (w < n_win) {
+        const WinDesc d = win[w];
+        const uint64_t n = (uint64_t)d.n_internal + d.n_pre + d.n_suf;
+        bool ok = d.wtype <= 1 && d.draft_len <= kMaxSeqLen && d.first_arm >= a_lo && d.first_arm <= a_hi &&
+                  n <= a_hi - d.first_arm;
+        if (ok && d.draft_len)
+            ok = d.draft_off >= b_lo && d.draft_off <= b_hi && ((uint64_t)d.draft_len + 1) / 2 <= b_hi - d.draft_off;
+        uint64_t max_len = 0, sum_len = 0, n_seq = 0, sum_arm = 0;
+        const uint32_t mark = d.wtype == 0 ? 2 : 0;
+        if (ok) {
+            for (uint64_t k = 0; k < n; ++k) {
+                const ArmDesc a = arms[d.first_arm + k];
+                if (a.reserved != 0 || a.len > kMaxSeqLen) { ok = false; break; }
+                if (a.len == 0) continue;   // never read (reference src/Window.cpp:103,114,125,182)
+                if (a.off < b_lo || a.off > b_hi || ((uint64_t)a.len + 3) / 4 > b_hi - a.off) { ok = false; break; }
+                const uint64_t l = (uint64_t)a.len + mark;   // upper bound (prefix/suffix arms carry 1 marker)
+                max_len = max_len > l ? max_len : l;
+                sum_len += l;
+                sum_arm += a.len;
+                ++n_seq;
+            }
+        }
+        // the rule of hypo_gpu_window_bounds
+        const uint64_t out_bound = d.wtype == 1 ? 2 * sum_arm + d.draft_len + 2 : sum_arm + 2 * n + d.draft_len + 2;
+        // backbone / seq 0: draft (SHORT without internal arms, LONG round 1) or the previous
+        // consensus (LONG round 2, never longer than the node count of round 1)
+        uint64_t bound_len = 0, sum_raw = (uint64_t)d.draft_len + sum_arm;
+        const uint64_t dl = (uint64_t)d.draft_len + mark;
+        if (d.wtype == 1) {
+            // round-2 backbone = curated round-1 consensus <= nodes of round 1 <= sum_len + draft
+            const uint64_t b = sum_len + d.draft_len;
+            max_len = max_len > d.draft_len ? max_len : d.draft_len;
+            bound_len = b;
+            sum_len += b;
+            sum_raw += b;   // generous: path slot must hold the round-2 backbone too
+            ++n_seq;
+        } else if (d.n_internal == 0) {
+            max_len = max_len > dl ? max_len : dl;
+            sum_len += dl;
+            ++n_seq;
+        }
+        if (!ok) atomicAdd(&ctrl->bad, 1u);
+        WinStat s;
+        s.max_len = sat32(max_len); s.bound_len = sat32(bound_len > max_len ? bound_len : max_len);
+        s.sum_len = sat32(sum_len); s.n_seq = sat32(n_seq); s.sum_raw = sat32(sum_raw);
+        st[w] = s;
+        bound[w] = ok ? out_bound : 0;
+        if (ok) {
+            // route to the first tier whose static limits the window satisfies
+            // (sum_len of a LONG window counts the round-2 backbone bound as well: about twice the bases)
+            const bool is_long = d.wtype == 1;
+            const uint64_t est = max_len + sum_len * (is_long ? 8u : 15u) / 1000u;
+            t = cfg.first_tier;
+            while (t < kNumTiers - 1 &&
+                   (max_len > cfg.lcap[t] || (is_long ? !(cfg.flags[t] & 1u) : (cfg.flags[t] & 2u) != 0) ||
+                    est > cfg.est_cap[t]))
+                ++t;
+            atomicMax(&smax[t][0], s.max_len);
+            atomicMax(&smax[t][1], s.bound_len);
+            atomicMax(&smax[t][2], s.sum_len);
+            atomicMax(&smax[t][3], s.n_seq);
+            atomicMax(&smax[t][4], s.sum_raw);
+            if (is_long) atomicMax(&smax[t][5], 1u);
+        }
+    }
+    // append to the tier's list, one atomic per (warp, tier)
+    {
+        const unsigned peers = __match_any_sync(0xffffffffu, t);
+        if (t >= 0) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&ctrl->tmax[t].count, (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            lists[(uint64_t)t * n_win + base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)w;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNumTiers * kMaxFields; i += blockDim.x) {
+        const uint32_t v = (&smax[0][0])[i];
+        if (v) atomicMax(&ctrl->tmax[i / kMaxFields].max_len + (i % kMaxFields), v);
+    }
+}
+
+// Maxima over the windows actually on a bound-driven tier's list (sizes its workspace).
+__global__ void listmax_kernel(const WinDesc* __restrict__ win, const WinStat* __restrict__ st,
+                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_ptr,
+                               TierMax* __restrict__ tm) {
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t w = list[i];
+        const WinStat s = st[w];
+        atomicMax(&tm->max_len, s.max_len);
+        atomicMax(&tm->bound_len, s.bound_len);
+        atomicMax(&tm->sum_len, s.sum_len);
+        atomicMax(&tm->n_seq, s.n_seq);
+        atomicMax(&tm->sum_raw, s.sum_raw);
+        if (win[w].wtype == 1) atomicMax(&tm->any_long, 1u);
+    }
+}
+
+// One warp per window: gather scratch consensus into the compact, window-ordered output.
+__global__ void gather_kernel(const char* __restrict__ scratch, const uint64_t* __restrict__ pos,
+                              const uint32_t* __restrict__ len, const uint64_t* __restrict__ off,
+                              char* __restrict__ dst, uint64_t n_win) {
+    const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_win) return;
+    const int lane = threadIdx.x & 31;
+    const char* s = scratch + pos[w];
+    char* d = dst + off[w];
+    for (uint32_t i = lane; i < len[w]; i += 32) d[i] = s[i];
+}
+
+__global__ void widen_kernel(const uint32_t* __restrict__ len, uint64_t* __restrict__ len64, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) len64[i] = len[i];
+}
 
 int check_scores(const int8_t s[6]) {
     if (s[2] > 0 || s[5] > 0)
@@ -263,101 +344,139 @@ int check_scores(const int8_t s[6]) {
     return HYPO_OK;
 }
 
-// Core: everything on the device.  d_out_pos/d_bound semantics: window w may write up to
-// bound[w] bytes at d_out + d_out_pos[w].
-int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t n_arms,
-               const uint8_t* d_packed, uint64_t packed_bytes, char* d_out, const uint64_t* d_out_pos,
-               uint32_t* d_out_len, const WinStat* d_stats, cudaStream_t stream, bool accumulate = false) {
-    if (!accumulate) {
+inline DevCtrl* host_ctrl(Ctx& g) { return (DevCtrl*)g.pinned_ctrl; }
+inline uint64_t* host_words(Ctx& g) { return (uint64_t*)((char*)g.pinned_ctrl + 3072); }
+
+// Stage 1 of a pass: classify + route `n_win` windows.  Nothing is synchronised here; the caller copies
+// the control block back (fetch_ctrl) together with whatever else it needs and synchronises ONCE.
+int stage_classify(Ctx& g, const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t a_lo, uint64_t a_hi,
+                   uint64_t b_lo, uint64_t b_hi, WinStat* d_stats, uint64_t* d_bound, cudaStream_t stream) {
+    if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
+    CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
+    // tier lists, the list of windows no tier could hold, and the per-window size projections
+    CUDA_TRY(g.lists.reserve(sizeof(uint32_t) * ((uint64_t)(kNumTiers + 2) * n_win + 64)));
+    CUDA_TRY(cudaMemsetAsync(g.ctrl.p, 0, sizeof(DevCtrl), stream));
+    uint32_t* d_lists = (uint32_t*)g.lists.p;
+    uint32_t* d_need = d_lists + (uint64_t)(kNumTiers + 1) * n_win;
+    CUDA_TRY(cudaMemsetAsync(d_need, 0, sizeof(uint32_t) * n_win, stream));
+    RouteCfg cfg;
+    for (int t = 0; t < kNumTiers; ++t) {
+        cfg.lcap[t] = (uint32_t)kTiers[t].lcap;
+        cfg.flags[t] = (kTiers[t].long_ok ? 1u : 0u) | (t == kLongOnlyTier ? 2u : 0u);   // bit 0: LONG allowed, bit 1: SHORT not routed here
+        cfg.est_cap[t] = kTiers[t].est_cap;
+    }
+    cfg.first_tier = std::min(std::max(G.opt.first_tier, 0), kNumTiers - 1);
+    const int tb = 128;
+    classify_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_arms, n_win, a_lo, a_hi, b_lo, b_hi,
+                                                                        d_stats, d_bound, cfg, d_lists,
+                                                                        (DevCtrl*)g.ctrl.p);
+    ++G.launches;
+    CUDA_TRY(cudaGetLastError());
+    return HYPO_OK;
+}
+
+cudaError_t fetch_ctrl(Ctx& g, cudaStream_t stream) {
+    return cudaMemcpyAsync(g.pinned_ctrl, g.ctrl.p, sizeof(DevCtrl), cudaMemcpyDeviceToHost, stream);
+}
+
+int check_bad(Ctx& g, bool quiet) {
+    const uint32_t bad = host_ctrl(g)->bad;
+    if (!bad) return HYPO_OK;
+    if (quiet) return HYPO_E_ARG;
+    return fail(HYPO_E_ARG, "%u window descriptor(s) reference arms/bytes out of range (or lengths above %u)", bad,
+                kMaxSeqLen);
+}
+
+inline void merge_max(TierMax& e, const TierMax& r) {
+    e.max_len = std::max(e.max_len, r.max_len); e.bound_len = std::max(e.bound_len, r.bound_len);
+    e.sum_len = std::max(e.sum_len, r.sum_len); e.n_seq = std::max(e.n_seq, r.n_seq);
+    e.sum_raw = std::max(e.sum_raw, r.sum_raw); e.any_long |= r.any_long;
+}
+
+// Stage 2 of a pass: the tier launches.  host_ctrl(g) holds the control block as of the end of stage 1
+// (routed counts and maxima).  The lists live on the device: a launch appends the windows it abandons to its
+// successor's list, so consecutive launches need no host round trip; the host only looks again before a
+// bound-driven tier (whose capacities come from maxima it has to know) and at the end.
+int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms,
+                const uint8_t* d_packed, char* d_out, const uint64_t* d_out_pos, uint32_t* d_out_len,
+                const WinStat* d_stats, cudaStream_t stream) {
+    if (pass == 0) {
         g.poa_ms = 0.f;
         g.poa_launches = 0;
         memset(g.tier_windows, 0, sizeof(g.tier_windows));
         memset(g.fail_hist, 0, sizeof(g.fail_hist));
     }
     if (n_win == 0) return HYPO_OK;
-    if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
-    // control block: [0..kNumTiers) TierMax, then queue counters
-    const size_t ctrl_bytes = sizeof(TierMax) * (kNumTiers + 1) + (64 + kNumFailReasons) * sizeof(uint32_t);
-    CUDA_TRY(g.ctrl.reserve(ctrl_bytes));
-    CUDA_TRY(g.lists.reserve(sizeof(uint32_t) * ((uint64_t)kNumTiers * n_win + (n_win + 1) * 2 + 64)));
-    CUDA_TRY(cudaMemsetAsync(g.ctrl.p, 0, ctrl_bytes, stream));
-    TierMax* d_tmax = (TierMax*)g.ctrl.p;
-    uint32_t* d_queue = (uint32_t*)((char*)g.ctrl.p + sizeof(TierMax) * (kNumTiers + 1));
+    DevCtrl* const d_ctrl = (DevCtrl*)g.ctrl.p;
+    DevCtrl* const h = host_ctrl(g);
     uint32_t* d_lists = (uint32_t*)g.lists.p;
-    // behind the tier lists: the overflow list of the running launch, then the per-window size projections
-    uint32_t* d_over = d_lists + (uint64_t)kNumTiers * n_win;
-    uint32_t* d_need = d_over + (n_win + 1);
-    CUDA_TRY(cudaMemsetAsync(d_need, 0, sizeof(uint32_t) * n_win, stream));
-    uint32_t* d_tier_lcap = d_queue + 16;
-    uint32_t* d_tier_long = d_queue + 32;
-    uint32_t* d_tier_seq = d_queue + 48;
-    uint32_t* d_fail = d_queue + 64;
+    uint32_t* d_need = d_lists + (uint64_t)(kNumTiers + 1) * n_win;
 
-    uint32_t h_lcap[16] = {0}, h_long[16] = {0}, h_seq[16] = {0};
+    // upper bound of each tier's work and maxima over everything that can reach it (routed + handed on)
+    uint64_t ub[kNumTiers + 1] = {0};
+    TierMax eff[kNumTiers + 1];
+    memset(eff, 0, sizeof(eff));
+    bool launched[kNumTiers] = {false};
     for (int t = 0; t < kNumTiers; ++t) {
-        h_lcap[t] = (uint32_t)kTiers[t].lcap;
-        h_long[t] = (kTiers[t].long_ok ? 1u : 0u) | (t == kLongOnlyTier ? 2u : 0u);   // bit 0: LONG allowed, bit 1: SHORT not routed here
-        h_seq[t] = kTiers[t].est_cap;
+        ub[t] += h->tmax[t].count;
+        merge_max(eff[t], h->tmax[t]);
+        if (ub[t] == 0) continue;
+        const int nx = kTiers[t].next;
+        ub[nx] += ub[t];
+        if (nx < kNumTiers) merge_max(eff[nx], eff[t]);
     }
-    CUDA_TRY(cudaMemcpyAsync(d_tier_lcap, h_lcap, sizeof(h_lcap), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(d_tier_long, h_long, sizeof(h_long), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(d_tier_seq, h_seq, sizeof(h_seq), cudaMemcpyHostToDevice, stream));
+    const int S = std::max({std::abs((int)G.scores[0]), std::abs((int)G.scores[1]), std::abs((int)G.scores[2]),
+                            std::abs((int)G.scores[3]), std::abs((int)G.scores[4]), std::abs((int)G.scores[5])});
     const int tb = 256;
-    route_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_stats, n_win, kNumTiers,
-                                                                     d_tier_lcap, d_tier_long, d_tier_seq, d_lists,
-                                                                     d_tmax);
-    ++g.launches;
-    CUDA_TRY(cudaGetLastError());
 
-    TierMax* h_tmax = (TierMax*)g.pinned_ctrl;
-    uint32_t* h_ovf_count = (uint32_t*)((char*)g.pinned_ctrl + 1024);
-    CUDA_TRY(cudaMemcpyAsync(h_tmax, d_tmax, sizeof(TierMax) * kNumTiers, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    uint32_t routed[16];
-    for (int t = 0; t < kNumTiers; ++t) routed[t] = h_tmax[t].count;
-
-    // Windows that overflow tier t at run time are appended to the list of tier kTiers[t].next
-    // (always a later one), behind its routed windows: every list holds each window at most once.
-    uint32_t pend[16] = {0};
+    bool counts_fresh = true;   // h->tmax[].count is exact for the tiers not yet launched
     for (int t = 0; t < kNumTiers; ++t) {
         const Tier& T = kTiers[t];
-        uint32_t* d_work = d_lists + (uint64_t)t * n_win;
-        const uint32_t n_work = routed[t] + pend[t];
-        if (n_work == 0) continue;
-        CUDA_TRY(cudaMemsetAsync(d_over, 0, sizeof(uint32_t), stream));
+        if (ub[t] == 0) continue;
+        TierMax M = eff[t];
+        uint64_t work_ub = ub[t];
+        if (T.from_bounds) {
+            // a bound-driven tier is expensive to set up (workspace sized from the maxima): look first
+            if (!counts_fresh) {
+                CUDA_TRY(fetch_ctrl(g, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                counts_fresh = true;
+            }
+            work_ub = h->tmax[t].count;
+            if (work_ub == 0) continue;
+            // exact maxima over the windows that really are on the list
+            TierMax* d_tm = &d_ctrl->tmax[kNumTiers + 1];
+            CUDA_TRY(cudaMemsetAsync(d_tm, 0, sizeof(TierMax), stream));
+            listmax_kernel<<<(unsigned)std::min<uint64_t>((work_ub + tb - 1) / tb, 1024), tb, 0, stream>>>(
+                d_win, d_stats, d_lists + (uint64_t)t * n_win, &d_ctrl->tmax[t].count, d_tm);
+            ++G.launches;
+            CUDA_TRY(cudaMemcpyAsync(&h->tmax[kNumTiers + 1], d_tm, sizeof(TierMax), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            M = h->tmax[kNumTiers + 1];
+        }
 
         Caps caps;
         caps.ncap = T.ncap; caps.ecap = T.ecap; caps.acap = T.acap; caps.scap = T.scap; caps.lcap = T.lcap;
         caps.alslots = t < kNumFixedTiers ? fixed_caps(t).alslots : kAlSlotsMax;
-        bool need_paths = false;
-        uint32_t sum_raw = 0, n_seq = 0;
-        if (T.from_bounds || T.long_ok) {
-            TierMax* d_tm = d_tmax + kNumTiers;
-            CUDA_TRY(cudaMemsetAsync(d_tm, 0, sizeof(TierMax), stream));
-            listmax_kernel<<<(n_work + tb - 1) / tb, tb, 0, stream>>>(d_win, d_stats, d_work, n_work, d_tm);
-            ++g.launches;
-            CUDA_TRY(cudaMemcpyAsync(h_tmax, d_tm, sizeof(TierMax), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            sum_raw = h_tmax->sum_raw; n_seq = h_tmax->n_seq;
-            need_paths = h_tmax->any_long != 0;
-            if (T.from_bounds) {
-                uint32_t lc = std::min<uint32_t>(std::max<uint32_t>(h_tmax->bound_len, 1), (uint32_t)T.lcap);
-                // The only sequence that can be longer than the longest input is the round-2 backbone of a
-                // LONG window: bounded by the node count of round 1, in practice about as long as the draft.
-                // Sizing the columns (hence the DP slot, hence how many warps fit the workspace) for that
-                // bound starves the grid, so every bound-driven tier but the last sizes them for twice the
-                // longest input; a backbone beyond that leaves the tier with kFailLen and runs in the next.
-                if (t + 1 < kNumTiers) lc = std::min<uint32_t>(lc, std::max<uint32_t>(2 * h_tmax->max_len + 64, 1023));
-                caps.lcap = (int)lc;
-                const uint32_t nb = std::max<uint32_t>(h_tmax->sum_len + 2, 64);
-                caps.ncap = (int)std::min<uint32_t>(nb, (uint32_t)T.ncap);
-                caps.ecap = (int)std::min<uint32_t>(nb + 64, (uint32_t)T.ecap);
-                caps.acap = (int)std::min<uint32_t>(nb, (uint32_t)T.acap);
-                caps.scap = (int)std::min<uint32_t>(2 * nb + 64, (uint32_t)T.scap);
-            }
-            if (n_seq > 32000)
-                return fail(HYPO_E_CAPACITY, "window with %u sequences exceeds 16-bit edge weights", n_seq);
+        const bool need_paths = T.long_ok && M.any_long != 0;
+        if (T.from_bounds) {
+            uint32_t lc = std::min<uint32_t>(std::max<uint32_t>(M.bound_len, 1), (uint32_t)T.lcap);
+            // The only sequence that can be longer than the longest input is the round-2 backbone of a
+            // LONG window: bounded by the node count of round 1, in practice about as long as the draft.
+            // Sizing the columns (hence the DP slot, hence how many warps fit the workspace) for that
+            // bound starves the grid, so every bound-driven tier but the last sizes them for twice the
+            // longest input; a backbone beyond that leaves the tier with kFailLen and runs in the next.
+            if (t + 1 < kNumTiers) lc = std::min<uint32_t>(lc, std::max<uint32_t>(2 * M.max_len + 64, 1023));
+            caps.lcap = (int)lc;
+            const uint32_t nb = std::max<uint32_t>(M.sum_len + 2, 64);
+            caps.ncap = (int)std::min<uint32_t>(nb, (uint32_t)T.ncap);
+            caps.ecap = (int)std::min<uint32_t>(nb + 64, (uint32_t)T.ecap);
+            caps.acap = (int)std::min<uint32_t>(nb, (uint32_t)T.acap);
+            caps.scap = (int)std::min<uint32_t>(2 * nb + 64, (uint32_t)T.scap);
+            if (G.opt.scap > 0 && t + 1 < kNumTiers) caps.scap = G.opt.scap;
         }
+        if (M.n_seq > 32000)
+            return fail(HYPO_E_CAPACITY, "window with %u sequences exceeds 16-bit edge weights", M.n_seq);
         caps.tiles = T.one_tile ? 1 : (caps.lcap + 1 + kTileCols - 1) / kTileCols;
         const ArenaLayout L = arena_layout(caps);
 
@@ -371,9 +490,17 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
         }
         int blocks = g.sms * bps;
         uint64_t warps = (uint64_t)blocks * wpb;
-        if (warps > n_work) { blocks = (int)((n_work + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
-        // matrix rows (+ spare) and, behind them, the two boundary arrays of the multi-tile fill
-        const uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
+        if (warps > work_ub) { blocks = (int)((work_ub + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
+        // matrix rows (+ spare) and, behind them, the two boundary arrays of the multi-tile fill; the last
+        // tier doubles the slot when a window may need 32-bit cells (same test as the kernel's guard, on
+        // the upper bounds)
+        const bool wide = t == kNumTiers - 1;
+        uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
+        if (wide) {
+            const uint64_t cols = (uint64_t)caps.tiles * kTileCols;
+            if ((uint64_t)S * ((uint64_t)caps.ncap + 1 + cols) > (uint64_t)kMaxH16 || 2ull * S * cols > (uint64_t)kMaxH16)
+                h_slot = (2 * (uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 63) & ~63ull;
+        }
         // keep the DP workspace bounded: shrink the grid if the slots would exceed ~24 GB
         while (warps * h_slot * 2 > (24ull << 30) && blocks > 1) { blocks = (blocks + 1) / 2; warps = (uint64_t)blocks * wpb; }
         CUDA_TRY(g.H.reserve(warps * h_slot * sizeof(int16_t)));
@@ -383,77 +510,445 @@ int run_device(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint
             CUDA_TRY(g.gws.reserve(warps * g_slot));
         }
         if (need_paths) {
-            p_slot = ((uint64_t)sum_raw + 2 * ((uint64_t)n_seq + 4) + 64 + 7) & ~7ull;
+            p_slot = ((uint64_t)M.sum_raw + 2 * ((uint64_t)M.n_seq + 4) + 64 + 7) & ~7ull;
             CUDA_TRY(g.paths.reserve(warps * p_slot * sizeof(uint16_t)));
         }
 
+        const int nx = T.next;   // kNumTiers = the list of windows nothing could hold
         Params P;
         P.win = d_win; P.arms = d_arms; P.packed = d_packed;
-        P.work = d_work; P.n_work = n_work;
-        P.queue = d_queue + t;
+        P.work = d_lists + (uint64_t)t * n_win; P.n_work = &d_ctrl->tmax[t].count;
+        P.queue = &d_ctrl->queue[t];
         P.out = d_out; P.out_pos = d_out_pos; P.out_len = d_out_len;
-        P.overflow = d_over;
-        P.fail_hist = d_fail;
+        P.next_list = d_lists + (uint64_t)nx * n_win; P.next_count = &d_ctrl->tmax[nx].count;
+        P.fail_hist = d_ctrl->fail;
         P.need = d_need;
         P.H = (int16_t*)g.H.p; P.h_slot = h_slot;
         P.gws = (uint8_t*)g.gws.p; P.g_slot = g_slot;
         P.paths = need_paths ? (uint16_t*)g.paths.p : nullptr; P.p_slot = p_slot;
         P.caps = caps;
-        P.sr_m = g.scores[0]; P.sr_n = g.scores[1]; P.sr_g = g.scores[2];
-        P.lr_m = g.scores[3]; P.lr_n = g.scores[4]; P.lr_g = g.scores[5];
-        CUDA_TRY(cudaEventRecord(g.ev0, stream));
-        CUDA_TRY(launch_poa(P, t, T.smem_graph, T.one_tile, blocks, wpb, smem, stream));
-        CUDA_TRY(cudaEventRecord(g.ev1, stream));
-        ++g.launches;
-        CUDA_TRY(cudaMemcpyAsync(h_ovf_count, d_over, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        {
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
-            g.poa_ms += ms;
-            g.poa_launches += 1;
-            g.tier_windows[t] += n_work;
-        }
-        const uint32_t over = *h_ovf_count;
-        if (over != 0) {
-            const int nxt = T.next;
-            if (nxt >= kNumTiers)
-                return fail(HYPO_E_CAPACITY, "%u window(s) exceed every device capacity tier (graph > 65534 nodes or "
-                                             "scores outside the 16-bit DP range)", over);
-            CUDA_TRY(cudaMemcpyAsync(d_lists + (uint64_t)nxt * n_win + routed[nxt] + pend[nxt], d_over + 1,
-                                     sizeof(uint32_t) * over, cudaMemcpyDeviceToDevice, stream));
-            pend[nxt] += over;
-        }
+        P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
+        P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
+        CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
+        CUDA_TRY(launch_poa(P, t, T.smem_graph, wide, blocks, wpb, smem, stream));
+        CUDA_TRY(cudaEventRecord(g.tev1[pass][t], stream));
+        ++G.launches;
+        launched[t] = true;
+        counts_fresh = false;
     }
-    uint32_t* h_fail = (uint32_t*)((char*)g.pinned_ctrl + 2560);
-    CUDA_TRY(cudaMemcpyAsync(h_fail, d_fail, sizeof(g.fail_hist), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(fetch_ctrl(g, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    for (int k = 0; k < kNumFailReasons; ++k) g.fail_hist[k] += h_fail[k];
+    for (int t = 0; t < kNumTiers; ++t) {
+        if (!launched[t]) continue;
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g.tev0[pass][t], g.tev1[pass][t]));
+        g.poa_ms += ms;
+        g.poa_launches += 1;
+        g.tier_windows[t] += h->tmax[t].count;
+    }
+    for (int k = 0; k < kNumFailReasons; ++k) g.fail_hist[k] += h->fail[k];
+    const uint32_t lost = h->tmax[kNumTiers].count;
+    if (lost != 0)
+        return fail(HYPO_E_CAPACITY, "%u window(s) exceed every device capacity tier (a graph of more than 65534 nodes, "
+                                     "a node with more than 254 in-edges, or more than 32000 reads)", lost);
     return HYPO_OK;
 }
 
-// Per-window static facts and output bounds of windows [0, n_win) of d_win into d_stats / d_bound.
-// n_arms / packed_bytes are the limits the descriptors are validated against (`quiet`: a violation is
-// reported as HYPO_E_ARG without a message: the pipelined path uses it to detect an input whose head
-// windows reference data of the tail).
-int prepare_stats(const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t n_arms,
-                  uint64_t packed_bytes, WinStat* d_stats, uint64_t* d_bound, cudaStream_t stream,
-                  bool quiet = false) {
-    uint32_t* d_bad = (uint32_t*)((char*)g.stats.p + g.stats.cap - 64);
-    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), stream));
-    const int tb = 128;
-    classify_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_arms, n_win, n_arms, packed_bytes,
-                                                                        d_stats, d_bound, d_bad);
-    ++g.launches;
-    CUDA_TRY(cudaGetLastError());
-    uint32_t* h_bad = (uint32_t*)((char*)g.pinned_ctrl + 2048);
-    CUDA_TRY(cudaMemcpyAsync(h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (*h_bad) {
-        if (quiet) return HYPO_E_ARG;
-        return fail(HYPO_E_ARG, "%u window descriptor(s) reference arms/bytes out of range", *h_bad);
+// ---------------------------------------------------------------------------------------
+// One device, one contiguous window range [w0, w1) of a host batch ("shard"; the whole batch when one
+// device is driven).  shard_compute leaves the range's consensus bytes compacted on the device
+// (g.out_compact, window order) with their n+1 local offsets in g.out_off; shard_fetch copies them out.
+// ---------------------------------------------------------------------------------------
+struct Shard {
+    uint64_t w0 = 0, w1 = 0;   // windows
+    uint64_t a0 = 0, a1 = 0;   // arm-table range the windows reference (made resident)
+    uint64_t b0 = 0, b1 = 0;   // byte range of the packed slab (made resident)
+    uint64_t total = 0;        // consensus bytes of the range
+    int rc = HYPO_OK;
+};
+
+// The caller's host buffers must not be touched after an entry point returns, on any path.
+struct CopyGuard {
+    cudaStream_t c;
+    bool armed = false;
+    ~CopyGuard() { if (armed) cudaStreamSynchronize(c); }
+};
+
+int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t* packed, Shard& sh) {
+    CUDA_TRY(cudaSetDevice(g.device));
+    cudaStream_t s = g.stream;
+    const uint64_t n_win = sh.w1 - sh.w0;
+    sh.total = 0;
+    if (n_win == 0) return HYPO_OK;
+    const uint64_t n_arms = sh.a1 - sh.a0, n_bytes = sh.b1 - sh.b0;
+
+    CUDA_TRY(g.win.reserve(sizeof(WinDesc) * n_win));
+    CUDA_TRY(g.arms.reserve(sizeof(ArmDesc) * std::max<uint64_t>(n_arms, 1)));
+    CUDA_TRY(g.packed.reserve(n_bytes + 16));
+    CUDA_TRY(g.out_pos.reserve(sizeof(uint64_t) * (n_win + 1)));
+    CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
+    CUDA_TRY(g.out_len.reserve(sizeof(uint32_t) * n_win));
+    CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
+    const WinDesc* d_win = (const WinDesc*)g.win.p;
+    // virtual bases: the descriptors keep their batch-wide indices / offsets
+    const ArmDesc* d_arms = (const ArmDesc*)g.arms.p - sh.a0;
+    const uint8_t* d_packed = (const uint8_t*)g.packed.p - sh.b0;
+    uint64_t* d_bound = (uint64_t*)g.out_off.p;   // reused as the compact offsets later
+    uint64_t* d_pos = (uint64_t*)g.out_pos.p;
+    WinStat* d_stats = (WinStat*)g.stats.p;
+    uint64_t* h64 = host_words(g);
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = g.cub_tmp.cap;
+
+    // ---- split: head = first ~1/8 of the windows, copied first and run while the tail crosses PCIe -----
+    const WinDesc* hw = win + sh.w0;
+    uint64_t w_s = 0, a_s = 0, b_s = 0;
+    bool piped = n_win >= 65536 && n_arms > 0 && n_bytes > 0;
+    if (piped) {
+        w_s = std::max<uint64_t>(32768, n_win / 8);
+        a_s = hw[w_s].first_arm;
+        piped = a_s >= sh.a0 && a_s <= sh.a1;
+        if (piped) {
+            b_s = std::min<uint64_t>(hw[w_s].draft_off, a_s < sh.a1 ? arms[a_s].off : sh.b1);
+            piped = b_s >= sh.b0 && b_s <= sh.b1;
+        }
     }
+    // an upper bound of the windows' scratch need that does not require looking at the arms: a window
+    // may write up to 2 * sum(len) + 2 * arms + draft_len + 2 bytes (hypo_gpu_window_bounds; the factor 2
+    // is the LONG round-2 backbone), and every base occupies at least 2 bits of the slab
+    const uint64_t scratch_cap = 8 * n_bytes + 4 * n_arms + 8 * n_win + 64;
+
+    CopyGuard guard{g.copy_stream};
+    bool copies_issued = false;
+    if (piped) {
+        guard.armed = true;
+        CUDA_TRY(g.out_scratch.reserve(scratch_cap + 16));
+        cudaStream_t c = g.copy_stream;
+        copies_issued = true;
+        const uint64_t na_h = a_s - sh.a0, nb_h = b_s - sh.b0;
+        CUDA_TRY(cudaMemcpyAsync(g.win.p, hw, sizeof(WinDesc) * w_s, cudaMemcpyHostToDevice, c));
+        if (na_h) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms + sh.a0, sizeof(ArmDesc) * na_h, cudaMemcpyHostToDevice, c));
+        if (nb_h) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed + sh.b0, nb_h, cudaMemcpyHostToDevice, c));
+        CUDA_TRY(cudaEventRecord(g.ev_head, c));
+        CUDA_TRY(cudaMemcpyAsync((WinDesc*)g.win.p + w_s, hw + w_s, sizeof(WinDesc) * (n_win - w_s), cudaMemcpyHostToDevice, c));
+        if (n_arms > na_h)
+            CUDA_TRY(cudaMemcpyAsync((ArmDesc*)g.arms.p + na_h, arms + a_s, sizeof(ArmDesc) * (n_arms - na_h), cudaMemcpyHostToDevice, c));
+        if (n_bytes > nb_h)
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)g.packed.p + nb_h, packed + b_s, n_bytes - nb_h, cudaMemcpyHostToDevice, c));
+        CUDA_TRY(cudaEventRecord(g.ev_tail, c));
+
+        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_head, 0));
+        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+        // head descriptors must only reference what has arrived: limits a_s / b_s
+        if (int rc = stage_classify(g, d_win, w_s, d_arms, sh.a0, a_s, sh.b0, b_s, d_stats, d_bound, s)) return rc;
+        CUDA_TRY(cudaMemsetAsync(d_bound + w_s, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, w_s + 1, s));
+        ++G.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + w_s, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(fetch_ctrl(g, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (check_bad(g, /*quiet=*/true) != HYPO_OK) {
+            piped = false;   // not laid out in window order (or really invalid): single-copy path decides
+            CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
+        }
+    }
+
+    if (piped) {
+        // ---- head: kernels (the tail is still being copied) -----------------------------------------
+        const uint64_t head_bytes = *h64;
+        if (head_bytes > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
+        if (int rc = stage_tiers(g, 0, d_win, w_s, d_arms, d_packed, (char*)g.out_scratch.p, d_pos,
+                                 (uint32_t*)g.out_len.p, d_stats, s))
+            return rc;
+        // ---- tail -----------------------------------------------------------------------------------
+        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
+        const uint64_t n_tail = n_win - w_s;
+        if (int rc = stage_classify(g, d_win + w_s, n_tail, d_arms, sh.a0, sh.a1, sh.b0, sh.b1, d_stats + w_s,
+                                    d_bound + w_s, s))
+            return rc;
+        CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveScan(g.cub_tmp.p, tmp_bytes, d_bound + w_s, d_pos + w_s, cuda::std::plus<>{},
+                                                (uint64_t)head_bytes, n_tail + 1, s));
+        ++G.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(fetch_ctrl(g, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (int rc = check_bad(g, false)) return rc;
+        if (*h64 > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
+        if (int rc = stage_tiers(g, 1, d_win + w_s, n_tail, d_arms, d_packed, (char*)g.out_scratch.p,
+                                 d_pos + w_s, (uint32_t*)g.out_len.p + w_s, d_stats + w_s, s))
+            return rc;
+    } else {
+        // ---- single copy --------------------------------------------------------------------------
+        if (copies_issued) {
+            // the split was attempted and abandoned: everything is on its way on the copy stream
+            CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(g.win.p, hw, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
+            if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms + sh.a0, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
+            if (n_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed + sh.b0, n_bytes, cudaMemcpyHostToDevice, s));
+        }
+        if (int rc = stage_classify(g, d_win, n_win, d_arms, sh.a0, sh.a1, sh.b0, sh.b1, d_stats, d_bound, s)) return rc;
+        CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+        ++G.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(fetch_ctrl(g, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (int rc = check_bad(g, false)) return rc;
+        CUDA_TRY(g.out_scratch.reserve(*h64 + 16));
+        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+        if (int rc = stage_tiers(g, 0, d_win, n_win, d_arms, d_packed, (char*)g.out_scratch.p, d_pos,
+                                 (uint32_t*)g.out_len.p, d_stats, s))
+            return rc;
+    }
+
+    // compact on the device: lengths -> offsets -> gather.  The tier lists are dead now and hold the
+    // widened lengths (they are always larger than 8 * (n_win + 1) bytes); the bounds become the offsets.
+    uint64_t* d_len64 = (uint64_t*)g.lists.p;
+    const int tb = 256;
+    widen_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, s>>>((const uint32_t*)g.out_len.p, d_len64, n_win);
+    CUDA_TRY(cudaMemsetAsync(d_len64 + n_win, 0, sizeof(uint64_t), s));
+    uint64_t* d_off = (uint64_t*)g.out_off.p;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
+    CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    sh.total = *h64;
+    CUDA_TRY(g.out_compact.reserve(sh.total + 16));
+    gather_kernel<<<(unsigned)((n_win * 32 + tb - 1) / tb), tb, 0, s>>>((const char*)g.out_scratch.p, (const uint64_t*)g.out_pos.p,
+                                                                      (const uint32_t*)g.out_len.p, d_off,
+                                                                      (char*)g.out_compact.p, n_win);
+    G.launches += 3;
+    CUDA_TRY(cudaGetLastError());
     return HYPO_OK;
+}
+
+// Copies a range's result to the host: bytes to out + base, local offsets to out_off[w0 .. w1) (the
+// caller adds `base` afterwards).  Asynchronous on the device's stream; shard_wait finishes it.
+int shard_fetch(Ctx& g, const Shard& sh, char* out, uint64_t base, uint64_t* out_off, bool bytes_too) {
+    CUDA_TRY(cudaSetDevice(g.device));
+    const uint64_t n_win = sh.w1 - sh.w0;
+    if (n_win == 0) return HYPO_OK;
+    if (bytes_too && sh.total)
+        CUDA_TRY(cudaMemcpyAsync(out + base, g.out_compact.p, sh.total, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(out_off + sh.w0, g.out_off.p, sizeof(uint64_t) * n_win, cudaMemcpyDeviceToHost, g.stream));
+    return HYPO_OK;
+}
+
+int shard_wait(Ctx& g) {
+    CUDA_TRY(cudaSetDevice(g.device));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return HYPO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL, resolved at run time (libnccl.so.2: the process may already carry one, e.g. torch's)
+// ---------------------------------------------------------------------------------------
+struct Nccl {
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} nccl;
+
+int nccl_load() {
+    if (G.nccl_lib) return HYPO_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(HYPO_E_CUDA, "option gather=2 needs libnccl.so.2: %s", dlerror());
+    *(void**)&nccl.CommInitAll = dlsym(h, "ncclCommInitAll");
+    *(void**)&nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void**)&nccl.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void**)&nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+    *(void**)&nccl.Send = dlsym(h, "ncclSend");
+    *(void**)&nccl.Recv = dlsym(h, "ncclRecv");
+    *(void**)&nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+    if (!nccl.CommInitAll || !nccl.GroupStart || !nccl.GroupEnd || !nccl.Send || !nccl.Recv)
+        return fail(HYPO_E_CUDA, "libnccl.so.2 lacks the point-to-point entry points");
+    G.nccl_lib = h;
+    return HYPO_OK;
+}
+
+#define NCCL_TRY(x)                                                                                     \
+    do {                                                                                                \
+        int r_ = (x);                                                                                   \
+        if (r_ != 0)                                                                                    \
+            return fail(HYPO_E_CUDA, "%s failed: %s", #x, nccl.GetErrorString ? nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+int nccl_comms() {
+    if (G.comms_ready) return HYPO_OK;
+    if (int rc = nccl_load()) return rc;
+    int devs[HYPO_MAX_DEVICES];
+    for (int i = 0; i < G.n_dev; ++i) devs[i] = G.dev[i]->device;
+    NCCL_TRY(nccl.CommInitAll(G.comms, G.n_dev, devs));
+    G.comms_ready = true;
+    return HYPO_OK;
+}
+
+// The final consensus gather of SURVEY.md §8e over NVLink: every device sends its compacted bytes to
+// device 0 (grouped ncclSend / ncclRecv, single process), which then makes the one copy to the host.
+int gather_nccl(std::vector<Shard>& sh, const std::vector<uint64_t>& base, uint64_t total, char* out) {
+    if (int rc = nccl_comms()) return rc;
+    Ctx& g0 = *G.dev[0];
+    CUDA_TRY(cudaSetDevice(g0.device));
+    CUDA_TRY(g0.gather.reserve(total + 16));
+    if (sh[0].total)
+        CUDA_TRY(cudaMemcpyAsync(g0.gather.p, g0.out_compact.p, sh[0].total, cudaMemcpyDeviceToDevice, g0.stream));
+    NCCL_TRY(nccl.GroupStart());
+    for (int i = 1; i < G.n_dev; ++i) {
+        if (!sh[i].total) continue;
+        NCCL_TRY(nccl.Send(G.dev[i]->out_compact.p, sh[i].total, /*ncclChar*/ 0, 0, G.comms[i], G.dev[i]->stream));
+        NCCL_TRY(nccl.Recv((char*)g0.gather.p + base[i], sh[i].total, 0, i, G.comms[0], g0.stream));
+    }
+    NCCL_TRY(nccl.GroupEnd());
+    CUDA_TRY(cudaSetDevice(g0.device));
+    if (total) CUDA_TRY(cudaMemcpyAsync(out, g0.gather.p, total, cudaMemcpyDeviceToHost, g0.stream));
+    return HYPO_OK;
+}
+
+void release_ctx(Ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* bufs[] = {&c->win, &c->arms, &c->packed, &c->out_scratch, &c->out_pos, &c->out_len, &c->out_off,
+                      &c->out_compact, &c->stats, &c->lists, &c->ctrl, &c->H, &c->gws, &c->paths, &c->cub_tmp, &c->gather};
+    for (DevBuf* b : bufs) b->release();
+    if (c->pinned_ctrl) cudaFreeHost(c->pinned_ctrl);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_head) cudaEventDestroy(c->ev_head);
+    if (c->ev_tail) cudaEventDestroy(c->ev_tail);
+    for (int p = 0; p < kPasses; ++p)
+        for (int t = 0; t < kNumTiers; ++t) {
+            if (c->tev0[p][t]) cudaEventDestroy(c->tev0[p][t]);
+            if (c->tev1[p][t]) cudaEventDestroy(c->tev1[p][t]);
+        }
+    delete c;
+}
+
+void shutdown_locked() {
+    if (G.comms_ready && nccl.CommDestroy)
+        for (int i = 0; i < G.n_dev; ++i) if (G.comms[i]) nccl.CommDestroy(G.comms[i]);
+    G.comms_ready = false;
+    memset(G.comms, 0, sizeof(G.comms));
+    for (int i = 0; i < HYPO_MAX_DEVICES; ++i) { release_ctx(G.dev[i]); G.dev[i] = nullptr; }
+    G.n_dev = 0;
+    G.init = false;
+}
+
+int create_ctx(int device, Ctx** out) {
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(HYPO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    Ctx* c = new Ctx;
+    *out = c;   // in the table from here on: a failure below is cleaned up by shutdown_locked
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+    CUDA_TRY(cudaHostAlloc(&c->pinned_ctrl, 4096, cudaHostAllocDefault));
+    static_assert(sizeof(DevCtrl) <= 3072, "control block layout");
+    memset(c->pinned_ctrl, 0, 4096);
+    for (int p = 0; p < kPasses; ++p)
+        for (int t = 0; t < kNumTiers; ++t) {
+            CUDA_TRY(cudaEventCreate(&c->tev0[p][t]));
+            CUDA_TRY(cudaEventCreate(&c->tev1[p][t]));
+        }
+    return HYPO_OK;
+}
+
+int init_devices(const int8_t scores[6], const int* devices, int n) {
+    g_err.clear();
+    if (!scores) return fail(HYPO_E_ARG, "scores == NULL");
+    if (int rc = check_scores(scores)) return rc;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(HYPO_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (n < 1 || n > HYPO_MAX_DEVICES) return fail(HYPO_E_ARG, "device count %d out of range (1..%d)", n, HYPO_MAX_DEVICES);
+    for (int i = 0; i < n; ++i)
+        if (devices[i] < 0 || devices[i] >= n_dev)
+            return fail(HYPO_E_ARG, "device %d out of range (0..%d)", devices[i], n_dev - 1);
+    for (int t = 0; t < kNumFixedTiers; ++t) {   // the table must agree with the kernels' constants
+        const Caps c = fixed_caps(t);
+        const Tier& T = kTiers[t];
+        if (c.ncap != T.ncap || c.ecap != T.ecap || c.acap != T.acap || c.scap != T.scap || c.lcap != T.lcap ||
+            T.from_bounds || !T.smem_graph)
+            return fail(HYPO_E_ARG, "internal: tier table row %d disagrees with fixed_caps", t);
+    }
+    // same devices as before: keep the contexts (buffers, streams), only the scores change; otherwise
+    // everything that belonged to the old devices is released with them
+    bool same = G.init && G.n_dev == n;
+    for (int i = 0; same && i < n; ++i) same = G.dev[i]->device == devices[i];
+    if (!same) {
+        shutdown_locked();
+        for (int i = 0; i < n; ++i) {
+            const int rc = create_ctx(devices[i], &G.dev[i]);
+            G.n_dev = i + 1;
+            if (rc) { const std::string keep = g_err; shutdown_locked(); g_err = keep; return rc; }
+        }
+    }
+    memcpy(G.scores, scores, 6);
+    G.launches = 0;
+    G.init = true;
+    return HYPO_OK;
+}
+
+// Contiguous window ranges of equal estimated cost: reads x draft length^2 is what the DP of a window
+// costs to first order (cells = reads x nodes x length, nodes ~ length); contiguous ranges keep every
+// shard's arms and bytes contiguous in a batch laid out in window order.
+void cut_shards(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
+                uint64_t packed_bytes, int n, bool everything, std::vector<Shard>& sh) {
+    sh.assign(n, Shard());
+    std::vector<double> acc(n_win + 1);
+    acc[0] = 0.0;
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const double reads = (double)win[w].n_internal + win[w].n_pre + win[w].n_suf;
+        const double len = (double)win[w].draft_len + 2.0;
+        acc[w + 1] = acc[w] + reads * len * len + 64.0;
+    }
+    uint64_t w = 0;
+    for (int i = 0; i < n; ++i) {
+        sh[i].w0 = w;
+        const double target = acc[n_win] * (double)(i + 1) / (double)n;
+        if (i + 1 == n) w = n_win;
+        else w = std::max<uint64_t>(w, std::lower_bound(acc.begin(), acc.end(), target) - acc.begin());
+        if (w > n_win) w = n_win;
+        sh[i].w1 = w;
+    }
+    // arm / byte ranges; a batch that is not laid out in window order gets everything everywhere
+    bool ordered = !everything;
+    for (int i = 0; i < n && ordered; ++i) {
+        Shard& s = sh[i];
+        if (s.w0 == s.w1) { s.a0 = s.a1 = 0; s.b0 = s.b1 = 0; continue; }
+        s.a0 = win[s.w0].first_arm;
+        s.a1 = s.w1 < n_win ? win[s.w1].first_arm : n_arms;
+        ordered = s.a0 <= s.a1 && s.a1 <= n_arms;
+        if (!ordered) break;
+        s.b0 = win[s.w0].draft_off;
+        if (s.a0 < s.a1 && arms[s.a0].len) s.b0 = std::min<uint64_t>(s.b0, arms[s.a0].off);
+        if (s.w1 < n_win) {
+            s.b1 = win[s.w1].draft_off;
+            if (s.a1 < n_arms && arms[s.a1].len) s.b1 = std::min<uint64_t>(s.b1, arms[s.a1].off);
+        } else {
+            s.b1 = packed_bytes;
+        }
+        ordered = s.b0 <= s.b1 && s.b1 <= packed_bytes;
+    }
+    if (!ordered)
+        for (Shard& s : sh) { s.a0 = 0; s.a1 = n_arms; s.b0 = 0; s.b1 = packed_bytes; }
 }
 
 }  // namespace
@@ -464,55 +959,69 @@ int hypo_gpu_abi_version(void) { return HYPO_B200_ABI_VERSION; }
 
 const char* hypo_gpu_last_error(void) { return g_err.c_str(); }
 
-uint64_t hypo_gpu_launch_count(void) { return g.launches; }
+uint64_t hypo_gpu_launch_count(void) { return G.launches.load(); }
+
+int hypo_gpu_device_count(void) { return G.init ? G.n_dev : 0; }
 
 int hypo_gpu_init(const int8_t scores[6], int device) {
     std::lock_guard<std::mutex> lk(g_mu);
+    return init_devices(scores, &device, 1);
+}
+
+int hypo_gpu_init_multi(const int8_t scores[6], int n_gpus) {
+    std::lock_guard<std::mutex> lk(g_mu);
     g_err.clear();
-    if (!scores) return fail(HYPO_E_ARG, "scores == NULL");
-    if (int rc = check_scores(scores)) return rc;
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
         return fail(HYPO_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0 || device >= n_dev) return fail(HYPO_E_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
-    CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(HYPO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
-                    prop.major, prop.minor);
-    if (!g.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    if (!g.copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-    if (!g.ev_head) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_head, cudaEventDisableTiming));
-    if (!g.ev_tail) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_tail, cudaEventDisableTiming));
-    if (!g.pinned_ctrl) CUDA_TRY(cudaHostAlloc(&g.pinned_ctrl, 4096, cudaHostAllocDefault));
-    if (!g.ev0) CUDA_TRY(cudaEventCreate(&g.ev0));
-    if (!g.ev1) CUDA_TRY(cudaEventCreate(&g.ev1));
-    g.device = device;
-    g.sms = prop.multiProcessorCount;
-    g.smem_optin = (int)prop.sharedMemPerBlockOptin;
-    for (int t = 0; t < kNumFixedTiers; ++t) {   // the table must agree with the kernels' constants
-        const Caps c = fixed_caps(t);
-        const Tier& T = kTiers[t];
-        if (c.ncap != T.ncap || c.ecap != T.ecap || c.acap != T.acap || c.scap != T.scap || c.lcap != T.lcap ||
-            T.from_bounds || !T.smem_graph)
-            return fail(HYPO_E_ARG, "internal: tier table row %d disagrees with fixed_caps", t);
+    if (n_gpus <= 0) n_gpus = std::min(n_dev, HYPO_MAX_DEVICES);   // all visible devices
+    if (n_gpus > n_dev || n_gpus > HYPO_MAX_DEVICES)
+        return fail(HYPO_E_ARG, "%d GPUs requested, %d visible (at most %d are driven)", n_gpus, n_dev, HYPO_MAX_DEVICES);
+    int devs[HYPO_MAX_DEVICES];
+    for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+    return init_devices(scores, devs, n_gpus);
+}
+
+int hypo_gpu_set_option(const char* name, int64_t value) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err.clear();
+    if (!name) return fail(HYPO_E_ARG, "option name == NULL");
+    if (!strcmp(name, "first_tier")) {
+        if (value < 0 || value >= kNumTiers) return fail(HYPO_E_ARG, "first_tier must be 0..%d", kNumTiers - 1);
+        G.opt.first_tier = (int)value;
+    } else if (!strcmp(name, "scap")) {
+        if (value < 0 || value > 65534) return fail(HYPO_E_ARG, "scap must be 0..65534");
+        G.opt.scap = (int)value;
+    } else if (!strcmp(name, "gather")) {
+        if (value != 0 && value != 2) return fail(HYPO_E_ARG, "gather must be 0 (direct) or 2 (NCCL to device 0)");
+        G.opt.gather = (int)value;
+    } else {
+        return fail(HYPO_E_ARG, "unknown option '%s'", name);
     }
-    memcpy(g.scores, scores, 6);
-    g.launches = 0;
-    g.init = true;
+    return HYPO_OK;
+}
+
+int hypo_gpu_window_bounds(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
+                           uint64_t* bound) {
+    g_err.clear();
+    if ((!win && n_win) || !bound) return fail(HYPO_E_ARG, "NULL buffer");
+    for (uint64_t w = 0; w < n_win; ++w) {
+        const uint64_t n = (uint64_t)win[w].n_internal + win[w].n_pre + win[w].n_suf;
+        uint64_t sum = 0;
+        for (uint64_t k = 0; k < n && win[w].first_arm + k < n_arms; ++k) sum += arms[win[w].first_arm + k].len;
+        bound[w] = win[w].wtype == HYPO_WINDOW_LONG ? 2 * sum + win[w].draft_len + 2 : sum + 2 * n + win[w].draft_len + 2;
+    }
     return HYPO_OK;
 }
 
 uint64_t hypo_gpu_out_bound(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms) {
     uint64_t total = 0;
     for (uint64_t w = 0; w < n_win; ++w) {
-        uint64_t b = (uint64_t)win[w].draft_len + 2;
-        const uint64_t n = (uint64_t)win[w].n_internal + win[w].n_pre + win[w].n_suf;
-        for (uint64_t k = 0; k < n && win[w].first_arm + k < n_arms; ++k) b += (uint64_t)arms[win[w].first_arm + k].len + 2;
-        total += std::max<uint64_t>(b, win[w].draft_len);
+        uint64_t b = 0;
+        hypo_gpu_window_bounds(win + w, 1, arms, n_arms, &b);
+        total += b;
     }
     return total;
 }
@@ -522,180 +1031,82 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
                                     char* d_out, const uint64_t* d_out_pos, uint32_t* d_out_len, void* stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_err.clear();
-    if (!g.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    Ctx& g = *G.dev[0];
     CUDA_TRY(cudaSetDevice(g.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
     if (n_win == 0) return HYPO_OK;
     CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
     CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
-    if (int rc = prepare_stats((const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, n_arms, packed_bytes,
-                               (WinStat*)g.stats.p, (uint64_t*)g.out_off.p, s))
+    if (int rc = stage_classify(g, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, 0, n_arms, 0, packed_bytes,
+                                (WinStat*)g.stats.p, (uint64_t*)g.out_off.p, s))
         return rc;
-    return run_device((const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, n_arms, d_packed, packed_bytes, d_out,
-                      d_out_pos, d_out_len, (const WinStat*)g.stats.p, s);
+    CUDA_TRY(fetch_ctrl(g, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (int rc = check_bad(g, false)) return rc;
+    return stage_tiers(g, 0, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, d_packed, d_out, d_out_pos,
+                       d_out_len, (const WinStat*)g.stats.p, s);
 }
 
-// Host-buffer entry point.  The input is copied in two parts on a second stream: a head of the windows
-// (with the arms and packed bytes they reference) and the tail; the POA kernels of the head run while the
-// tail is still crossing PCIe, which hides most of the H2D time behind compute.  This relies on the
-// batch being laid out in window order (what hypo::WindowBatch and every sane packer produce); the head's
-// descriptors are validated on the device against the head's limits, and an input that is not laid out
-// that way silently takes the single-copy path instead.
 int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
                              const uint8_t* packed, uint64_t packed_bytes, char* out, uint64_t out_cap,
                              uint64_t* out_off) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_err.clear();
-    if (!g.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     if (!out_off) return fail(HYPO_E_ARG, "out_off == NULL");
     if (n_win == 0) { out_off[0] = 0; return HYPO_OK; }
     if (!win || (!arms && n_arms) || (!packed && packed_bytes)) return fail(HYPO_E_ARG, "NULL input buffer");
-    CUDA_TRY(cudaSetDevice(g.device));
-    cudaStream_t s = g.stream;
+    const WinDesc* hw = (const WinDesc*)win;
+    const ArmDesc* ha = (const ArmDesc*)arms;
 
-    CUDA_TRY(g.win.reserve(sizeof(WinDesc) * n_win));
-    CUDA_TRY(g.arms.reserve(sizeof(ArmDesc) * std::max<uint64_t>(n_arms, 1)));
-    CUDA_TRY(g.packed.reserve(packed_bytes + 16));
-    CUDA_TRY(g.out_pos.reserve(sizeof(uint64_t) * (n_win + 1)));
-    CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 1)));
-    CUDA_TRY(g.out_len.reserve(sizeof(uint32_t) * n_win));
-    CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
-    const WinDesc* d_win = (const WinDesc*)g.win.p;
-    const ArmDesc* d_arms = (const ArmDesc*)g.arms.p;
-    const uint8_t* d_packed = (const uint8_t*)g.packed.p;
-    uint64_t* d_bound = (uint64_t*)g.out_off.p;   // reused as the compact offsets later
-    uint64_t* d_pos = (uint64_t*)g.out_pos.p;
-    WinStat* d_stats = (WinStat*)g.stats.p;
-    uint64_t* h64 = (uint64_t*)((char*)g.pinned_ctrl + 3072);
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_bound, d_pos, n_win + 1, s));
-    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
-    tmp_bytes = g.cub_tmp.cap;
-
-    // ---- split: head = first ~1/8 of the windows -------------------------------------------------
-    uint64_t w_s = 0, a_s = 0, b_s = 0;
-    bool piped = n_win >= 65536 && n_arms > 0 && packed_bytes > 0;
-    if (piped) {
-        w_s = std::max<uint64_t>(32768, n_win / 8);
-        a_s = win[w_s].first_arm;
-        piped = a_s <= n_arms;
-        if (piped) {
-            b_s = std::min<uint64_t>(win[w_s].draft_off, a_s < n_arms ? arms[a_s].off : packed_bytes);
-            piped = b_s <= packed_bytes;
-        }
-    }
-    // an upper bound of the windows' scratch need that does not require looking at the arms: a window
-    // may write up to 2 * sum(len + 2) + 2 * draft_len + 4 bytes (classify_kernel; the factor 2 is the
-    // LONG round-2 backbone), and every base occupies at least 2 bits of the slab
-    const uint64_t scratch_cap = 8 * packed_bytes + 4 * n_arms + 8 * n_win + 64;
-
-    // the caller's host buffers must not be touched after this function returns, on any path
-    struct CopyGuard {
-        cudaStream_t c;
-        bool armed = false;
-        ~CopyGuard() { if (armed) cudaStreamSynchronize(c); }
-    } guard{g.copy_stream};
-    bool copies_issued = false;
-    if (piped) {
-        guard.armed = true;
-        CUDA_TRY(g.out_scratch.reserve(scratch_cap + 16));
-        cudaStream_t c = g.copy_stream;
-        copies_issued = true;
-        CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * w_s, cudaMemcpyHostToDevice, c));
-        if (a_s) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * a_s, cudaMemcpyHostToDevice, c));
-        if (b_s) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, b_s, cudaMemcpyHostToDevice, c));
-        CUDA_TRY(cudaEventRecord(g.ev_head, c));
-        CUDA_TRY(cudaMemcpyAsync((WinDesc*)g.win.p + w_s, win + w_s, sizeof(WinDesc) * (n_win - w_s), cudaMemcpyHostToDevice, c));
-        if (n_arms > a_s)
-            CUDA_TRY(cudaMemcpyAsync((ArmDesc*)g.arms.p + a_s, arms + a_s, sizeof(ArmDesc) * (n_arms - a_s), cudaMemcpyHostToDevice, c));
-        if (packed_bytes > b_s)
-            CUDA_TRY(cudaMemcpyAsync((uint8_t*)g.packed.p + b_s, packed + b_s, packed_bytes - b_s, cudaMemcpyHostToDevice, c));
-        CUDA_TRY(cudaEventRecord(g.ev_tail, c));
-
-        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_head, 0));
-        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
-        // head descriptors must only reference what has arrived: limits a_s / b_s
-        const int rc_head = prepare_stats(d_win, w_s, d_arms, a_s, b_s, d_stats, d_bound, s, /*quiet=*/true);
-        if (rc_head == HYPO_E_ARG) {
-            piped = false;   // not laid out in window order (or really invalid): single-copy path decides
-            CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
-        } else if (rc_head != HYPO_OK) {
-            return rc_head;
-        }
-    }
-
-    if (piped) {
-        // ---- head: positions, kernels (the tail is still being copied) ----------------------------
-        CUDA_TRY(cudaMemsetAsync(d_bound + w_s, 0, sizeof(uint64_t), s));
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, w_s + 1, s));
-        ++g.launches;
-        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + w_s, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        const uint64_t head_bytes = *h64;
-        if (head_bytes > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
-        if (int rc = run_device(d_win, w_s, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p, d_pos,
-                                (uint32_t*)g.out_len.p, d_stats, s))
-            return rc;
-        // ---- tail -----------------------------------------------------------------------------------
-        CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
-        const uint64_t n_tail = n_win - w_s;
-        if (int rc = prepare_stats(d_win + w_s, n_tail, d_arms, n_arms, packed_bytes, d_stats + w_s, d_bound + w_s, s))
-            return rc;
-        CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
-        CUDA_TRY(cub::DeviceScan::ExclusiveScan(g.cub_tmp.p, tmp_bytes, d_bound + w_s, d_pos + w_s, cuda::std::plus<>{},
-                                                (uint64_t)head_bytes, n_tail + 1, s));
-        ++g.launches;
-        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (*h64 > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
-        if (int rc = run_device(d_win + w_s, n_tail, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p,
-                                d_pos + w_s, (uint32_t*)g.out_len.p + w_s, d_stats + w_s, s, /*accumulate=*/true))
-            return rc;
+    const int n = G.n_dev;
+    std::vector<Shard> sh;
+    if (n == 1) {
+        sh.assign(1, Shard());
+        sh[0].w0 = 0; sh[0].w1 = n_win; sh[0].a0 = 0; sh[0].a1 = n_arms; sh[0].b0 = 0; sh[0].b1 = packed_bytes;
+        if (int rc = shard_compute(*G.dev[0], hw, ha, packed, sh[0])) return rc;
     } else {
-        // ---- single copy --------------------------------------------------------------------------
-        if (copies_issued) {
-            // the split was attempted and abandoned: everything is on its way on the copy stream
-            CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(g.win.p, win, sizeof(WinDesc) * n_win, cudaMemcpyHostToDevice, s));
-            if (n_arms) CUDA_TRY(cudaMemcpyAsync(g.arms.p, arms, sizeof(ArmDesc) * n_arms, cudaMemcpyHostToDevice, s));
-            if (packed_bytes) CUDA_TRY(cudaMemcpyAsync(g.packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, s));
+        // one host thread per device; each runs the single-device pipeline on its range.  A batch whose
+        // ranges turn out not to be self-contained (not laid out in window order) is re-run with every
+        // device holding the whole arm table and slab.
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            cut_shards(win, n_win, arms, n_arms, packed_bytes, n, attempt == 1, sh);
+            const bool partial = sh[0].a1 - sh[0].a0 != n_arms || sh[0].b1 - sh[0].b0 != packed_bytes;
+            std::vector<std::thread> th;
+            for (int i = 0; i < n; ++i)
+                th.emplace_back([&, i]() {
+                    g_err.clear();
+                    sh[i].rc = shard_compute(*G.dev[i], hw, ha, packed, sh[i]);
+                    G.dev[i]->err = g_err;   // (the message is thread-local to this worker)
+                });
+            for (auto& t : th) t.join();
+            int rc = HYPO_OK;
+            for (int i = 0; i < n && !rc; ++i)
+                if (sh[i].rc) { g_err = G.dev[i]->err; rc = sh[i].rc; }
+            if (rc == HYPO_E_ARG && partial && attempt == 0) continue;
+            if (rc) return rc;
+            break;
         }
-        CUDA_TRY(cudaMemsetAsync((char*)g.out_off.p + sizeof(uint64_t) * n_win, 0, sizeof(uint64_t), s));
-        if (int rc = prepare_stats(d_win, n_win, d_arms, n_arms, packed_bytes, d_stats, d_bound, s)) return rc;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, n_win + 1, s));
-        ++g.launches;
-        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        CUDA_TRY(g.out_scratch.reserve(*h64 + 16));
-        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
-        if (int rc = run_device(d_win, n_win, d_arms, n_arms, d_packed, packed_bytes, (char*)g.out_scratch.p, d_pos,
-                                (uint32_t*)g.out_len.p, d_stats, s))
-            return rc;
     }
-
-    // compact on the device: lengths -> offsets -> gather; then one D2H of the exact bytes
-    uint64_t* d_len64 = d_bound;
-    const int tb = 256;
-    widen_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, s>>>((const uint32_t*)g.out_len.p, d_len64, n_win);
-    CUDA_TRY(cudaMemsetAsync(d_len64 + n_win, 0, sizeof(uint64_t), s));
-    CUDA_TRY(g.lists.reserve(sizeof(uint64_t) * (n_win + 1)));
-    uint64_t* d_off = (uint64_t*)g.lists.p;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
-    CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    const uint64_t total = *h64;
+    std::vector<uint64_t> base(n + 1, 0);
+    for (int i = 0; i < n; ++i) base[i + 1] = base[i] + sh[i].total;
+    const uint64_t total = base[n];
     if (total > out_cap) return fail(HYPO_E_OUT_CAP, "output needs %llu bytes, out_cap is %llu", (unsigned long long)total,
                                      (unsigned long long)out_cap);
-    CUDA_TRY(g.out_compact.reserve(total + 16));
-    gather_kernel<<<(unsigned)((n_win * 32 + tb - 1) / tb), tb, 0, s>>>((const char*)g.out_scratch.p, (const uint64_t*)g.out_pos.p,
-                                                                      (const uint32_t*)g.out_len.p, d_off,
-                                                                      (char*)g.out_compact.p, n_win);
-    g.launches += 3;
-    CUDA_TRY(cudaGetLastError());
-    if (total) CUDA_TRY(cudaMemcpyAsync(out, g.out_compact.p, total, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_off, d_off, sizeof(uint64_t) * (n_win + 1), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    // gather in window order: shard i's bytes start at base[i]
+    const bool via_dev0 = n > 1 && G.opt.gather == 2;
+    if (via_dev0)
+        if (int rc = gather_nccl(sh, base, total, out)) return rc;
+    for (int i = 0; i < n; ++i)
+        if (int rc = shard_fetch(*G.dev[i], sh[i], out, base[i], out_off, !via_dev0)) return rc;
+    for (int i = 0; i < n; ++i)
+        if (int rc = shard_wait(*G.dev[i])) return rc;
+    for (int i = 1; i < n; ++i) {
+        const uint64_t b = base[i];
+        for (uint64_t w = sh[i].w0; w < sh[i].w1; ++w) out_off[w] += b;
+    }
+    out_off[n_win] = total;
     return HYPO_OK;
 }
 
@@ -704,7 +1115,8 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
                             uint64_t* total, void* stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_err.clear();
-    if (!g.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    Ctx& g = *G.dev[0];
     CUDA_TRY(cudaSetDevice(g.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
     if (n_win == 0) { if (total) *total = 0; return HYPO_OK; }
@@ -717,50 +1129,45 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len64, d_off, n_win + 1, s));
     CUDA_TRY(g.cub_tmp.reserve(tmp_bytes));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
-    uint64_t* h64 = (uint64_t*)((char*)g.pinned_ctrl + 3072);
+    uint64_t* h64 = host_words(g);
     CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (total) *total = *h64;
     if (*h64 > compact_cap) return fail(HYPO_E_OUT_CAP, "compact output needs %llu bytes, capacity is %llu",
                                         (unsigned long long)*h64, (unsigned long long)compact_cap);
     gather_kernel<<<(unsigned)((n_win * 32 + tb - 1) / tb), tb, 0, s>>>(d_scratch, d_out_pos, d_out_len, d_off, d_compact, n_win);
-    g.launches += 3;
+    G.launches += 3;
     CUDA_TRY(cudaGetLastError());
     return HYPO_OK;
 }
 
 int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[8]) {
-    if (poa_kernel_ms) *poa_kernel_ms = g.poa_ms;
-    if (poa_launches) *poa_launches = g.poa_launches;
-    if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = g.tier_windows[t];
+    float ms = 0.f;
+    uint32_t n = 0, tw[8] = {0};
+    for (int i = 0; i < G.n_dev; ++i) {
+        const Ctx& g = *G.dev[i];
+        ms = std::max(ms, g.poa_ms);   // the devices run side by side
+        n += g.poa_launches;
+        for (int t = 0; t < 8; ++t) tw[t] += g.tier_windows[t];
+    }
+    if (poa_kernel_ms) *poa_kernel_ms = ms;
+    if (poa_launches) *poa_launches = n;
+    if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = tw[t];
     return HYPO_OK;
 }
 
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]) {
-    if (reasons) for (int k = 0; k < kNumFailReasons; ++k) reasons[k] = g.fail_hist[k];
+    if (!reasons) return HYPO_OK;
+    for (int k = 0; k < kNumFailReasons; ++k) {
+        reasons[k] = 0;
+        for (int i = 0; i < G.n_dev; ++i) reasons[k] += G.dev[i]->fail_hist[k];
+    }
     return HYPO_OK;
 }
 
 void hypo_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g.init && !g.stream) return;
-    cudaSetDevice(g.device);
-    DevBuf* bufs[] = {&g.win, &g.arms, &g.packed, &g.out_scratch, &g.out_pos, &g.out_len, &g.out_off, &g.out_compact,
-                      &g.stats, &g.lists, &g.ctrl, &g.H, &g.gws, &g.paths, &g.cub_tmp};
-    for (DevBuf* b : bufs) b->release();
-    if (g.pinned_ctrl) cudaFreeHost(g.pinned_ctrl);
-    g.pinned_ctrl = nullptr;
-    if (g.stream) cudaStreamDestroy(g.stream);
-    g.stream = nullptr;
-    if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
-    g.copy_stream = nullptr;
-    if (g.ev_head) cudaEventDestroy(g.ev_head);
-    if (g.ev_tail) cudaEventDestroy(g.ev_tail);
-    g.ev_head = g.ev_tail = nullptr;
-    if (g.ev0) cudaEventDestroy(g.ev0);
-    if (g.ev1) cudaEventDestroy(g.ev1);
-    g.ev0 = g.ev1 = nullptr;
-    g.init = false;
+    shutdown_locked();
 }
 
 }  // extern "C"

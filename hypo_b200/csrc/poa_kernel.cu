@@ -32,7 +32,6 @@ struct Graph {
     uint8_t* seq;         // current sequence, letter codes (= colseq + 1)
     uint16_t* cur;        // per sequence position: aligned node / resolved node
     uint8_t* mark;        // toposort scratch
-    uint16_t* lists;      // toposort scratch: per-lane emission lists
     uint16_t* anch;       // order_update scratch
     uint16_t* newa;
     int32_t* score;       // epilogue
@@ -105,7 +104,6 @@ __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout&
     g.seq = base + L.colseq + 1;
     g.cur = (uint16_t*)(base + L.cur);
     g.mark = base + L.mark;
-    g.lists = (uint16_t*)(base + L.lists);
     g.anch = (uint16_t*)(base + L.anch);
     g.newa = (uint16_t*)(base + L.newa);
     g.score = (int32_t*)(base + L.score);
@@ -306,7 +304,8 @@ constexpr int kRowNearShift = 28;
 
 // End cell (reference :276-288,328-340): best last-column score over the candidate rows
 // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
-__device__ __forceinline__ EndCell end_cell(const Graph& g, const int16_t* __restrict__ H, int n, int cols,
+template <typename HT>
+__device__ __forceinline__ EndCell end_cell(const Graph& g, const HT* __restrict__ H, int n, int cols,
                                             int len, int type) {
     const int lane = lane_id();
     // per lane: best score, its lowest row, and how many candidate rows reach it
@@ -502,13 +501,69 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
 #endif
         __syncwarp();   // the boundary values of this tile are read by every lane in the next one
     }
-    return end_cell(g, H, n, (int)c.stride, len, type);
+    return end_cell<int16_t>(g, H, n, (int)c.stride, len, type);
 }
 // Emitted here (not at its first use) so that the hottest loop of the compact tier sits at the front
 // of the kernel's code: with 27 warps in different phases the placement of the row loop relative
 // to the other per-read phases decides how well the instruction caches hold (measured: 5 %).
 template __device__ EndCell dp_fill_row<true, 0, false>(const GState&, int16_t* __restrict__, int16_t* __restrict__, int,
                                                     int, int, int, Scores);
+
+// ------------------------------------------------------------------------------------------
+// 32-bit DP fill: the reference's H is int32 throughout (sisd_alignment_engine.cpp:263-342), so a
+// window whose scores x size leave the 16-bit range (|H^| > kMaxH16) is never refused: the last
+// tier fills such a read with plain 32-bit cells - one column per lane, 32 columns per step, the
+// horizontal pass as a warp prefix max with a carry between steps.  Same g-normalised values
+// (H^[i][j] = H[i][j] - j*g), same row-major layout (row stride `cols`), so end cell and traceback
+// are the code above instantiated for int32_t.  Built for exactness, not speed: it only ever runs
+// for windows no 16-bit tier can hold.
+// ------------------------------------------------------------------------------------------
+template <bool kSmem, int kTier>
+__device__ __noinline__ EndCell dp_fill_wide(const GState& st, int32_t* __restrict__ H, int cols, int len,
+                                             int type, Scores sc) {
+    const Graph g = make_graph<kSmem, kTier>(st);
+    const int lane = lane_id();
+    const int n = g.n_nodes;
+    const int mm = sc.m - sc.g, nn = sc.n - sc.g;
+    constexpr int kNeg32 = -(1 << 30);
+    const int used = ((len + 1 + 31) / 32) * 32;   // <= cols (a multiple of kTileCols)
+#pragma unroll 1
+    for (int j = lane; j < used; j += 32) H[j] = 0;   // row 0: H^[0][j] = 0
+    __syncwarp();
+#pragma unroll 1
+    for (int rk = 0; rk < n; ++rk) {
+        const uint32_t info = g.rowinfo[rk];
+        const int np = (info >> 16) & 0xff;
+        const int code = (info >> 24) & 7;
+        const uint16_t* pr = g.prows + (info & 0xffffu);
+        int32_t* Hi = H + (size_t)(rk + 1) * (size_t)cols;
+        int carry = kNeg32;
+#pragma unroll 1
+        for (int j0 = 0; j0 < used; j0 += 32) {
+            const int j = j0 + lane;
+            const int s = ((int)g.colseq[j] == code) ? mm : nn;
+            int x = kNeg32;
+            int k = 0;
+#pragma unroll 1
+            do {   // no predecessor: the virtual row 0 (reference :300-301)
+                const int32_t* Hp = H + (size_t)(np ? pr[k] : 0) * (size_t)cols;
+                x = max(x, Hp[j] + sc.g);
+                if (j >= 1) x = max(x, Hp[j - 1] + s);
+            } while (++k < np);
+            if (j == 0 && type == kROV) x = 0;   // reference :229-239
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(kFull, x, d);
+                if (lane >= d) x = max(x, y);
+            }
+            x = max(x, carry);
+            carry = __shfl_sync(kFull, x, 31);
+            Hi[j] = x;
+        }
+        __syncwarp();   // later rows read this one across lanes
+    }
+    return end_cell<int32_t>(g, H, n, cols, len, type);
+}
 
 // ------------------------------------------------------------------------------------------
 // Traceback (reference sisd_alignment_engine.cpp:344-437).
@@ -525,8 +580,8 @@ struct AlnSpan {
     int first, last;
 };
 
-template <bool kSmem, int kTier>
-__device__ __noinline__ AlnSpan traceback_dp(const GState& st, const int16_t* __restrict__ H, int cols,
+template <bool kSmem, int kTier, typename HT>
+__device__ __noinline__ AlnSpan traceback_dp(const GState& st, const HT* __restrict__ H, int cols,
                                           EndCell ec, int type, Scores sc, int max_steps) {
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
@@ -836,161 +891,14 @@ __device__ __noinline__ bool add_to_graph(GState& st, const Caps& caps_dyn, int 
 
 // ------------------------------------------------------------------------------------------
 // Topological sort (reference graph.cpp:293-353).  The rank order spoa's iterative DFS produces
-// decides every tie (end cell, heaviest bundle, branch completion), so it is reproduced exactly.
-//
-// The DFS's outer loop visits node ids in ascending order.  The warp processes 32 consecutive ids
-// per round: lane l replays, on its own, what the DFS would do when its outer loop reaches node
-// i0+l — assuming the lanes below it have already emitted — with a bounded recursion
-// (bulk_eval) that follows the reference's exploration order: aligned nodes last-to-first (only
-// their sources: their check_aligned flag is cleared), then the node's own not-yet-emitted
-// sources last-to-first, then the node followed by its aligned nodes.  Nodes a lane would emit
-// besides its own ("extras") are announced in a claim table; a lane may rely on extras announced
-// by LOWER lanes (second/third pass), any extra announced twice or any lane that cannot decide
-// within its bounds cuts the round there, and that one node is handled by the serial DFS
-// (dfs_from) — identical to the reference loop — before the next round starts behind it.
-// oracle/poa_oracle.c carries a sequential simulation of this scheme that is checked against
-// the plain DFS on every sort when POA_ORACLE_CHECK_BULK is set.
+// decides every tie (end cell, heaviest bundle, branch completion, MSA column ids), so where the
+// order matters it is reproduced exactly: the reference's DFS, verbatim, on one lane.  Exact sorts
+// are rare (order_update keeps a valid order between them), so the serial walk costs nothing on
+// SHORT workloads and 7-10 % on LONG windows.
 //
 // mark bits: 0-1 = node mark (0 unmarked, 1 temporary, 2 permanent), bit 2 = "do not check
 // aligned nodes" (check_aligned_nodes[id] == false).
 // ------------------------------------------------------------------------------------------
-constexpr int kBulkDepth = 4;
-constexpr int kBulkMaxNodes = kBulkList - 1;   // list[0] = count, then up to kBulkList-1 nodes
-
-struct SortCtx {
-    const uint8_t* mark;
-    const uint8_t* al_cnt;
-    uint16_t* claim;     // node -> (round << 5 | lane) of the lane that announced it this round
-    const uint16_t* in_head;
-    const uint16_t* e_next;
-    const uint16_t* e_src;
-    const uint16_t* al_blk;
-    const uint16_t* al_pool;
-    uint16_t* list;      // [0] = n, [1..n] = nodes in emission order
-    int i0, id, lane, round, als;
-    unsigned emit_mask;  // lanes whose replay succeeded in an earlier pass
-    bool use_claims;
-};
-
-// "emitted by the time it is needed": permanently marked, a lower lane of this round, announced by
-// a lower lane of this round (later passes), or already in this lane's own emission list.
-__device__ __forceinline__ bool s_ok(const SortCtx& c, int s) {
-    if ((c.mark[s] & 3) == 2) return true;
-    if (s >= c.i0 && s < c.id) return true;
-    const int cl = c.claim[s];
-    if (cl == ((c.round << 5) | c.lane)) return true;        // in this lane's own list
-    return c.use_claims && (cl >> 5) == c.round && (cl & 31) < c.lane && ((c.emit_mask >> (cl & 31)) & 1);
-}
-
-// Appends to the lane's emission list; extras are announced (and remembered) in the claim table.
-__device__ __forceinline__ bool s_push(const SortCtx& c, int x) {
-    const int n = c.list[0];
-    if (n >= kBulkMaxNodes) return false;
-    // Lanes run concurrently: another lane may have overwritten this lane's claim on x, after
-    // which s_ok no longer recognises x as already emitted here.  Never list a node twice.
-#pragma unroll 1
-    for (int k = 1; k <= n; ++k)
-        if (c.list[k] == x) return false;
-    c.list[n + 1] = (uint16_t)x;
-    c.list[0] = (uint16_t)(n + 1);
-    if (x != c.id) c.claim[x] = (uint16_t)((c.round << 5) | c.lane);
-    return true;
-}
-
-// unit(u): u fresh; its aligned nodes fresh with all sources emitted; at most one not-yet-emitted
-// source per level, forming a chain of <= kBulkDepth fresh nodes without aligned nodes.
-// Emits chain (deepest first), u, aligned(u).
-__device__ __forceinline__ bool s_unit(const SortCtx& c, int u) {
-    if (c.mark[u] != 0) return false;
-    const int mu = c.al_cnt[u];
-    const int ublk = c.al_blk[u];
-#pragma unroll 1
-    for (int k = 0; k < mu; ++k) {
-        const int b = c.al_pool[ublk * c.als + k];
-        if (c.mark[b] != 0 || s_ok(c, b)) return false;
-#pragma unroll 1
-        for (int e = c.in_head[b]; e != kNone; e = c.e_next[e])
-            if (!s_ok(c, c.e_src[e])) return false;
-    }
-    unsigned long long chain = 0ull;   // up to kBulkDepth 16-bit node ids
-    int nc = 0, w = u;
-#pragma unroll 1
-    for (;;) {
-        int next = -1;
-#pragma unroll 1
-        for (int e = c.in_head[w]; e != kNone; e = c.e_next[e]) {
-            const int s = c.e_src[e];
-            if (s_ok(c, s)) continue;
-            if (next != -1) return false;
-            next = s;
-        }
-        if (next == -1) break;
-        if (nc == kBulkDepth || c.mark[next] != 0 || c.al_cnt[next] > 0) return false;
-        chain |= (unsigned long long)next << (16 * nc);
-        ++nc;
-        w = next;
-    }
-#pragma unroll 1
-    for (int q = nc - 1; q >= 0; --q)
-        if (!s_push(c, (int)((chain >> (16 * q)) & 0xffffull))) return false;
-    if (!s_push(c, u)) return false;
-#pragma unroll 1
-    for (int k = 0; k < mu; ++k)
-        if (!s_push(c, c.al_pool[ublk * c.als + k])) return false;
-    return true;
-}
-
-// Replay of what the DFS does when its outer loop reaches node c.id.  Returns 1 (emit c.list) or
-// 2 (cannot decide within the bounds).  Same code shape as bulk_eval in oracle/poa_oracle.c.
-__device__ __forceinline__ int bulk_eval_inner(const SortCtx& c) {
-    const int id = c.id;
-    c.list[0] = 0;
-    if (c.mark[id] != 0) return 2;
-    const int nm = c.al_cnt[id];
-    const int blk = c.al_blk[id];
-    // targets: aligned nodes last-to-first (only their sources are explored), then the node itself
-#pragma unroll 1
-    for (int t = nm - 1; t >= -1; --t) {
-        const int x = t >= 0 ? (int)c.al_pool[blk * c.als + t] : id;
-        if (t >= 0 && (c.mark[x] != 0 || s_ok(c, x))) return 2;
-        unsigned long long und = 0ull;   // up to three 16-bit node ids
-        int n_und = 0;
-#pragma unroll 1
-        for (int e = c.in_head[x]; e != kNone; e = c.e_next[e]) {
-            const int s = c.e_src[e];
-            if (s_ok(c, s)) continue;
-            if (n_und == 3) return 2;
-            und |= (unsigned long long)s << (16 * n_und);
-            ++n_und;
-        }
-#pragma unroll 1
-        for (int q = n_und - 1; q >= 0; --q) {
-            const int u = (int)((und >> (16 * q)) & 0xffffull);
-            if (!s_ok(c, u) && !s_unit(c, u)) return 2;
-        }
-    }
-    if (!s_push(c, id)) return 2;
-#pragma unroll 1
-    for (int k = 0; k < nm; ++k)
-        if (!s_push(c, c.al_pool[blk * c.als + k])) return 2;
-    return 1;
-}
-
-__device__ __forceinline__ int bulk_eval(const SortCtx& c) {
-    const int r = bulk_eval_inner(c);
-    if (r == 2) {   // withdraw the announcements of the abandoned replay
-        const int n = c.list[0];
-        const int me = (c.round << 5) | c.lane;
-#pragma unroll 1
-        for (int k = 1; k <= n; ++k) {
-            const int x = c.list[k];
-            if (c.claim[x] == me) c.claim[x] = 0;
-        }
-        c.list[0] = 0;
-    }
-    return r;
-}
-
 // Serial DFS from one root (lane 0), verbatim the reference's inner loop.
 __device__ __forceinline__ bool dfs_from(const Graph& g, const Caps& caps, int root, int& nr) {
     int sp = 0;
@@ -1048,115 +956,19 @@ __device__ __noinline__ bool topo_sort(const GState& st, const Caps& caps_dyn) {
     const Graph g = make_graph<kSmem, kTier>(st);
     const int lane = lane_id();
     const int n = g.n_nodes;
-    uint16_t* claim = g.n2r;   // node -> (round << 5 | lane) of the lane that announced it
     __syncwarp();   // the sort's scratch aliases the row records other lanes may still be reading
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) { g.mark[i] = 0; claim[i] = 0; }
+    for (int i = lane; i < n; i += 32) g.mark[i] = 0;
     __syncwarp();
-    uint16_t* list = g.lists + lane * kBulkList;
-    int nr = 0, i0 = 0, round = 0;
-#ifndef HYPO_BULK_SORT
-    // DEFAULT: the reference's DFS, verbatim, on one lane.  The warp-parallel replay below (32 roots
-    // per round, unsynchronised claim table) is several times faster, but a randomised parity run
-    // found it to produce a different (still valid) order for about one LONG window in 10^6 - the
-    // outcome depends on how the lanes interleave - so it stays disabled until the claim protocol
-    // is made race-free.  Since the exact order is only derived where it can matter (end-cell ties,
-    // LONG windows, tied bundles), the serial sort costs nothing on the headline shape.
-    {
-        int ok = 1;
-        if (lane == 0) {
+    int ok = 1;
+    if (lane == 0) {
+        int nr = 0;
 #pragma unroll 1
-            for (int id = 0; id < n && ok; ++id)
-                if ((g.mark[id] & 3) != 2) ok = dfs_from(g, caps, id, nr) ? 1 : 0;
-        }
-        ok = __shfl_sync(kFull, ok, 0);
-        if (!ok) return give_up(st, kFailStack);
-        i0 = n;
-        __syncwarp();
+        for (int id = 0; id < n && ok; ++id)
+            if ((g.mark[id] & 3) != 2) ok = dfs_from(g, caps, id, nr) ? 1 : 0;
     }
-#endif
-#pragma unroll 1
-    while (i0 < n) {
-        if (++round == 2047) {   // claim encoding would wrap: start over with clean claims
-#pragma unroll 1
-            for (int i = lane; i < n; i += 32) claim[i] = 0;
-            round = 1;
-            __syncwarp();
-        }
-        const int id = i0 + lane;
-        // status: 0 nothing to emit, 1 emit list, 2 undecided/failed, 3 superseded
-        int status = (id < n && (g.mark[id] & 3) != 2) ? 2 : 0;
-        SortCtx c;
-        c.mark = g.mark; c.al_cnt = g.al_cnt; c.claim = claim; c.in_head = g.in_head; c.e_next = g.e_next;
-        c.e_src = g.e_src; c.al_blk = g.al_blk; c.al_pool = g.al_pool; c.als = g.als;
-        c.list = list; c.i0 = i0; c.id = id; c.lane = lane; c.round = round;
-        c.emit_mask = 0u;
-#pragma unroll 1
-        for (int pass = 0; pass < 5; ++pass) {
-            bool changed = false;
-            if (status == 2) {
-                c.use_claims = pass > 0;
-                if (bulk_eval(c) == 1) { status = 1; changed = true; }
-            }
-            __syncwarp();
-            c.emit_mask = __ballot_sync(kFull, status == 1);
-            if (!__any_sync(kFull, changed)) break;
-            if (!__any_sync(kFull, status == 2)) break;
-        }
-        // a node announced by a lower lane is emitted there, not by its own lane
-        if (status == 1) {
-            const int cl = claim[id];
-            if ((cl >> 5) == round && (cl & 31) < lane) status = 3;
-        }
-        // where does the round end?
-        int cut = 32;
-        if (status == 2) cut = lane;
-        if (status == 3 && list[0] > 1) cut = lane;          // it announced extras it will not emit
-        if (status == 1) {
-            const int cnt = list[0];
-#pragma unroll 1
-            for (int k = 1; k <= cnt; ++k) {
-                const int x = list[k];
-                if (x == id) continue;
-                const int cl = claim[x] & 31;
-                // announced by two lanes (or withdrawn under this lane's feet): this lane's replay
-                // can no longer be trusted (lanes run concurrently, its own list may even hold the
-                // node twice), so the round ends here; the lane holding the claim, if higher, is
-                // cut as well, if lower it emits the node legitimately.
-                if (cl != lane) cut = min(cut, lane);
-            }
-        }
-        cut = __reduce_min_sync(kFull, cut);
-        // commit the lanes below the cut, in lane order
-        const int cnt = (status == 1 && lane < cut) ? (int)list[0] : 0;
-        int off = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(kFull, off, d);
-            if (lane >= d) off += y;
-        }
-        const int total = __shfl_sync(kFull, off, 31);
-        off -= cnt;
-#pragma unroll 1
-        for (int k = 1; k <= cnt; ++k) {
-            const int x = list[k];
-            g.r2n[nr + off + k - 1] = (uint16_t)x;
-            g.mark[x] = 2;
-        }
-        nr += total;
-        __syncwarp();
-        if (cut < 32 && i0 + cut < n) {
-            int ok = 1;
-            if (lane == 0 && (g.mark[i0 + cut] & 3) != 2) ok = dfs_from(g, caps, i0 + cut, nr) ? 1 : 0;
-            ok = __shfl_sync(kFull, ok, 0);
-            nr = __shfl_sync(kFull, nr, 0);
-            if (!ok) return give_up(st, kFailStack);
-            i0 += cut + 1;
-            __syncwarp();
-        } else {
-            i0 += 32;
-        }
-    }
+    ok = __shfl_sync(kFull, ok, 0);
+    if (!ok) return give_up(st, kFailStack);
     __syncwarp();
 #pragma unroll 1
     for (int r = lane; r < n; r += 32) g.n2r[g.r2n[r]] = (uint16_t)r;
@@ -1432,6 +1244,15 @@ __device__ __noinline__ int heaviest_bundle(const GState& st, bool exact_order) 
     return len;
 }
 
+// The path scores of the heaviest bundle are sums of edge weights (2 per traversal): the reference
+// accumulates them in int64 (graph.cpp:610-634), this kernel in int32 - exact as long as
+// nodes x 2 x sequences stays below 2^31, which holds for every window a 16-bit node id and a 16-bit
+// edge weight admit except the absurd corner (> 32 K nodes AND > 16 K reads); that corner is refused.
+__device__ __forceinline__ bool bundle_fits(const GState& st, const WarpState* ws) {
+    if ((long long)ws->n_nodes * 2ll * (long long)ws->n_seq <= 0x7fffffffll) return true;
+    return give_up(st, kFailRange);
+}
+
 __device__ __forceinline__ char code_to_char(int c) {
     return "ACGTNJO"[c];
 }
@@ -1448,7 +1269,7 @@ struct SeqSrc {
     int type;
 };
 
-template <bool kSmem, bool kOneTile, int kTier>
+template <bool kSmem, bool kOneTile, int kTier, bool kWide>
 __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int16_t* H, const SeqSrc& s,
                                           Scores sc, uint16_t* path) {
     const Caps caps = tier_caps<kTier>(caps_dyn);
@@ -1510,25 +1331,43 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
         const int cols = tiles * kTileCols;
         // 16-bit range guard: |H^| <= S*(rows+cols) and <= 2*S*cols
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
-        if (S * (nodes_before + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16) return give_up(st, kFailRange);
-        // boundary arrays of the multi-tile fill live behind the matrix slot
-        const int bnd_len = caps.ncap + 4;
-        int16_t* bnd = H + (size_t)(caps.ncap + 4) * (size_t)(caps.tiles * kTileCols);
-        EndCell ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
-        if (ec.tie && !ws->exact) {
-            // the reference breaks this tie by rank in ITS order: derive it and redo the fill
-            if (!topo_sort<kSmem, kTier>(st, caps)) return false;
-            if (lane == 0) ws->exact = 1;
-            __syncwarp();
-            build_rows<kSmem, kTier>(st);
-            ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+        const bool narrow = !(S * (nodes_before + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16);
+        if (!kWide && !narrow) return give_up(st, kFailRange);
+        unsigned lines;   // 128-byte lines of the matrix this read leaves behind
+        if (!kWide || narrow) {
+            // boundary arrays of the multi-tile fill live behind the matrix slot
+            const int bnd_len = caps.ncap + 4;
+            int16_t* bnd = H + (size_t)(caps.ncap + 4) * (size_t)(caps.tiles * kTileCols);
+            EndCell ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+            if (ec.tie && !ws->exact) {
+                // the reference breaks this tie by rank in ITS order: derive it and redo the fill
+                if (!topo_sort<kSmem, kTier>(st, caps)) return false;
+                if (lane == 0) ws->exact = 1;
+                __syncwarp();
+                build_rows<kSmem, kTier>(st);
+                ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+            }
+            span = traceback_dp<kSmem, kTier, int16_t>(st, H, cols, ec, s.type, sc, nodes_before + len + 4);
+            lines = (unsigned)(nodes_before + 1) * (unsigned)cols / 64u;
+        } else {
+            // scores x size beyond int16: 32-bit cells, as the reference computes them (the slot of a
+            // kWide launch is sized for them)
+            int32_t* H32 = reinterpret_cast<int32_t*>(H);
+            EndCell ec = dp_fill_wide<kSmem, kTier>(st, H32, cols, len, s.type, sc);
+            if (ec.tie && !ws->exact) {
+                if (!topo_sort<kSmem, kTier>(st, caps)) return false;
+                if (lane == 0) ws->exact = 1;
+                __syncwarp();
+                build_rows<kSmem, kTier>(st);
+                ec = dp_fill_wide<kSmem, kTier>(st, H32, cols, len, s.type, sc);
+            }
+            span = traceback_dp<kSmem, kTier, int32_t>(st, H32, cols, ec, s.type, sc, nodes_before + len + 4);
+            lines = (unsigned)(nodes_before + 1) * (unsigned)cols / 32u;
         }
-        span = traceback_dp<kSmem, kTier>(st, H, cols, ec, s.type, sc, nodes_before + len + 4);
         // The matrix of this read is dead now.  Drop its lines from L2 instead of letting them be
         // written back: without this every DP row ends up in HBM (1 TB per million windows) just
         // to be overwritten by the next read.
         {
-            const unsigned lines = (unsigned)(nodes_before + 1) * (unsigned)cols / 64u;   // 128-byte lines
             char* hb = reinterpret_cast<char*>(H);
 #pragma unroll 1
             for (unsigned l = lane; l < lines; l += 32)
@@ -1552,7 +1391,7 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
 // ------------------------------------------------------------------------------------------
 // Window driver (reference src/Window.cpp:44-254)
 // ------------------------------------------------------------------------------------------
-template <bool kSmem, bool kOneTile, int kTier>
+template <bool kSmem, bool kOneTile, int kTier, bool kWide>
 __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                          const WinDesc& w, char* out) {
     const int lane = lane_id();
@@ -1568,7 +1407,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
         if constexpr (kProjects<kOneTile, kTier>) n_added += d.len > 0;
         else added |= d.len > 0;
         // the reads' packed bytes are needed one read at a time: pull them into L2 now
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + d.off));
+        if (d.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + d.off));
     }
     if constexpr (kProjects<kOneTile, kTier>) {
         n_added = __reduce_add_sync(kFull, n_added);
@@ -1589,31 +1428,32 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
         s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
         s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
 #pragma unroll 1
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
-        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
 #pragma unroll 1
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
-        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
 #pragma unroll 1
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
-        if (!add_sequence<kSmem, kOneTile, kTier>(g, caps, H, s, sc, nullptr)) return -2;
+        if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     // The heaviest bundle rarely depends on WHICH valid order the ranks are in; only then is spoa's
     // exact order derived first.
+    if (!bundle_fits(g, ws)) return -2;
     int nc = heaviest_bundle<kSmem, kTier>(g, ws->exact != 0);
     if (nc < 0) {
         if (!topo_sort<kSmem, kTier>(g, caps)) return -2;
@@ -1631,7 +1471,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
 
 // LONG windows: two rounds with the lr scores, all kNW, support counts and
 // curation (reference src/Window.cpp:156-254, graph.cpp:371-388,533-568).
-template <bool kSmem, bool kOneTile, int kTier>
+template <bool kSmem, bool kOneTile, int kTier, bool kWide>
 __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& caps, int16_t* H,
                                         const WinDesc& w, char* out, uint16_t* paths, uint64_t p_slot) {
     const int lane = lane_id();
@@ -1646,10 +1486,14 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
     // (UINT)std::floor(_num_internal * _cThresh), float _cThresh = 0.4 (reference :28,245)
     const uint32_t thres = (uint32_t)floorf(__fmul_rn((float)w.n_internal, 0.4f));
 
-    // path slot: [0, n_arms+2) 32-bit start offsets (as two u16 each), then node ids
+    // path slot: [0, n_added+2) 32-bit start offsets (as two u16 each) - one per sequence that is
+    // actually added (seq 0 + the non-empty arms) plus the end marker - then node ids.  (Zero-length
+    // arms are never added, reference src/Window.cpp:182, so they take no slot.)
+    const uint64_t phdr = 2ull * ((uint64_t)n_added + 2);
+    if (phdr > p_slot) { give_up(g, kFailPaths); return -2; }
     uint32_t* pstart = reinterpret_cast<uint32_t*>(paths);
-    uint16_t* pnodes = paths + 2 * (n_arms + 2);
-    const uint64_t pcap = p_slot - 2 * (n_arms + 2);
+    uint16_t* pnodes = paths + phdr;
+    const uint64_t pcap = p_slot - phdr;
 
     int n_cons = 0;
 #pragma unroll 1
@@ -1667,7 +1511,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return give_up(g, kFailPaths);
             if (lane == 0) pstart[ws->n_seq] = used;
-            const bool ok = add_sequence<kSmem, kOneTile, kTier>(g, caps, H, q, sc, pnodes + used);
+            const bool ok = add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, q, sc, pnodes + used);
             used += q.len;
             return ok;
         };
@@ -1693,6 +1537,7 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
             if (lane == 0) ws->exact = 1;
             __syncwarp();
         }
+        if (!bundle_fits(g, ws)) return -2;
         const int nc = heaviest_bundle<kSmem, kTier>(g, true);
         const Graph gv = make_graph<kSmem, kTier>(g);
         // MSA column ids (graph.cpp:371-388) -> reuse n2r (free after the bundle)
@@ -1748,7 +1593,8 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
 }
 
 // kMinBlocks = 3: the compact tier (27 warps / SM, <= 72 registers); 2: every other tier.
-template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks, int kTier>
+// kWide: reads whose scores x size leave the 16-bit DP range are filled with 32-bit cells (last tier).
+template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks, int kTier, bool kWide = false>
 __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
@@ -1770,13 +1616,14 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 
+    const uint32_t n_work = __ldg(P.n_work);   // complete: only earlier launches append to this tier's list
 #pragma unroll 1
     for (;;) {
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(P.queue, 1u);
         wi = __shfl_sync(kFull, wi, 0);
-        if (wi >= P.n_work) break;
-        const uint32_t widx = P.work ? P.work[wi] : wi;
+        if (wi >= n_work) break;
+        const uint32_t widx = P.work[wi];
         const WinDesc w = P.win[widx];
         char* out = P.out + P.out_pos[widx];
         const uint32_t n = w.n_internal + w.n_pre + w.n_suf;
@@ -1794,8 +1641,8 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
             give_up(g, kFailForwarded);
             res = -2;
         } else if (n >= 2) {
-            if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier>(g, P, caps, H, w, out);
-            else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier>(g, P, caps, H, w, out, paths, P.p_slot);
+            if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier, kWide>(g, P, caps, H, w, out);
+            else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier, kWide>(g, P, caps, H, w, out, paths, P.p_slot);
             else { give_up(g, kFailNoLong); res = -2; }
         } else {
             res = -1;
@@ -1811,8 +1658,8 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         }
         if (lane == 0) {
             if (res == -2) {
-                const uint32_t k = atomicAdd(P.overflow, 1u);
-                P.overflow[1 + k] = widx;
+                const uint32_t k = atomicAdd(P.next_count, 1u);
+                P.next_list[k] = widx;
                 if constexpr (kProjects<kOneTile, kTier>) {
                     // (run_short / run_long zero it when they start a window; non-zero = abandoned on projection)
                     const uint32_t proj = pass_on ? 0u : warp_state<kSmem, kTier>(g)->need;
@@ -1832,7 +1679,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------
 // Host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile, int blocks,
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream) {
     void (*k)(const Params) = nullptr;
     if (warps_per_block * 32 > 288) return cudaErrorInvalidConfiguration;
@@ -1846,7 +1693,7 @@ cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool one_tile
         case 5: k = poa_kernel<true, false, true, 2, 5>; break;    // T1
         default:                                                   // bound-driven tiers, DAG in global memory
             if (smem_graph) return cudaErrorInvalidConfiguration;
-            k = one_tile ? poa_kernel<false, true, false, 2, -1> : poa_kernel<false, false, true, 2, -1>;
+            k = wide ? poa_kernel<false, false, true, 2, -1, true> : poa_kernel<false, false, true, 2, -1, false>;
     }
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;

@@ -53,7 +53,6 @@ constexpr int kAlSlotsMax = 6;               // clique <= 7 letters (J O A C G T
 constexpr int kNumCodes = 7;                 // A C G T N J O
 constexpr int kCodeJ = 5, kCodeO = 6;
 constexpr int kMaxH16 = 29000;               // int16 safety bound for |H^|
-constexpr int kBulkList = 10;                // per-lane emission list of the bulk topological sort
 
 enum AlignType { kNW = 0, kLOV = 1, kROV = 2 };
 
@@ -90,13 +89,14 @@ struct Params {
     const WinDesc* win;
     const ArmDesc* arms;
     const uint8_t* packed;
-    const uint32_t* work;        // window ids to process in this launch (nullptr = identity)
-    uint32_t n_work;
+    const uint32_t* work;        // window ids to process in this launch (this tier's list)
+    const uint32_t* n_work;      // device: entries in `work` (routed windows + those earlier launches handed on)
     uint32_t* queue;             // [0] = next work index (atomic)
     char* out;                   // consensus bytes
     const uint64_t* out_pos;     // where window w writes
     uint32_t* out_len;           // consensus length of window w
-    uint32_t* overflow;          // [0] = count, [1..] = window ids that exceeded this tier
+    uint32_t* next_list;         // windows that exceed this tier are appended to the successor tier's list ...
+    uint32_t* next_count;        // ... whose (atomic) length this is; the tier lists never need the host in between
     uint32_t* fail_hist;         // [kNumFailReasons] why windows left a tier (diagnostics; may be null)
     uint32_t* need;              // per window: projected nodes | edges << 16 left by a tier that abandoned it
                                  // on projection (0 = none; may be null)
@@ -121,7 +121,7 @@ struct ArenaLayout {
     uint32_t in_deg;    // u8  in-degree (saturating; 255 => tier overflow)
     uint32_t in_head;   // u16 first in-edge (insertion order)
     uint32_t al_blk;    // u16 block of al_pool holding aligned_nodes_ids_
-    uint32_t n2r;       // u16 node -> rank (claim scratch while sorting)
+    uint32_t n2r;       // u16 node -> rank
     uint32_t r2n;       // u16 rank -> node
     // edges
     uint32_t e_src, e_w, e_next;   // u16 each
@@ -134,7 +134,6 @@ struct ArenaLayout {
     uint32_t fp;        // u16 [ncap+1] first predecessor row of each DP row (0 = virtual row 0)
     uint32_t fp4;       // u16 [ncap+1] fp applied four times (traceback jump pointers)
     uint32_t mark;      // u8  [ncap]   sort marks            (aliases rows)
-    uint32_t lists;     // u16 [32][kBulkList] bulk lists     (aliases rows)
     uint32_t stack;     // u16 [scap]   DFS stack             (aliases rows)
     uint32_t anch;      // u16 [lcap+1] order_update anchors  (aliases rows)
     uint32_t newa;      // u16 [lcap+1] order_update          (aliases rows)
@@ -182,7 +181,6 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     // topological-sort scratch over the (dead) rows
     k.o = rows0;
     L.mark = k.take(c.ncap);
-    L.lists = k.take(2u * 32 * kBulkList);
     L.stack = k.take(2u * c.scap);
     if (k.o > end) end = k.o;
     // order-update scratch

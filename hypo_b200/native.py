@@ -17,6 +17,10 @@ LIB_PATH = os.path.join(_HERE, "libhypo_b200.so")
 
 ABI_SYMBOLS = (
     "hypo_gpu_init",
+    "hypo_gpu_init_multi",
+    "hypo_gpu_device_count",
+    "hypo_gpu_set_option",
+    "hypo_gpu_window_bounds",
     "hypo_gpu_out_bound",
     "hypo_gpu_consensus_batch",
     "hypo_gpu_consensus_batch_device",
@@ -54,6 +58,13 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.hypo_gpu_init.restype = C.c_int
         L.hypo_gpu_init.argtypes = [C.POINTER(C.c_int8), C.c_int]
+        L.hypo_gpu_init_multi.restype = C.c_int
+        L.hypo_gpu_init_multi.argtypes = [C.POINTER(C.c_int8), C.c_int]
+        L.hypo_gpu_device_count.restype = C.c_int
+        L.hypo_gpu_set_option.restype = C.c_int
+        L.hypo_gpu_set_option.argtypes = [C.c_char_p, C.c_int64]
+        L.hypo_gpu_window_bounds.restype = C.c_int
+        L.hypo_gpu_window_bounds.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.hypo_gpu_out_bound.restype = C.c_uint64
         L.hypo_gpu_out_bound.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         L.hypo_gpu_consensus_batch.restype = C.c_int
@@ -86,6 +97,30 @@ def init(scores: Sequence[int] = (5, -4, -8, 3, -5, -4), device: int = 0) -> Non
     """Window::prepare_for_poa (reference src/Window.cpp:31-42): fix the score parameters."""
     sc = (C.c_int8 * 6)(*[int(x) for x in scores])
     _check(lib().hypo_gpu_init(sc, int(device)))
+
+
+def init_multi(scores: Sequence[int] = (5, -4, -8, 3, -5, -4), n_gpus: int = 0) -> None:
+    """One host process driving n_gpus devices (0 = all visible): batches are cut into contiguous
+    window ranges of equal estimated cost, one per device."""
+    sc = (C.c_int8 * 6)(*[int(x) for x in scores])
+    _check(lib().hypo_gpu_init_multi(sc, int(n_gpus)))
+
+
+def device_count() -> int:
+    return int(lib().hypo_gpu_device_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """Test / measurement knobs of the C ABI (first_tier, scap, gather)."""
+    _check(lib().hypo_gpu_set_option(name.encode(), int(value)))
+
+
+def window_bounds(batch: WindowBatch) -> np.ndarray:
+    """hypo_gpu_window_bounds: bytes every window's output slot must hold (host arithmetic)."""
+    b = np.zeros(batch.n_win, np.uint64)
+    _check(lib().hypo_gpu_window_bounds(batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data, batch.n_arms,
+                                        b.ctypes.data))
+    return b
 
 
 def shutdown() -> None:

@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define HYPO_B200_ABI_VERSION 1
+#define HYPO_B200_ABI_VERSION 2
+#define HYPO_MAX_DEVICES 16
 
 /* Window types — hypo::WindowType, reference include/Window.hpp:35-38 */
 #define HYPO_WINDOW_SHORT 0u
@@ -43,7 +44,12 @@ extern "C" {
 #define HYPO_E_OUT_CAP     4   /* output buffer too small (see hypo_gpu_out_bound)     */
 #define HYPO_E_SCORES      5   /* gap penalty > 0 (spoa rejects it too,
                                   reference external/spoa/src/alignment_engine.cpp:42-49) */
-#define HYPO_E_CAPACITY    6   /* a window exceeds every device capacity tier          */
+#define HYPO_E_CAPACITY    6   /* a window exceeds every device capacity tier: a graph of
+                                  more than 65534 nodes, a node with more than 254
+                                  in-edges, or more than 32000 reads in one window.
+                                  Scores x size never cause it: reads beyond the 16-bit DP
+                                  range are computed with 32-bit cells like the reference
+                                  (external/spoa/src/sisd_alignment_engine.cpp:263-342)  */
 
 /*
  * One weak-region window == one hypo::Window (reference include/Window.hpp:122-135).
@@ -88,16 +94,47 @@ typedef struct HypoArmDesc {
  * Replaces hypo::Window::prepare_for_poa(const ScoreParams&, num_threads)
  * (reference src/Window.cpp:31-42).  scores = {sr_match, sr_mismatch, sr_gap,
  * lr_match, lr_mismatch, lr_gap} == hypo::ScoreParams (reference
- * include/globalDefs.hpp:58-66).  device = CUDA ordinal to run on (one process
- * per GPU; multi-GPU sharding happens above this ABI).
- * May be called again to change scores/device.
+ * include/globalDefs.hpp:58-66).
+ *
+ * hypo_gpu_init       drives ONE device (CUDA ordinal `device`); this is what a
+ *                     one-process-per-GPU launcher (torchrun, MPI) calls.
+ * hypo_gpu_init_multi drives devices 0 .. n_gpus-1 from this ONE host process, as the
+ *                     reference is one process (src/Hypo.cpp:34-35, OpenMP):
+ *                     hypo_gpu_consensus_batch then cuts every batch into n_gpus
+ *                     contiguous window ranges of equal estimated cost, runs them side by
+ *                     side (one host thread per device) and returns the consensus strings
+ *                     in window order - byte-identical for every n_gpus.  n_gpus <= 0:
+ *                     all visible devices.
+ * Either may be called again: with the same devices only the scores change; with other
+ * devices everything held on the old ones (buffers, streams, events) is released first.
  */
 int hypo_gpu_init(const int8_t scores[6], int device);
+int hypo_gpu_init_multi(const int8_t scores[6], int n_gpus);
+
+/* Number of devices the library currently drives (0 before init / after shutdown). */
+int hypo_gpu_device_count(void);
 
 /*
- * Upper bound of the consensus bytes a batch can produce (used to size `out`):
- * sum over windows of max(draft_len, sum(arm_len + 2) + draft_len + 2).
+ * Knobs for tests and measurements (the defaults are what production uses):
+ *   "first_tier" 0..7  routing starts at this capacity tier (7 = the bound-driven last tier)
+ *   "scap"       n     DFS-stack entries of the bound-driven tiers except the last (0 = from bounds)
+ *   "gather"     0|2   multi-device result gather: 0 every device copies its bytes to the host
+ *                      itself, 2 NCCL send/recv to device 0 over NVLink, then one copy
+ * Returns HYPO_E_ARG for an unknown name or a value out of range.
  */
+int hypo_gpu_set_option(const char* name, int64_t value);
+
+/*
+ * Per-window upper bound of the bytes window w may write while it is being computed (its
+ * consensus is never longer, its intermediate LONG round-1 consensus may be):
+ *     SHORT: sum(arm_len) + 2 * n_arms + draft_len + 2      (>= nodes of the marked graph)
+ *     LONG : 2 * sum(arm_len) + draft_len + 2               (round-2 backbone <= nodes of round 1)
+ * This is the size every d_out_pos slot of hypo_gpu_consensus_batch_device must have, and what
+ * the host entry point reserves internally.  hypo_gpu_out_bound is the sum over the batch
+ * (a safe size for `out` of hypo_gpu_consensus_batch).  Pure host arithmetic, no device needed.
+ */
+int hypo_gpu_window_bounds(const HypoWindowDesc* win, uint64_t n_win,
+                           const HypoArmDesc* arms, uint64_t n_arms, uint64_t* bound);
 uint64_t hypo_gpu_out_bound(const HypoWindowDesc* win, uint64_t n_win,
                             const HypoArmDesc* arms, uint64_t n_arms);
 
@@ -118,15 +155,15 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win,
                              char* out, uint64_t out_cap, uint64_t* out_off);
 
 /*
- * Same computation with every buffer already resident in device memory on the
- * device given to hypo_gpu_init (d_* are device pointers; `stream` is a
- * cudaStream_t passed as void*, NULL = default stream).  The call is
- * asynchronous with respect to the host except for internal tier bookkeeping;
- * results are valid after the stream is synchronised.
+ * Same computation with every buffer already resident in device memory on the FIRST device
+ * the library drives (d_* are device pointers; `stream` is a cudaStream_t passed as void*,
+ * NULL = the library's own stream).  The call launches its kernels on `stream` and BLOCKS the
+ * calling thread until they are done (it synchronises the stream two to four times for tier
+ * bookkeeping); results are valid on return.
  *   d_out_len[w]  = consensus length of window w
- *   d_out         = consensus bytes, window w at d_out + d_out_pos[w] where
- *                   d_out_pos is caller-provided (n_win entries, e.g. an
- *                   exclusive scan of per-window bounds).
+ *   d_out         = consensus bytes, window w at d_out + d_out_pos[w]; d_out_pos is
+ *                   caller-provided (n_win entries) and slot w must hold the bytes
+ *                   hypo_gpu_window_bounds reports for w (e.g. an exclusive scan of them).
  */
 int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
                                     const HypoArmDesc* d_arms, uint64_t n_arms,

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.hypo_gpu_abi_version.restype = ctypes.c_int
-    assert lib.hypo_gpu_abi_version() == 1
+    assert lib.hypo_gpu_abi_version() == 2
 
 
 def test_descriptor_layouts_match_header():
