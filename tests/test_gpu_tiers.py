@@ -160,17 +160,18 @@ def test_malformed_descriptors_return_arg_error(n_win):
     sizes, so malformed input usually killed the context instead of returning HYPO_E_ARG."""
     good = random_batch(130 + n_win, n_win, length=30, n_arms=6)
     want, _ = oracle_consensus(good)
+    out, off = np.empty(int(good.out_bound().sum()) + 16, np.uint8), np.zeros(n_win + 1, np.uint64)
     for field, value in (("first_arm", 1 << 40), ("draft_off", 1 << 50), ("draft_len", 0xFFFFFFFF), ("wtype", 9)):
         b = random_batch(130 + n_win, n_win, length=30, n_arms=6)
         b.win[field][n_win // 2] = value
         with pytest.raises(native.HypoGpuError) as e:
-            native.consensus(b)
+            native.consensus_batch_host(b, out, off)
         assert e.value.code == 3, field
     for field, value in (("off", (1 << 64) - 2), ("len", 0xFFFFFFFE), ("len", 0x80000000), ("reserved", 1)):
         b = random_batch(130 + n_win, n_win, length=30, n_arms=6)
         b.arms[field][b.n_arms // 2] = value
         with pytest.raises(native.HypoGpuError) as e:
-            native.consensus(b)
+            native.consensus_batch_host(b, out, off)
         assert e.value.code == 3, field
     _same(native.consensus(good), want, good, "after malformed input")
 
@@ -229,7 +230,7 @@ def test_small_batches_need_few_host_round_trips():
     want, _ = oracle_consensus(b)
     l0 = native.launch_count()
     _same(native.consensus(b), want, b, "small batch")
-    assert native.launch_count() - l0 <= 10
+    assert native.launch_count() - l0 <= 12   # classify, 2 scans, widen, gather, <= 7 tier launches
 
 
 @pytest.mark.parametrize("gather", [0, 2])
