@@ -1,26 +1,37 @@
 #!/usr/bin/env python
 """bench.py — Mbp polished / s of the POA-consensus hot path (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch of synthetic windows.  Workload at N=1:
-BASELINE.json configs[1], "synthetic 1M windows (30 reads x 120 bp)", all-internal SHORT windows,
-scores 5/-4/-8 (generator: hypo_b200/host/host_capi.cpp, distribution of BASELINE.md §3).
-N>1: every rank polishes its own shard of the same shape (weak scaling, no data-path
-collective), then the consensus bytes are gathered to rank 0 over NCCL.
+A "step" is one pass of the hot path over ONE FIXED set of windows.  Default workload: BASELINE.json
+configs[1], "synthetic 1M windows (30 reads x 120 bp)", all-internal SHORT windows, scores 5/-4/-8
+(generator: hypo_b200/host/host_capi.cpp, distribution of BASELINE.md §3).  Other workloads:
+  --mix pipeline          window shapes as the reference pipeline produces them
+  --stream FILE [FILE..]  windows CAPTURED from the reference command-line program (its own per-window dump,
+                          reference src/Contig.cpp:368-453; tools/capture/): BASELINE.json configs[0]-style sets
 
-  value  : whole-job Mbp/s with the batch resident in HBM (device pointers through
-           hypo_gpu_consensus_batch_device + on-device compaction [+ NCCL gather]); CUDA events.
-  e2e    : the same metric through the host-buffer C-ABI call hypo_gpu_consensus_batch
-           (pinned host buffers; H2D, kernels, compaction, D2H all inside the timed region).
+N > 1 (one process per GPU, torchrun): STRONG scaling.  Every rank builds the same window set (fixed seed)
+and polishes its contiguous, cost-balanced range of it - the path shards with no data-path collective -
+then the exact consensus bytes and per-window lengths are gathered to rank 0 over NCCL (send/recv of the
+exact sizes), which holds the result in window order; after the timed region rank 0 recomputes the whole
+set alone and checks that the gathered bytes are identical.
+
+  value    : whole-job Mbp/s with the batch resident in HBM (device pointers through
+             hypo_gpu_consensus_batch_device + on-device compaction [+ NCCL gather]); CUDA events.
+  e2e      : the same metric through the plugin call a maintainer makes: hypo::Window objects in host memory
+             -> WindowBatch::run (pack into page-locked buffers, H2D, kernels, compaction, D2H, scatter into
+             Window::_consensus), chunked and double-buffered; wall clock, max over ranks.
+  e2e_packed: the bare host-buffer C-ABI call on an already packed batch (what e2e was in round 1).
   roofline / cpu_baseline: see DESIGN.md §measurement.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, compiled from the
 unmodified reference sources; falls back to the C port when it was not built) on the same config.
 """
 import argparse
+import gzip
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -39,27 +50,37 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--windows", type=int, default=1_000_000, help="windows per GPU")
+    ap.add_argument("--windows", type=int, default=1_000_000, help="windows in the set (all GPUs together)")
     ap.add_argument("--arms", type=int, default=30)
     ap.add_argument("--length", type=int, default=120)
     ap.add_argument("--kind", default="internal")
     ap.add_argument("--err", type=float, default=0.01)
+    ap.add_argument("--wtype", type=int, default=0, help="0 SHORT, 1 LONG windows (synthetic workloads)")
     ap.add_argument("--seed", type=int, default=2026)
-    ap.add_argument("--cpu-sample", type=int, default=12000, help="windows timed on the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="windows timed on the CPU baseline per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-compute-roofline", action="store_true")
     ap.add_argument("--mix", default="", choices=["", "pipeline"],
                     help="pipeline: window shapes as the reference CLI produces them (SURVEY.md §6: draft length "
                          "p50 9 / p90 68 / max 100, 10-48 arms, 8 %% of the windows with prefix/suffix arms) "
                          "instead of one fixed shape; --windows is the total")
+    ap.add_argument("--stream", nargs="+", default=[],
+                    help="inspect files (optionally .gz) captured from the reference CLI; replaces the synthetic set")
+    ap.add_argument("--repeat", type=int, default=1, help="--stream: use the captured set this many times over")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.stream:
+        names = ",".join(os.path.basename(p) for p in a.stream)
+        rep = f" x{a.repeat}" if a.repeat > 1 else ""
+        return f"windows captured from the reference CLI ({names}){rep}"
     if a.mix == "pipeline":
-        return (f"synthetic {a.windows} windows/GPU, pipeline shape mix (draft 6-100 bp, median 9; 11-48 arms; "
+        return (f"synthetic {a.windows} windows, pipeline shape mix (draft 6-100 bp, median 9; 11-48 arms; "
                 f"8 % with prefix/suffix arms; SHORT, err {a.err})")
-    return f"synthetic {a.windows} windows/GPU ({a.arms} reads x {a.length} bp, {a.kind}, SHORT, err {a.err})"
+    wt = "LONG" if a.wtype else "SHORT"
+    return f"synthetic {a.windows} windows ({a.arms} reads x {a.length} bp, {a.kind}, {wt}, err {a.err})"
 
 
 # (draft length, weight) and (arms, weight): the two datasets measured in SURVEY.md §6
@@ -67,23 +88,61 @@ PIPELINE_LEN = ((6, 0.20), (9, 0.32), (14, 0.14), (25, 0.12), (40, 0.08), (68, 0
 PIPELINE_ARMS = ((11, 0.30), (16, 0.15), (30, 0.15), (39, 0.25), (48, 0.15))
 
 
-def make_batch(a, seed):
-    """The synthetic shard of one rank (one fixed shape, or the pipeline shape mix)."""
+def load_streams(paths, repeat):
+    from hypo_b200.batch import concat_batches
+    from hypo_b200.hostlib import InspectStream
+    parts = []
+    for p in paths:
+        if p.endswith(".gz"):
+            with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as t:
+                t.write(gzip.open(p).read())
+                tmp = t.name
+            s = InspectStream(tmp)
+            os.unlink(tmp)
+        else:
+            s = InspectStream(p)
+        parts.append(s.batch)
+        s.close()
+    parts = parts * max(1, repeat)
+    return parts[0] if len(parts) == 1 else concat_batches(parts, {"stream": list(paths)})
+
+
+def make_batch(a, seed, n_windows=None):
+    """The window set of the run (one fixed shape, the pipeline shape mix, or captured streams)."""
     from hypo_b200.batch import concat_batches
     from hypo_b200.hostlib import synth_batch
+    n_windows = a.windows if n_windows is None else n_windows
+    if a.stream:
+        b = load_streams(a.stream, a.repeat)
+        return b if n_windows >= b.n_win or n_windows == a.windows else b.select(np.arange(n_windows))
     if a.mix != "pipeline":
-        return synth_batch(seed, a.windows, a.length, a.arms, a.kind, a.err)
+        return synth_batch(seed, n_windows, a.length, a.arms, a.kind, a.err, wtype=a.wtype)
     parts, k = [], 0
     for ln, wl in PIPELINE_LEN:
         for na, wa in PIPELINE_ARMS:
             for kind, wk in (("internal", 0.92), ("mixed", 0.08)):
-                n = int(round(a.windows * wl * wa * wk))
+                n = int(round(n_windows * wl * wa * wk))
                 k += 1
                 if n > 0:
                     parts.append(synth_batch(seed + 104729 * k, n, ln, na, kind, a.err))
     b = concat_batches(parts, {"mix": "pipeline"})
     perm = np.random.default_rng(seed).permutation(b.n_win)
     return b.select(perm)
+
+
+def shard_range(batch, rank, world):
+    """Contiguous window range of rank `rank`: equal estimated cost (reads x draft length^2, the rule of
+    hypo_gpu_init_multi's cut_shards)."""
+    if world == 1:
+        return 0, batch.n_win
+    w = batch.win
+    cost = (w["n_internal"] + w["n_pre"] + w["n_suf"]).astype(np.float64) * (w["draft_len"].astype(np.float64) + 2) ** 2 + 64
+    acc = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for i in range(1, world):
+        cuts.append(max(cuts[-1], int(np.searchsorted(acc, acc[-1] * i / world))))
+    cuts.append(batch.n_win)
+    return cuts[rank], cuts[rank + 1]
 
 
 class ClockSampler:
@@ -141,13 +200,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_time(batch, n_sample, schedule=1):
+def cpu_reference_time(batch, n_sample, schedule=1, offset=0):
     """Times the reference's CPU path (oracle/_ref) or, if absent, the C port on a bounded sample.
     Returns (Mbp/s, cores, kind, sample description)."""
     from tests import oracle_util as ou
     n = min(n_sample, batch.n_win)
-    sub = batch.select(np.arange(n))
+    lo = (offset * n) % max(1, batch.n_win - n + 1)
+    sub = batch.select(np.arange(lo, lo + n))
     cores = os.cpu_count() or 1
+    sched = "schedule(dynamic,1)" if schedule else "schedule(static,1) as shipped (reference src/Hypo.cpp:240)"
     if ou.ref_lib(False) is not None:
         # the faster of the reference's two CPU engines (SISD default build, AVX2 -mavx2 build)
         best, which = None, None
@@ -158,13 +219,13 @@ def cpu_reference_time(batch, n_sample, schedule=1):
             if best is None or sec < best:
                 best, which = sec, ("AVX2" if simd else "SISD")
         kind = "reference"
-        desc = (f"first {n} windows of the workload, unmodified reference Window::generate_consensus under OpenMP "
-                f"schedule(dynamic,1), {cores} threads, faster of SISD/AVX2 builds ({which})")
+        desc = (f"{n} windows of the workload, unmodified reference Window::generate_consensus under OpenMP "
+                f"{sched}, {cores} threads, faster of SISD/AVX2 builds ({which})")
         sec = best
     else:
         _, sec = ou.oracle_consensus(sub, SCORES, threads=cores)
         kind = "port"
-        desc = f"first {n} windows of the workload, oracle/poa_oracle.c under OpenMP, {cores} threads"
+        desc = f"{n} windows of the workload, oracle/poa_oracle.c under OpenMP, {cores} threads"
     return sub.polished_bp / 1e6 / sec, cores, kind, desc
 
 
@@ -172,26 +233,23 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from hypo_b200.hostlib import synth_batch
-    n_gen = max(a.cpu_sample, 1000)
-    gen = argparse.Namespace(**vars(a))
-    gen.windows = n_gen   # the reference arm times a bounded sample of the same workload
-    batch = make_batch(gen, a.seed)
-    # bounded sample per step so that steps+warmup finish within minutes
-    per_step = max(500, min(a.cpu_sample, n_gen) // 3)
-    vals = []
+    # the reference arm times a bounded sample of the same workload: --cpu-sample windows per step
+    n_gen = a.cpu_sample * 3
+    batch = make_batch(a, a.seed, n_windows=n_gen)
+    per_step = min(a.cpu_sample, batch.n_win)
+    vals, bps = [], []
     for s in range(a.warmup + a.steps):
-        v, cores, kind, desc = cpu_reference_time(batch, per_step)
+        v, cores, kind, desc = cpu_reference_time(batch, per_step, offset=s)
         if s >= a.warmup:
             vals.append(v)
     value = float(np.mean(vals))
-    sample = desc.replace(f"first {min(per_step, batch.n_win)}", f"{per_step}")
+    bp_step = batch.polished_bp * per_step / batch.n_win
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * (batch.select(np.arange(per_step)).polished_bp / 1e6) / value,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * (bp_step / 1e6) / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": workload_name(a), "scores": list(SCORES)},
-        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,7 +265,7 @@ def main():
     import torch
     import torch.distributed as dist
     from hypo_b200 import native
-    from hypo_b200.hostlib import synth_batch
+    from hypo_b200.hostlib import HostWindows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,12 +276,17 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # the host side of every rank packs with its share of the cores
+        # (torchrun presets OMP_NUM_THREADS=1; libhypo_host.so reads it when it is first loaded, below)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     native.init(SCORES, local)
 
-    # ---- synthetic shard of this rank --------------------------------------------------
-    batch = make_batch(a, a.seed + 7919 * rank)
+    # ---- the window set (identical on every rank) and this rank's range of it ----------------
+    full = make_batch(a, a.seed)
+    w_lo, w_hi = shard_range(full, rank, world)
+    batch = full.select(np.arange(w_lo, w_hi)) if world > 1 else full
     n_win, n_arms = batch.n_win, batch.n_arms
-    bp = batch.polished_bp
+    bp_total = full.polished_bp
     bound = batch.out_bound()
     out_pos_np = np.concatenate([[0], np.cumsum(bound)[:-1]]).astype(np.uint64)
     scratch_bytes = int(bound.sum()) + 16
@@ -235,13 +298,43 @@ def main():
     d_out_pos = to_dev(out_pos_np)
     d_scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
     d_out_len = torch.zeros(n_win, dtype=torch.int32, device=dev)
-    compact_cap = int(bp * 1.5) + 4096
+    compact_cap = int(batch.polished_bp * 1.5) + 4096
     d_compact = torch.zeros(compact_cap, dtype=torch.uint8, device=dev)
     d_off = torch.zeros(n_win + 1, dtype=torch.int64, device=dev)
-    gather_list = [torch.empty(compact_cap, dtype=torch.uint8, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
     stream = torch.cuda.current_stream().cuda_stream
     totals = []
+    # rank 0 holds the whole result in window order: bytes and per-window lengths
+    if world > 1:
+        counts = [shard_range(full, r, world) for r in range(world)]
+        g_cap = int(bp_total * 1.5) + 4096 * world
+        g_bytes = torch.zeros(g_cap if rank == 0 else 1, dtype=torch.uint8, device=dev)
+        g_len = torch.zeros(full.n_win if rank == 0 else 1, dtype=torch.int32, device=dev)
+        t_total = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def gather_exact(total):
+        """Final consensus gather, the only collective of the path: sizes by all-gather,
+        then send/recv of exactly the bytes and lengths each rank produced."""
+        mine = torch.tensor([total], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(t_total, mine)
+        sizes = t_total.cpu().tolist()
+        ops = []
+        if rank == 0:
+            g_bytes[:total].copy_(d_compact[:total])
+            g_len[:n_win].copy_(d_out_len)
+            base = total
+            for r in range(1, world):
+                lo, hi = counts[r]
+                if sizes[r]:
+                    ops.append(dist.P2POp(dist.irecv, g_bytes[base:base + sizes[r]], r))
+                ops.append(dist.P2POp(dist.irecv, g_len[lo:hi], r))
+                base += sizes[r]
+        else:
+            if total:
+                ops.append(dist.P2POp(dist.isend, d_compact[:total], 0))
+            ops.append(dist.P2POp(dist.isend, d_out_len, 0))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return int(sum(sizes))
 
     def step_device():
         native.consensus_batch_device(d_win.data_ptr(), n_win, d_arms.data_ptr(), n_arms, d_packed.data_ptr(),
@@ -250,8 +343,8 @@ def main():
         total = native.compact_device(d_scratch.data_ptr(), d_out_pos.data_ptr(), d_out_len.data_ptr(), n_win,
                                       d_compact.data_ptr(), compact_cap, d_off.data_ptr(), stream)
         totals.append(total)
-        if world > 1:   # final consensus gather: the only collective of the path
-            dist.gather(d_compact, gather_list, dst=0)
+        if world > 1:
+            totals[-1] = (total, gather_exact(total))
 
     def sync_all():
         if world > 1:
@@ -266,27 +359,34 @@ def main():
         clocks.start()
     l0 = native.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    poa_ms = []
+    poa_ms, cells = [], []
     ev0.record()
     for _ in range(a.steps):
         step_device()
         poa_ms.append(native.last_timing()[0])
+        cells.append(native.last_cells())
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = native.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     tiers = native.last_timing()[2]
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(np.mean(poa_ms)), float(cells[-1])], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_max, k_ms, cells_total = float(tmax[0]), float(tmax[1]), float(t[2])
+    else:
+        ms_max, k_ms, cells_total = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = ms_max / a.steps
-    value = (bp * world) / 1e6 / (ms_per_step / 1e3)
-    total_cons = totals[-1]
+    value = bp_total / 1e6 / (ms_per_step / 1e3)
+    total_cons = totals[-1] if world == 1 else totals[-1][1]
+    my_cons = totals[-1] if world == 1 else totals[-1][0]
 
-    # parity spot-check of what was just timed: first windows against the CPU oracle
-    ok = None
+    # parity of what was just timed: first windows against the CPU oracle; N > 1: the gathered result against
+    # the whole set recomputed on rank 0 alone (strong scaling must not change a byte)
+    ok, same_as_single = None, None
     if rank == 0:
         from tests.oracle_util import oracle_consensus
         k = min(256, n_win)
@@ -295,43 +395,79 @@ def main():
         got = [raw[int(off[i]):int(off[i + 1])].decode() for i in range(k)]
         want, _ = oracle_consensus(batch.select(np.arange(k)), SCORES)
         ok = got == want
+        # a strided sample over the whole range as well
+        idx = np.unique(np.linspace(0, n_win - 1, 256).astype(np.int64))
+        offs = d_off.cpu().numpy()
+        allraw = d_compact[:my_cons].cpu().numpy().tobytes()
+        got = [allraw[int(offs[i]):int(offs[i + 1])].decode() for i in idx]
+        want, _ = oracle_consensus(batch.select(idx), SCORES)
+        ok = bool(ok and got == want)
+    if world > 1:
+        if rank == 0:
+            gathered = g_bytes[:total_cons].cpu().numpy().tobytes()
+            gathered_len = g_len.cpu().numpy().copy()
+            single = native.consensus_batch_host(full)
+            s_bytes = single[0][: int(single[1][-1])].tobytes()
+            same_as_single = bool(gathered == s_bytes and
+                                  np.array_equal(gathered_len.astype(np.uint64), np.diff(single[1])))
+        dist.barrier()
 
-    # ---- end to end through the host-buffer C ABI ---------------------------------------
-    e2e = None
+    # ---- end to end: hypo::Window objects -> WindowBatch::run (pack, copies, kernels, scatter) ------------
+    e2e, e2e_packed, host_t = None, None, None
     if not a.no_e2e:
-        def pin(x):
-            t_ = torch.from_numpy(x.view(np.uint8).reshape(-1)).pin_memory()
-            return t_
-        p_win, p_arms, p_packed = pin(batch.win), pin(batch.arms), pin(batch.packed)
-        p_out = torch.empty(compact_cap, dtype=torch.uint8).pin_memory()
-        p_off = torch.empty(n_win + 1, dtype=torch.int64).pin_memory()
-        L = native.lib()
-
-        def step_e2e():
-            rc = L.hypo_gpu_consensus_batch(p_win.data_ptr(), n_win, p_arms.data_ptr(), n_arms, p_packed.data_ptr(),
-                                            batch.packed.size, p_out.data_ptr(), compact_cap, p_off.data_ptr())
-            if rc != 0:
-                raise native.HypoGpuError(rc, L.hypo_gpu_last_error().decode())
-
-        step_e2e()
+        hw = HostWindows(batch)
+        hw.run()   # warm-up: page-locked buffers are allocated here
         sync_all()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            step_e2e()
-        torch.cuda.synchronize()
+            host_t = hw.run()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        e2e_total = int(p_off[n_win].item())
-        e2e = {"value": (bp * world) / 1e6 / (dt / a.steps), "unit": "Mbp/s",
+        cons_b, cons_off = hw.consensus_bytes()
+        e2e = {"value": bp_total / 1e6 / (dt / a.steps), "unit": "Mbp/s",
                "h2d_bytes_per_step": int(batch.win.nbytes + batch.arms.nbytes + batch.packed.nbytes),
-               "d2h_bytes_per_step": int(e2e_total + 8 * (n_win + 1))}
+               "d2h_bytes_per_step": int(cons_b.size + 8 * (n_win + 1)),
+               "path": "hypo::Window objects -> WindowBatch::run (pack + H2D + kernels + D2H + scatter, chunked, "
+                       "double-buffered); wall clock, max over ranks",
+               "host_threads": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+               "rank0_breakdown_s": host_t}
         if rank == 0:
-            # e2e output must equal the device-resident output
-            same = bytes(p_out[:e2e_total].numpy().tobytes()) == d_compact[:total_cons].cpu().numpy().tobytes()
+            same = cons_b.tobytes() == d_compact[:my_cons].cpu().numpy().tobytes()
             ok = bool(ok and same)
+        hw.close()
+
+        # the bare C-ABI call on pre-packed page-locked buffers
+        def pin(x):
+            return torch.from_numpy(x.view(np.uint8).reshape(-1)).pin_memory()
+        p_win, p_arms, p_packed = pin(batch.win), pin(batch.arms), pin(batch.packed)
+        p_out = torch.empty(compact_cap, dtype=torch.uint8).pin_memory()
+        p_off = torch.empty(n_win + 1, dtype=torch.int64).pin_memory()
+        L = native.lib()
+
+        def step_packed():
+            rc = L.hypo_gpu_consensus_batch(p_win.data_ptr(), n_win, p_arms.data_ptr(), n_arms, p_packed.data_ptr(),
+                                            batch.packed.size, p_out.data_ptr(), compact_cap, p_off.data_ptr())
+            if rc != 0:
+                raise native.HypoGpuError(rc, L.hypo_gpu_last_error().decode())
+
+        step_packed()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step_packed()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_packed = {"value": bp_total / 1e6 / (float(t.item()) / a.steps), "unit": "Mbp/s",
+                      "path": "hypo_gpu_consensus_batch on an already packed batch in page-locked memory"}
+        if rank == 0:
+            tot = int(p_off[n_win].item())
+            ok = bool(ok and bytes(p_out[:tot].numpy().tobytes()) == d_compact[:my_cons].cpu().numpy().tobytes())
 
     if rank != 0:
         if world > 1:
@@ -340,16 +476,15 @@ def main():
 
     # ---- roofline of the dominant kernel (POA tier kernels) -------------------------------
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = batch.algorithmic_bytes(total_cons)
-    k_ms = float(np.mean(poa_ms))
+    alg_bytes = batch.algorithmic_bytes(my_cons)   # per launch = this rank's range
     achieved = alg_bytes / 1e9 / (k_ms / 1e3)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if (not a.mix and tj.get("windows") == a.windows and tj.get("arms") == a.arms
-                    and tj.get("length") == a.length):
+            if (not a.mix and not a.stream and world == 1 and tj.get("windows") == a.windows
+                    and tj.get("arms") == a.arms and tj.get("length") == a.length):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -357,24 +492,55 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel": "poa_kernel (all tier launches of one step)", "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms / ms_per_step,
-                "note": "integer DP on an irregular DAG: issue/latency bound, not HBM bound (DESIGN.md §roofline)"}
+                "note": "integer DP on an irregular DAG: issue bound, not HBM bound - see `compute`"}
+    if not a.no_compute_roofline:
+        # what binds the kernel: the DPX issue rate, measured on this device right now
+        rates = {native.ISSUE_OPS[i]: native.issue_rate(i) for i in range(len(native.ISSUE_OPS))}
+        gcups = cells_total / 1e9 / (k_ms / 1e3)
+        # a cell needs two DPX operations per predecessor (diagonal and vertical VIADDMNMX); one S16x2 warp
+        # instruction serves 64 cells => 32 cells per DPX warp instruction at best
+        dpx_peak = rates["VIADDMNMX.S16x2"] * 32.0 * world
+        roofline["compute"] = {
+            "bound": "int-issue", "achieved": gcups, "unit": "GCUPS", "peak": dpx_peak, "frac": gcups / dpx_peak,
+            "cells_per_step": cells_total,
+            "peak_definition": "measured VIADDMNMX.S16x2 issue rate x 32 cells per warp instruction (2 DPX ops per "
+                               "cell and predecessor, 64 cells per instruction): the fill with nothing but its two "
+                               "DPX operations",
+            "measured_issue_rates_gwarp_instr_per_s": rates,
+            "note": "the fill issues ~70 warp instructions per 128-cell row of which 4 are these DPX operations; "
+                    "issue-slot utilisation of the kernel (ncu) is in profiles/"}
 
-    cpu = None
+    cpu, cpu_static = None, None
     if world == 1 and not a.no_cpu_baseline:
         v, cores, kind, desc = cpu_reference_time(batch, a.cpu_sample)
         cpu = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": desc}
+        if kind == "reference":
+            v0, _, _, desc0 = cpu_reference_time(batch, a.cpu_sample, schedule=0)
+            cpu_static = {"value": v0, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": desc0}
 
+    meta = None
+    if a.stream:
+        mp = os.path.join(os.path.dirname(a.stream[0]), os.path.basename(a.stream[0]).split("_ctg")[0] + ".meta.json")
+        if os.path.exists(mp):
+            meta = json.load(open(mp))
     line = {
         "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int16", "data": "synthetic",
-        "config": {"workload": workload_name(a), "scores": list(SCORES), "windows_total": a.windows * world,
-                   "polished_bp_per_step": bp * world, "sharding": f"{world} rank(s), independent window shards",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int16", "data": "captured" if a.stream else "synthetic",
+        "config": {"workload": workload_name(a), "scores": list(SCORES), "windows_total": full.n_win,
+                   "polished_bp_per_step": bp_total,
+                   "sharding": f"{world} rank(s): one fixed window set, contiguous cost-balanced ranges, NCCL gather of "
+                               f"the exact consensus bytes + lengths to rank 0",
                    "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" %
+                         ((batch.win.nbytes + batch.arms.nbytes + batch.packed.nbytes) / 1e6)
+                         if (batch.win.nbytes + batch.arms.nbytes + batch.packed.nbytes) > 126e6 else
+                         "inputs (%.0f MB/GPU) fit the L2: every step re-reads them from a cold HBM copy only if evicted; "
+                         "the DP workspace written in between (> 200 MB) flushes them" %
                          ((batch.win.nbytes + batch.arms.nbytes + batch.packed.nbytes) / 1e6),
-                   "tier_windows": tiers},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "parity_spot_check": ok,
+                   "tier_windows": tiers, "reference_capture": meta},
+        "clocks": clk, "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu, "cpu_baseline_as_shipped": cpu_static,
+        "parity_spot_check": ok, "same_bytes_as_one_gpu": same_as_single,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

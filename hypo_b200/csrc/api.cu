@@ -151,6 +151,7 @@ struct DevCtrl {
     uint32_t fail[kNumFailReasons];   // why windows were abandoned (diagnostics)
     uint32_t bad;                     // malformed descriptors
     uint32_t pad[3];
+    unsigned long long cells;         // DP cells of the completed windows (work counter, GCUPS)
 };
 
 struct RouteCfg {
@@ -182,6 +183,7 @@ struct Ctx {
     uint32_t poa_launches = 0;
     uint32_t tier_windows[8] = {0};
     uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
+    unsigned long long cells = 0;                // DP cells of the last batch call
     std::string err;             // message of a failure on this device's worker thread
 };
 
@@ -405,6 +407,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         g.poa_launches = 0;
         memset(g.tier_windows, 0, sizeof(g.tier_windows));
         memset(g.fail_hist, 0, sizeof(g.fail_hist));
+        g.cells = 0;
     }
     if (n_win == 0) return HYPO_OK;
     DevCtrl* const d_ctrl = (DevCtrl*)g.ctrl.p;
@@ -522,6 +525,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.out = d_out; P.out_pos = d_out_pos; P.out_len = d_out_len;
         P.next_list = d_lists + (uint64_t)nx * n_win; P.next_count = &d_ctrl->tmax[nx].count;
         P.fail_hist = d_ctrl->fail;
+        P.cells = &d_ctrl->cells;
         P.need = d_need;
         P.H = (int16_t*)g.H.p; P.h_slot = h_slot;
         P.gws = (uint8_t*)g.gws.p; P.g_slot = g_slot;
@@ -547,6 +551,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         g.tier_windows[t] += h->tmax[t].count;
     }
     for (int k = 0; k < kNumFailReasons; ++k) g.fail_hist[k] += h->fail[k];
+    g.cells += h->cells;
     const uint32_t lost = h->tmax[kNumTiers].count;
     if (lost != 0)
         return fail(HYPO_E_CAPACITY, "%u window(s) exceed every device capacity tier (a graph of more than 65534 nodes, "
@@ -1156,6 +1161,78 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
     return HYPO_OK;
 }
 
+uint64_t hypo_gpu_last_cells(void) {
+    uint64_t c = 0;
+    for (int i = 0; i < G.n_dev; ++i) c += G.dev[i]->cells;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Issue-rate micro-benchmark: what the SMs sustain for the instructions the DP fill is made of.
+// Eight independent chains per thread, 32 warps per SM resident, so the rate measured is the pipe's,
+// not a latency.  (VIADDMNMX / VIMNMX3 are the sm_100 DPX instructions behind __viaddmax / __vimax3.)
+// ---------------------------------------------------------------------------------------
+}  // extern "C" (kernels have C++ linkage)
+
+namespace {
+template <int kOp>
+__global__ void __launch_bounds__(256) issue_kernel(uint32_t* sink, int iters, uint32_t seed) {
+    uint32_t a[8], b = seed * 0x9e3779b9u + threadIdx.x, c = seed ^ 0x01010101u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k * 0x10001u + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (kOp == 0) a[k] = __viaddmax_s16x2(a[k], b, c);
+                else if (kOp == 1) a[k] = __vimax3_s16x2(a[k], b, c);
+                else if (kOp == 2) a[k] = (uint32_t)__viaddmax_s32((int)a[k], (int)b, (int)c);
+                else if (kOp == 3) a[k] = __shfl_up_sync(0xffffffffu, a[k], 1);
+                else if (kOp == 4) a[k] = __byte_perm(a[k], b, 0x5432);
+                else a[k] = a[k] + b;
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x ^= a[k];
+    if (x == 0x12345678u) sink[0] = x;   // never true in practice; keeps the chains alive
+}
+}  // namespace
+
+extern "C" {
+
+int hypo_gpu_issue_rate(int op, double* g_warp_instr_per_s) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err.clear();
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (op < 0 || op > 5 || !g_warp_instr_per_s) return fail(HYPO_E_ARG, "op must be 0..5");
+    Ctx& g = *G.dev[0];
+    CUDA_TRY(cudaSetDevice(g.device));
+    CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
+    void (*k)(uint32_t*, int, uint32_t) = op == 0 ? issue_kernel<0> : op == 1 ? issue_kernel<1> : op == 2 ? issue_kernel<2>
+                                        : op == 3 ? issue_kernel<3> : op == 4 ? issue_kernel<4> : issue_kernel<5>;
+    const int iters = 4096, blocks = g.sms * 4, threads = 256;
+    cudaEvent_t e0 = g.tev0[0][0], e1 = g.tev1[0][0];
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up
+        CUDA_TRY(cudaEventRecord(e0, g.stream));
+        k<<<blocks, threads, 0, g.stream>>>((uint32_t*)g.ctrl.p + 60, iters, 12345u + rep);
+        CUDA_TRY(cudaEventRecord(e1, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        CUDA_TRY(cudaGetLastError());
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double warp_instr = (double)blocks * (threads / 32) * (double)iters * 32.0;
+        if (rep > 0) best = std::max(best, warp_instr / (ms * 1e-3) / 1e9);
+    }
+    G.launches += 4;
+    *g_warp_instr_per_s = best;
+    return HYPO_OK;
+}
+
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]) {
     if (!reasons) return HYPO_OK;
     for (int k = 0; k < kNumFailReasons; ++k) {
@@ -1163,6 +1240,19 @@ int hypo_gpu_last_fail_hist(uint32_t reasons[16]) {
         for (int i = 0; i < G.n_dev; ++i) reasons[k] += G.dev[i]->fail_hist[k];
     }
     return HYPO_OK;
+}
+
+void* hypo_gpu_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void hypo_gpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 void hypo_gpu_shutdown(void) {

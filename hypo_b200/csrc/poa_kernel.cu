@@ -56,6 +56,7 @@ struct WarpState {
     int n_total;         // sequences this window (round) will add in all
     uint32_t base;       // nodes | edges << 16 after the second sequence (growth is measured from here)
     uint32_t need;       // projected final nodes | edges << 16 when the window was abandoned on projection
+    unsigned long long cells;   // DP cells filled for this window so far: sum of (rows + 1) x (columns + 1)
 };
 
 // Tiers that extrapolate a window's growth and abandon it early (add_sequence): the multi-tile ones with
@@ -1333,6 +1334,8 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
         const int S = max(max(abs(sc.m), abs(sc.n)), abs(sc.g));
         const bool narrow = !(S * (nodes_before + 1 + cols) > kMaxH16 || 2 * S * cols > kMaxH16);
         if (!kWide && !narrow) return give_up(st, kFailRange);
+        // (the reference's matrix of this read: (nodes + 1) x (len + 1), sisd_alignment_engine.cpp:52-75)
+        if (lane == 0) ws->cells += (unsigned long long)(nodes_before + 1) * (unsigned long long)(len + 1);
         unsigned lines;   // 128-byte lines of the matrix this read leaves behind
         if (!kWide || narrow) {
             // boundary arrays of the multi-tile fill live behind the matrix slot
@@ -1635,6 +1638,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
             if (P.need) need = P.need[widx];
             pass_on = (int)(need & 0xffffu) > caps.ncap + caps.ncap / 8 || (int)(need >> 16) > caps.ecap + caps.ecap / 8;
         }
+        if (lane == 0) warp_state<kSmem, kTier>(g)->cells = 0;
         if (w.n_empty > n) {
             res = 0;   // reference src/Window.cpp:47-49
         } else if (kProjects<kOneTile, kTier> && pass_on) {
@@ -1668,6 +1672,7 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
                 }
             } else {
                 P.out_len[widx] = (uint32_t)res;
+                if (P.cells) atomicAdd(P.cells, warp_state<kSmem, kTier>(g)->cells);
             }
         }
         __syncwarp();

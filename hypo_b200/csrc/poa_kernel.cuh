@@ -98,6 +98,8 @@ struct Params {
     uint32_t* next_list;         // windows that exceed this tier are appended to the successor tier's list ...
     uint32_t* next_count;        // ... whose (atomic) length this is; the tier lists never need the host in between
     uint32_t* fail_hist;         // [kNumFailReasons] why windows left a tier (diagnostics; may be null)
+    unsigned long long* cells;   // sum of the DP cells (rows x columns of every fill) of the windows this
+                                 // launch completed: the work counter behind the GCUPS figures (may be null)
     uint32_t* need;              // per window: projected nodes | edges << 16 left by a tier that abandoned it
                                  // on projection (0 = none; may be null)
     int16_t* H;                  // DP workspace, one slot per warp
@@ -114,7 +116,7 @@ __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & 
 
 // Per-warp graph arena.  Node arrays are indexed by node id, row arrays by rank (+1 = DP row).
 struct ArenaLayout {
-    uint32_t state;     // WarpState: element counts of the window being built (32 bytes)
+    uint32_t state;     // WarpState: element counts of the window being built (40 bytes)
     // nodes
     uint32_t ninfo;     // u8  letter code (bits 0-2) | has-out-edge (bit 3)
     uint32_t al_cnt;    // u8  number of aligned nodes
@@ -159,7 +161,7 @@ struct LayoutCursor {
 __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     ArenaLayout L{};
     LayoutCursor k{0};
-    L.state = k.take(32);
+    L.state = k.take(48);
     L.ninfo = k.take(c.ncap);
     L.al_cnt = k.take(c.ncap);
     L.in_deg = k.take(c.ncap);

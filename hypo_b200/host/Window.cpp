@@ -7,6 +7,9 @@
 
 #include <omp.h>
 
+#include <algorithm>
+#include <thread>
+
 #include "WindowBatch.hpp"
 
 namespace hypo {
@@ -46,6 +49,17 @@ std::ostream& operator<<(std::ostream& os, const Window& wnd) {
     return os;
 }
 
+WindowBatch::~WindowBatch() {
+    _slot[0].release();
+    _slot[1].release();
+}
+
+void WindowBatch::Slot::release() {
+    hypo_gpu_host_free(win); hypo_gpu_host_free(arms); hypo_gpu_host_free(packed);
+    hypo_gpu_host_free(out); hypo_gpu_host_free(off);
+    *this = Slot();
+}
+
 void WindowBatch::clear() {
     _windows.clear(); _win.clear(); _arms.clear(); _packed.reset(); _packed_bytes = 0; _n_packed = 0; _bp = 0;
 }
@@ -59,73 +73,148 @@ void WindowBatch::add(Window* w) {
     _bp += w->_draft.get_seq_size();
 }
 
-void WindowBatch::pack(int threads) {
-    const size_t n = _windows.size();
-    if (_n_packed == n) return;
-    if (threads <= 0) threads = omp_get_max_threads();
-    // pass 1: arms and bytes per window
-    std::vector<uint64_t> arm0(n + 1), byte0(n + 1);
-    arm0[0] = 0; byte0[0] = 0;
+namespace {
+
+// Sizes of windows [first, first + n): prefix sums of arms and bytes (n + 1 entries each).
+void measure(Window* const* ws, size_t n, int threads, std::vector<uint64_t>& arm0, std::vector<uint64_t>& byte0) {
+    arm0.assign(n + 1, 0);
+    byte0.assign(n + 1, 0);
 #pragma omp parallel for schedule(static, 512) num_threads(threads)
     for (size_t i = 0; i < n; ++i) {
-        const Window* w = _windows[i];
-        uint64_t bytes = w->_draft.data_size();
-        for (const auto* v : {&w->_internal_arms, &w->_pre_arms, &w->_suf_arms})
-            for (const auto& a : *v) bytes += a.data_size();
-        arm0[i + 1] = w->_internal_arms.size() + w->_pre_arms.size() + w->_suf_arms.size();
+        const Window* w = ws[i];
+        uint64_t bytes = w->draft().data_size();
+        uint64_t arms = 0;
+        w->for_each_arm([&](const PackedSeq<2>& a) { bytes += a.data_size(); ++arms; });
+        arm0[i + 1] = arms;
         byte0[i + 1] = bytes;
     }
     for (size_t i = 0; i < n; ++i) { arm0[i + 1] += arm0[i]; byte0[i + 1] += byte0[i]; }
-    _win.resize(n);
-    _arms.resize(arm0[n]);
-    _packed_bytes = byte0[n];
-    _packed.reset(new uint8_t[_packed_bytes + 16]);
-    uint8_t* const slab = _packed.get();
-    // pass 2: every window fills its own slice (arms in container order: internal, prefix, suffix)
+}
+
+// Every window fills its own slice (arms in container order: internal, prefix, suffix).
+void fill(Window* const* ws, size_t n, int threads, const std::vector<uint64_t>& arm0, const std::vector<uint64_t>& byte0,
+          HypoWindowDesc* win, HypoArmDesc* arms, uint8_t* slab) {
 #pragma omp parallel for schedule(static, 512) num_threads(threads)
     for (size_t i = 0; i < n; ++i) {
-        const Window* w = _windows[i];
+        const Window* w = ws[i];
         uint64_t pos = byte0[i];
         HypoWindowDesc d;
         memset(&d, 0, sizeof(d));
         d.draft_off = pos;
-        d.draft_len = (uint32_t)w->_draft.get_seq_size();
-        memcpy(slab + pos, w->_draft.data(), w->_draft.data_size());
-        pos += w->_draft.data_size();
+        d.draft_len = (uint32_t)w->draft().get_seq_size();
+        memcpy(slab + pos, w->draft().data(), w->draft().data_size());
+        pos += w->draft().data_size();
         d.first_arm = arm0[i];
-        d.n_internal = (uint32_t)w->_internal_arms.size();
-        d.n_pre = (uint32_t)w->_pre_arms.size();
-        d.n_suf = (uint32_t)w->_suf_arms.size();
-        d.n_empty = w->_num_empty;
-        d.wtype = w->_wtype == WindowType::LONG ? HYPO_WINDOW_LONG : HYPO_WINDOW_SHORT;
-        HypoArmDesc* ad = _arms.data() + arm0[i];
-        for (const auto* v : {&w->_internal_arms, &w->_pre_arms, &w->_suf_arms})
-            for (const auto& a : *v) {
-                ad->off = pos;
-                ad->len = (uint32_t)a.get_seq_size();
-                ad->reserved = 0;
-                memcpy(slab + pos, a.data(), a.data_size());
-                pos += a.data_size();
-                ++ad;
-            }
-        _win[i] = d;
+        w->counts(d.n_internal, d.n_pre, d.n_suf, d.n_empty);
+        d.wtype = w->get_type() == WindowType::LONG ? HYPO_WINDOW_LONG : HYPO_WINDOW_SHORT;
+        HypoArmDesc* ad = arms + arm0[i];
+        w->for_each_arm([&](const PackedSeq<2>& a) {
+            ad->off = pos;
+            ad->len = (uint32_t)a.get_seq_size();
+            ad->reserved = 0;
+            memcpy(slab + pos, a.data(), a.data_size());
+            pos += a.data_size();
+            ++ad;
+        });
+        win[i] = d;
     }
+}
+
+template <class T>
+void grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    hypo_gpu_host_free(p);
+    cap = need + need / 4 + 64;
+    p = static_cast<T*>(hypo_gpu_host_alloc(cap * sizeof(T)));
+    if (!p) {
+        fprintf(stderr, "[Hypo::GPU] Error: cannot allocate %zu bytes of page-locked host memory\n", cap * sizeof(T));
+        exit(1);
+    }
+}
+
+}  // namespace
+
+void WindowBatch::pack(int threads) {
+    const size_t n = _windows.size();
+    if (_n_packed == n) return;
+    if (threads <= 0) threads = omp_get_max_threads();
+    std::vector<uint64_t> arm0, byte0;
+    measure(_windows.data(), n, threads, arm0, byte0);
+    _win.resize(n);
+    _arms.resize(arm0[n]);
+    _packed_bytes = byte0[n];
+    _packed.reset(new uint8_t[_packed_bytes + 16]);
+    fill(_windows.data(), n, threads, arm0, byte0, _win.data(), _arms.data(), _packed.get());
     _n_packed = n;
 }
 
-void WindowBatch::run() {
-    if (_windows.empty()) return;
-    pack();
-    const uint64_t cap = hypo_gpu_out_bound(_win.data(), _win.size(), _arms.data(), _arms.size());
-    _out.resize(cap + 16);
-    _off.resize(_win.size() + 1);
-    if (hypo_gpu_consensus_batch(_win.data(), _win.size(), _arms.data(), _arms.size(), _packed.get(), _packed_bytes,
-                                 _out.data(), _out.size(), _off.data()) != HYPO_OK)
-        die("POA of windows");
-    const size_t n = _windows.size();
+void WindowBatch::pack_chunk(Slot& s, size_t first, size_t n, int threads) {
+    std::vector<uint64_t> arm0, byte0;
+    measure(_windows.data() + first, n, threads, arm0, byte0);
+    grow(s.win, s.win_cap, n);
+    grow(s.arms, s.arms_cap, (size_t)arm0[n] + 1);
+    grow(s.packed, s.packed_cap, (size_t)byte0[n] + 16);
+    grow(s.off, s.off_cap, n + 1);
+    fill(_windows.data() + first, n, threads, arm0, byte0, s.win, s.arms, s.packed);
+    s.first = first; s.n_win = n; s.n_arms = arm0[n]; s.n_bytes = byte0[n];
+    grow(s.out, s.out_cap, (size_t)hypo_gpu_out_bound(s.win, n, s.arms, s.n_arms) + 16);
+}
+
+void WindowBatch::scatter_chunk(const Slot& s) {
 #pragma omp parallel for schedule(static, 512)
-    for (size_t i = 0; i < n; ++i)
-        _windows[i]->set_consensus(std::string(_out.data() + _off[i], _out.data() + _off[i + 1]));
+    for (size_t i = 0; i < s.n_win; ++i)
+        _windows[s.first + i]->set_consensus(std::string(s.out + s.off[i], s.out + s.off[i + 1]));
+}
+
+void WindowBatch::run(size_t chunk_windows) {
+    _timing = Timing();
+    const size_t n = _windows.size();
+    if (n == 0) return;
+    const double t_begin = omp_get_wtime();
+    const int threads = omp_get_max_threads();
+    if (chunk_windows == 0) chunk_windows = (size_t)131072 * (size_t)std::max(1, hypo_gpu_device_count());
+    const size_t n_chunks = (n + chunk_windows - 1) / chunk_windows;
+    auto chunk_lo = [&](size_t k) { return std::min(n, k * chunk_windows); };
+
+    double t0 = omp_get_wtime();
+    pack_chunk(_slot[0], 0, chunk_lo(1), threads);
+    _timing.pack += omp_get_wtime() - t0;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        Slot& cur = _slot[k & 1];
+        int rc = HYPO_OK;
+        std::string err;
+        double dev_sec = 0;
+        // the device call of chunk k on its own thread ...
+        std::thread worker([&]() {
+            const double d0 = omp_get_wtime();
+            rc = hypo_gpu_consensus_batch(cur.win, cur.n_win, cur.arms, cur.n_arms, cur.packed, cur.n_bytes, cur.out,
+                                          cur.out_cap, cur.off);
+            if (rc != HYPO_OK) err = hypo_gpu_last_error();
+            dev_sec = omp_get_wtime() - d0;
+        });
+        // ... while this thread scatters chunk k-1 and then packs chunk k+1 into the slot that frees
+        if (k > 0) {
+            t0 = omp_get_wtime();
+            scatter_chunk(_slot[(k - 1) & 1]);
+            _timing.scatter += omp_get_wtime() - t0;
+        }
+        if (k + 1 < n_chunks) {
+            t0 = omp_get_wtime();
+            pack_chunk(_slot[(k + 1) & 1], chunk_lo(k + 1), chunk_lo(k + 2) - chunk_lo(k + 1), threads);
+            _timing.pack += omp_get_wtime() - t0;
+        }
+        worker.join();
+        _timing.device += dev_sec;
+        if (rc != HYPO_OK) {
+            fprintf(stderr, "[Hypo::GPU] Error: POA of windows: %s\n", err.c_str());
+            exit(1);
+        }
+    }
+    t0 = omp_get_wtime();
+    scatter_chunk(_slot[(n_chunks - 1) & 1]);
+    _timing.scatter += omp_get_wtime() - t0;
+    _timing.chunks = n_chunks;
+    _timing.total = omp_get_wtime() - t_begin;
 }
 
 }  // namespace hypo

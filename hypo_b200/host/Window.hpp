@@ -116,6 +116,18 @@ public:
     }
     WindowType get_type() const { return _wtype; }
     const PackedSeq<4>& draft() const { return _draft; }
+    // Read-only views for the batch packer (the reference keeps these containers private,
+    // include/Window.hpp:130-134; INTEGRATION.md lists the accessors its Window needs).
+    template <class F>
+    void for_each_arm(F&& f) const {   // container order: internal, prefix, suffix
+        for (const auto& a : _internal_arms) f(a);
+        for (const auto& a : _pre_arms) f(a);
+        for (const auto& a : _suf_arms) f(a);
+    }
+    void counts(uint32_t& n_internal, uint32_t& n_pre, uint32_t& n_suf, uint32_t& n_empty) const {
+        n_internal = (uint32_t)_internal_arms.size(); n_pre = (uint32_t)_pre_arms.size();
+        n_suf = (uint32_t)_suf_arms.size(); n_empty = _num_empty;
+    }
 
     friend std::ostream& operator<<(std::ostream&, const Window&);
     friend class WindowBatch;

@@ -1,6 +1,7 @@
 // WindowStream.cpp — see WindowStream.hpp.
 #include "WindowStream.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <istream>
 #include <ostream>
@@ -29,7 +30,7 @@ void chomp(std::string& s) {
 }  // namespace
 
 bool WindowStream::read(std::istream& in, std::string* err) {
-    contig.clear(); regions.clear(); windows.clear(); recorded.clear();
+    contig.clear(); regions.clear(); windows.clear(); recorded.clear(); declared_regions = 0;
     std::string line;
     size_t ln = 0;
     uint64_t declared = 0;
@@ -81,15 +82,19 @@ bool WindowStream::read(std::istream& in, std::string* err) {
         recorded.push_back(cons);
         regions.push_back(std::move(r));
     }
-    if (have_count && declared != regions.size())
+    // The header announces _reg_type.size() - 1 regions, but with long reads the regions a LONG
+    // pseudo-window swallowed (reference src/Contig.cpp:292-343: null window pointers) are not printed
+    // (:424-451 has no branch for them): fewer region records than announced is the reference's own format.
+    if (have_count && declared < regions.size())
         return fail(err, "header announces " + std::to_string(declared) + " regions, file holds " +
                              std::to_string(regions.size()), ln);
+    declared_regions = have_count ? declared : regions.size();
     return true;
 }
 
 void WindowStream::write(std::ostream& os, bool recorded_consensus) const {
     os << ">" << contig << std::endl;
-    os << "#" << regions.size() << std::endl;
+    os << "#" << std::max<uint64_t>(declared_regions, regions.size()) << std::endl;
     for (const Region& r : regions) {
         os << "==========(" << r.beg << "-" << r.end << ")\t" << r.type << "\t";
         if (r.window < 0) {

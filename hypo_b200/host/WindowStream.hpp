@@ -51,6 +51,7 @@ public:
     uint64_t polished_bp() const;   // sum of Window::get_window_len()
 
     std::string contig;
+    uint64_t declared_regions = 0;   // the "#n" line (can exceed regions.size(), see read())
     std::vector<Region> regions;
     std::vector<std::unique_ptr<Window>> windows;
     std::vector<std::string> recorded;

@@ -337,6 +337,50 @@ int hypo_host_run(const int8_t scores[6], int device, const HypoWindowDesc* win,
     return HYPO_OK;
 }
 
+// ---- the plugin call a maintainer makes, for bench.py: hypo::Window objects in, consensus strings in the
+// same objects out (pack + copies + kernels + scatter), reference src/Hypo.cpp:236-248 ----------------
+struct HostWindows {
+    std::vector<std::unique_ptr<hypo::Window>> ws;
+    hypo::WindowBatch batch;   // kept: its page-locked buffer sets are reused from step to step
+};
+
+void* hypo_host_windows_create(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms,
+                               const uint8_t* packed) {
+    HostWindows* h = new HostWindows;
+    h->ws = build_windows(win, n_win, arms, packed);
+    return h;
+}
+
+void hypo_host_windows_free(void* h) { delete static_cast<HostWindows*>(h); }
+
+// One pass: every window through WindowBatch::run (hypo_gpu_init / hypo_gpu_init_multi must have been
+// called).  timing[0..4] = pack, device call, scatter, total seconds, chunks.
+int hypo_host_windows_run(void* hp, uint64_t chunk_windows, double timing[5]) {
+    HostWindows& h = *static_cast<HostWindows*>(hp);
+    h.batch.clear();
+    h.batch.reserve(h.ws.size());
+    for (auto& w : h.ws) h.batch.add(w.get());
+    h.batch.run((size_t)chunk_windows);
+    const hypo::WindowBatch::Timing& t = h.batch.last_timing();
+    if (timing) { timing[0] = t.pack; timing[1] = t.device; timing[2] = t.scatter; timing[3] = t.total; timing[4] = (double)t.chunks; }
+    return HYPO_OK;
+}
+
+// Concatenated Window::get_consensus() of all windows; returns the bytes needed (nothing is written
+// beyond out_cap).
+uint64_t hypo_host_windows_consensus(void* hp, char* out, uint64_t out_cap, uint64_t* out_off) {
+    HostWindows& h = *static_cast<HostWindows*>(hp);
+    uint64_t pos = 0;
+    for (size_t w = 0; w < h.ws.size(); ++w) {
+        const std::string c = h.ws[w]->get_consensus();
+        if (out_off) out_off[w] = pos;
+        if (out && pos + c.size() <= out_cap) memcpy(out + pos, c.data(), c.size());
+        pos += c.size();
+    }
+    if (out_off) out_off[h.ws.size()] = pos;
+    return pos;
+}
+
 // ---- window streams in the reference's inspect-file format (WindowStream.hpp) ---------------------
 
 // Writes a flat batch as one contig's inspect file: every window preceded by a short strong region,

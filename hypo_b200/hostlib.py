@@ -38,6 +38,14 @@ def lib():
         L.hypo_host_run.restype = C.c_int
         L.hypo_host_run.argtypes = [C.POINTER(C.c_int8), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_void_p]
+        L.hypo_host_windows_create.restype = C.c_void_p
+        L.hypo_host_windows_create.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.hypo_host_windows_free.restype = None
+        L.hypo_host_windows_free.argtypes = [C.c_void_p]
+        L.hypo_host_windows_run.restype = C.c_int
+        L.hypo_host_windows_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
+        L.hypo_host_windows_consensus.restype = C.c_uint64
+        L.hypo_host_windows_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.hypo_host_inspect_write.restype = C.c_int
         L.hypo_host_inspect_write.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]
@@ -89,6 +97,46 @@ def host_run(batch: WindowBatch, scores: Sequence[int] = (5, -4, -8, 3, -5, -4),
     if rc != 0:
         raise HypoGpuError(rc, "hypo_host_run failed")
     return split_consensus(out, off)
+
+
+class HostWindows:
+    """hypo::Window objects (built through the mirror's public add_* API) that are polished in place by
+    WindowBatch::run - pack, copies, kernels and scatter, chunked and double-buffered: the call a
+    maintainer makes instead of the OpenMP loop of reference src/Hypo.cpp:236-248."""
+
+    def __init__(self, batch: WindowBatch):
+        self.n_win = batch.n_win
+        self._h = lib().hypo_host_windows_create(batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data,
+                                                 batch.packed.ctypes.data)
+
+    def run(self, chunk_windows: int = 0) -> dict:
+        t = (C.c_double * 5)()
+        rc = lib().hypo_host_windows_run(self._h, int(chunk_windows), t)
+        if rc != 0:
+            raise HypoGpuError(rc, "hypo_host_windows_run failed")
+        return {"pack_s": t[0], "device_s": t[1], "scatter_s": t[2], "total_s": t[3], "chunks": int(t[4])}
+
+    def consensus_bytes(self):
+        n = int(lib().hypo_host_windows_consensus(self._h, None, 0, None))
+        out = np.empty(n + 1, np.uint8)
+        off = np.zeros(self.n_win + 1, np.uint64)
+        lib().hypo_host_windows_consensus(self._h, out.ctypes.data, n, off.ctypes.data)
+        return out[:n], off
+
+    def consensus(self) -> List[str]:
+        out, off = self.consensus_bytes()
+        return split_consensus(out, off)
+
+    def close(self):
+        if self._h:
+            lib().hypo_host_windows_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def long_arm_filter(batch: WindowBatch) -> np.ndarray:

@@ -27,8 +27,12 @@ ABI_SYMBOLS = (
     "hypo_gpu_last_fail_hist",
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
+    "hypo_gpu_last_cells",
+    "hypo_gpu_issue_rate",
     "hypo_gpu_launch_count",
     "hypo_gpu_last_error",
+    "hypo_gpu_host_alloc",
+    "hypo_gpu_host_free",
     "hypo_gpu_shutdown",
     "hypo_gpu_abi_version",
 )
@@ -80,6 +84,9 @@ def lib():
                                               C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
         L.hypo_gpu_last_timing.restype = C.c_int
         L.hypo_gpu_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.hypo_gpu_last_cells.restype = C.c_uint64
+        L.hypo_gpu_issue_rate.restype = C.c_int
+        L.hypo_gpu_issue_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.hypo_gpu_launch_count.restype = C.c_uint64
         L.hypo_gpu_last_error.restype = C.c_char_p
         L.hypo_gpu_shutdown.restype = None
@@ -175,6 +182,21 @@ def last_timing() -> Tuple[float, int, List[int]]:
     tiers = (C.c_uint32 * 8)()
     lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
     return float(ms.value), int(n.value), [int(x) for x in tiers]
+
+
+def last_cells() -> int:
+    """DP cells (sum of (nodes + 1) x (read length + 1) over all fills) of the last batch call."""
+    return int(lib().hypo_gpu_last_cells())
+
+
+ISSUE_OPS = ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "VIADDMNMX.S32", "SHFL.UP", "PRMT", "IADD")
+
+
+def issue_rate(op: int) -> float:
+    """Measured issue rate of one instruction of the fill's inner loop, 10^9 warp instructions / s."""
+    v = C.c_double(0)
+    _check(lib().hypo_gpu_issue_rate(int(op), C.byref(v)))
+    return float(v.value)
 
 
 def last_fail_hist() -> List[int]:

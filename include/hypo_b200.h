@@ -198,11 +198,31 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
  */
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]);
 
+/*
+ * Measurement hooks for the compute roofline: the DP cells of the most recent batch
+ * call - sum over windows and reads of (nodes + 1) x (read length + 1), the size of the matrix the
+ * reference fills for that read (external/spoa/src/sisd_alignment_engine.cpp:52-75) - and the rate the
+ * device sustains for one instruction of the fill's inner loop, measured on the spot in 10^9 warp
+ * instructions per second over the whole GPU:
+ *   op 0 VIADDMNMX.S16x2 (__viaddmax_s16x2)   1 VIMNMX3.S16x2 (__vimax3_s16x2)   2 VIADDMNMX.S32
+ *      3 SHFL.UP                              4 PRMT                             5 IADD
+ */
+uint64_t hypo_gpu_last_cells(void);
+int hypo_gpu_issue_rate(int op, double* g_warp_instr_per_s);
+
 /* Number of kernel launches issued by this library since hypo_gpu_init. */
 uint64_t hypo_gpu_launch_count(void);
 
 /* Thread-local message describing the last failure ("" if none). */
 const char* hypo_gpu_last_error(void);
+
+/*
+ * Page-locked host memory for the batch buffers (copies from it run at full PCIe speed and
+ * asynchronously).  Optional: every entry point accepts ordinary memory as well.  Valid until
+ * hypo_gpu_host_free; independent of init / shutdown.
+ */
+void* hypo_gpu_host_alloc(uint64_t bytes);
+void hypo_gpu_host_free(void* p);
 
 /* Releases device memory and streams. */
 void hypo_gpu_shutdown(void);

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Regenerates tests/golden/cli_{short,long}_60kb.inspect.gz: window streams captured from the REFERENCE
+# command-line program itself (built from /root/reference by tools/capture/build_reference_cli.sh; the
+# per-window dump is the reference's own Contig::generate_inspect_file, src/Contig.cpp:368-453) on
+# seeded synthetic genomes (tools/capture/make_dataset.py).  Run in the authoring container only
+# (needs /root/reference); the fixtures travel, the reference does not.
+set -euo pipefail
+HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd); W=${1:-/tmp/hypo_capture}
+"$ROOT/tools/capture/build_reference_cli.sh" /tmp/hypo_cli
+python "$ROOT/tools/capture/make_dataset.py" "$W/short" --size 60000 --cov 40 --seed 3
+"$ROOT/tools/capture/capture.sh" "$W/short" 8
+python "$ROOT/tools/capture/make_dataset.py" "$W/long" --size 60000 --cov 30 --long 25 --draft-err 0.04 --sr-gaps 0.15 --seed 5
+"$ROOT/tools/capture/capture.sh" "$W/long" 8
+gzip -9 -n -c "$W/short/aux/inspect_ctg1.txt" > "$HERE/cli_short_60kb.inspect.gz"
+gzip -9 -n -c "$W/long/aux/inspect_ctg1.txt" > "$HERE/cli_long_60kb.inspect.gz"

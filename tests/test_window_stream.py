@@ -55,11 +55,47 @@ def test_malformed_stream_is_rejected(tmp_path):
     p.write_text(">c\n#1\n==========(0-3)\tOTH\t1\t0\t0\t0\n++\tACGT\n")
     with pytest.raises(ValueError):
         InspectStream(str(p))
-    p.write_text(">c\n#2\n==========(0-3)\tSR\t0\t0\t0\t0\n++\tACGT\n++\tACGT\n")
+    p.write_text(">c\n#0\n==========(0-3)\tSR\t0\t0\t0\t0\n++\tACGT\n++\tACGT\n")
     with pytest.raises(ValueError):
         InspectStream(str(p))
+    # more regions announced than printed is the reference's own format once long reads are used
+    # (regions swallowed by a LONG pseudo-window are not printed, reference src/Contig.cpp:424-451)
+    p.write_text(">c\n#2\n==========(0-3)\tSR\t0\t0\t0\t0\n++\tACGT\n++\tACGT\n")
+    assert InspectStream(str(p)).n_regions == 1
     with pytest.raises(ValueError):
         InspectStream(str(tmp_path / "missing.txt"))
+
+
+# Streams captured from the reference COMMAND-LINE PROGRAM (tests/golden/make_cli_streams.sh): every window
+# the real pipeline made of a seeded 60 kb genome - solid-k-mer segmentation, arms cut out of aligned
+# reads, pruning - with the consensus the reference computed for it.
+CLI_STREAMS = (("cli_short_60kb.inspect.gz", 3443, 1720, 0), ("cli_long_60kb.inspect.gz", 2871, 1443, 25))
+
+
+def _cli_path(tmp_path, name):
+    p = tmp_path / name.replace(".gz", ".txt")
+    p.write_bytes(gzip.open(os.path.join(HERE, "golden", name)).read())
+    return str(p)
+
+
+@pytest.mark.parametrize("name,n_regions,n_windows,n_long", CLI_STREAMS)
+def test_cli_captured_streams_pin_the_oracle(tmp_path, name, n_regions, n_windows, n_long):
+    s = InspectStream(_cli_path(tmp_path, name))
+    assert (s.n_regions, s.n_windows) == (n_regions, n_windows)
+    assert int((s.batch.win["wtype"] == 1).sum()) == n_long
+    got, _ = oracle_consensus(s.batch, DEFAULT_SCORES)
+    assert got == s.recorded
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_regions,n_windows,n_long", CLI_STREAMS)
+def test_replay_cli_captured_streams_on_the_gpu(tmp_path, name, n_regions, n_windows, n_long):
+    path = _cli_path(tmp_path, name)
+    s = InspectStream(path)
+    out = str(tmp_path / "replayed.txt")
+    bad, sec = s.replay(DEFAULT_SCORES, 0, out)
+    assert bad == 0 and sec > 0
+    assert open(out, "rb").read() == open(path, "rb").read()   # byte-identical re-dump
 
 
 @pytest.mark.gpu
