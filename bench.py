@@ -112,11 +112,11 @@ def make_batch(a, seed, n_windows=None):
     from hypo_b200.batch import concat_batches
     from hypo_b200.hostlib import synth_batch
     n_windows = a.windows if n_windows is None else n_windows
-    if a.stream:
+    if getattr(a, "stream", None):
         b = load_streams(a.stream, a.repeat)
         return b if n_windows >= b.n_win or n_windows == a.windows else b.select(np.arange(n_windows))
     if a.mix != "pipeline":
-        return synth_batch(seed, n_windows, a.length, a.arms, a.kind, a.err, wtype=a.wtype)
+        return synth_batch(seed, n_windows, a.length, a.arms, a.kind, a.err, wtype=getattr(a, "wtype", 0))
     parts, k = [], 0
     for ln, wl in PIPELINE_LEN:
         for na, wa in PIPELINE_ARMS:
