@@ -284,7 +284,7 @@ def main():
     # ---- the window set (identical on every rank) and this rank's range of it ----------------
     full = make_batch(a, a.seed)
     w_lo, w_hi = shard_range(full, rank, world)
-    batch = full.select(np.arange(w_lo, w_hi)) if world > 1 else full
+    batch = full.select(np.arange(w_lo, w_hi)).compact() if world > 1 else full
     n_win, n_arms = batch.n_win, batch.n_arms
     bp_total = full.polished_bp
     bound = batch.out_bound()

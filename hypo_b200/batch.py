@@ -135,6 +135,23 @@ class WindowBatch:
         win["first_arm"] = new_first
         return WindowBatch(win, arms, self.packed, dict(self.meta))
 
+    def compact(self) -> "WindowBatch":
+        """Re-bases the descriptors onto the smallest slice of the packed slab that holds every byte they
+        reference (a contiguous range of a window-ordered batch then carries only its own bytes)."""
+        if self.n_win == 0:
+            return self
+        a_end = self.arms["off"].astype(np.int64) + (self.arms["len"].astype(np.int64) + 3) // 4
+        d_end = self.win["draft_off"].astype(np.int64) + (self.win["draft_len"].astype(np.int64) + 1) // 2
+        used = self.arms["len"] > 0
+        lo = int(min(self.win["draft_off"].min(), self.arms["off"][used].min() if used.any() else 1 << 62))
+        hi = int(max(d_end.max(), a_end[used].max() if used.any() else 0))
+        win, arms = self.win.copy(), self.arms.copy()
+        win["draft_off"] -= lo
+        arms["off"][used] -= lo
+        arms["off"][~used] = 0
+        packed = np.concatenate([self.packed[lo:hi], np.zeros(16, np.uint8)])
+        return WindowBatch(win, arms, packed, dict(self.meta))
+
     def spec(self, w: int) -> WindowSpec:
         d = self.win[w]
         a0 = int(d["first_arm"])

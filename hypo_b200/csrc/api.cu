@@ -178,6 +178,8 @@ struct Ctx {
     cudaEvent_t tev0[kPasses][kNumTiers] = {}, tev1[kPasses][kNumTiers] = {};
     DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
     DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp, gather;
+    DevBuf st_reg, st_contig, st_draft, st_doff, st_len, st_pos, st_out, st_cons, st_coff;   // output stitching
+    uint64_t resident_windows = 0;               // out_compact / out_off hold the result of this many windows
     void* pinned_ctrl = nullptr;                 // DevCtrl mirror + a few words
     float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
     uint32_t poa_launches = 0;
@@ -323,6 +325,51 @@ __global__ void listmax_kernel(const WinDesc* __restrict__ win, const WinStat* _
     }
 }
 
+// Output stitching (reference src/Contig.cpp:345-366).  Pass 1: length of every region; pass 2 (after
+// an exclusive scan): one warp per region copies draft bases (unpacked from 4-bit codes) or consensus bytes.
+struct RegionDesc {
+    uint64_t src;
+    uint32_t len, window;
+};
+static_assert(sizeof(RegionDesc) == 16, "ABI layout");
+
+__global__ void region_len_kernel(const RegionDesc* __restrict__ reg, uint64_t n_reg,
+                                  const uint64_t* __restrict__ cons_off, uint64_t n_win,
+                                  uint64_t* __restrict__ len, uint32_t* __restrict__ bad) {
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reg) return;
+    const RegionDesc d = reg[r];
+    uint64_t l = d.len;
+    if (d.window != HYPO_REGION_DRAFT) {
+        if (d.window >= n_win) { atomicAdd(bad, 1u); l = 0; }
+        else l = cons_off[d.window + 1] - cons_off[d.window];
+    }
+    len[r] = l;
+}
+
+__global__ void stitch_kernel(const RegionDesc* __restrict__ reg, uint64_t n_reg, const uint32_t* __restrict__ reg_contig,
+                              const uint8_t* __restrict__ drafts, const uint64_t* __restrict__ draft_off,
+                              const char* __restrict__ cons, const uint64_t* __restrict__ cons_off,
+                              const uint64_t* __restrict__ pos, char* __restrict__ out) {
+    const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_reg) return;
+    const int lane = threadIdx.x & 31;
+    const RegionDesc d = reg[r];
+    char* dst = out + pos[r];
+    if (d.window == HYPO_REGION_DRAFT) {
+        const uint8_t* src = drafts + draft_off[reg_contig[r]];
+        for (uint64_t i = lane; i < d.len; i += 32) {
+            const uint64_t p = d.src + i;
+            const int v = (src[p >> 1] >> ((p & 1) ? 0 : 4)) & 15;
+            dst[i] = "ACGTN"[v > 4 ? 4 : v];
+        }
+    } else {
+        const char* src = cons + cons_off[d.window];
+        const uint64_t l = cons_off[d.window + 1] - cons_off[d.window];
+        for (uint64_t i = lane; i < l; i += 32) dst[i] = src[i];
+    }
+}
+
 // One warp per window: gather scratch consensus into the compact, window-ordered output.
 __global__ void gather_kernel(const char* __restrict__ scratch, const uint64_t* __restrict__ pos,
                               const uint32_t* __restrict__ len, const uint64_t* __restrict__ off,
@@ -400,7 +447,7 @@ inline void merge_max(TierMax& e, const TierMax& r) {
 // successor's list, so consecutive launches need no host round trip; the host only looks again before a
 // bound-driven tier (whose capacities come from maxima it has to know) and at the end.
 int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms,
-                const uint8_t* d_packed, char* d_out, const uint64_t* d_out_pos, uint32_t* d_out_len,
+                const uint8_t* d_packed, uint64_t packed_end, char* d_out, const uint64_t* d_out_pos, uint32_t* d_out_len,
                 const WinStat* d_stats, cudaStream_t stream) {
     if (pass == 0) {
         g.poa_ms = 0.f;
@@ -531,6 +578,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.gws = (uint8_t*)g.gws.p; P.g_slot = g_slot;
         P.paths = need_paths ? (uint16_t*)g.paths.p : nullptr; P.p_slot = p_slot;
         P.caps = caps;
+        P.packed_end = packed_end;
         P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
         P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
         CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
@@ -584,6 +632,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
     cudaStream_t s = g.stream;
     const uint64_t n_win = sh.w1 - sh.w0;
     sh.total = 0;
+    g.resident_windows = 0;
     if (n_win == 0) return HYPO_OK;
     const uint64_t n_arms = sh.a1 - sh.a0, n_bytes = sh.b1 - sh.b0;
 
@@ -664,7 +713,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
         // ---- head: kernels (the tail is still being copied) -----------------------------------------
         const uint64_t head_bytes = *h64;
         if (head_bytes > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
-        if (int rc = stage_tiers(g, 0, d_win, w_s, d_arms, d_packed, (char*)g.out_scratch.p, d_pos,
+        if (int rc = stage_tiers(g, 0, d_win, w_s, d_arms, d_packed, sh.b1, (char*)g.out_scratch.p, d_pos,
                                  (uint32_t*)g.out_len.p, d_stats, s))
             return rc;
         // ---- tail -----------------------------------------------------------------------------------
@@ -682,7 +731,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
         CUDA_TRY(cudaStreamSynchronize(s));
         if (int rc = check_bad(g, false)) return rc;
         if (*h64 > scratch_cap) return fail(HYPO_E_CAPACITY, "internal: scratch bound exceeded");
-        if (int rc = stage_tiers(g, 1, d_win + w_s, n_tail, d_arms, d_packed, (char*)g.out_scratch.p,
+        if (int rc = stage_tiers(g, 1, d_win + w_s, n_tail, d_arms, d_packed, sh.b1, (char*)g.out_scratch.p,
                                  d_pos + w_s, (uint32_t*)g.out_len.p + w_s, d_stats + w_s, s))
             return rc;
     } else {
@@ -705,7 +754,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
         if (int rc = check_bad(g, false)) return rc;
         CUDA_TRY(g.out_scratch.reserve(*h64 + 16));
         CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
-        if (int rc = stage_tiers(g, 0, d_win, n_win, d_arms, d_packed, (char*)g.out_scratch.p, d_pos,
+        if (int rc = stage_tiers(g, 0, d_win, n_win, d_arms, d_packed, sh.b1, (char*)g.out_scratch.p, d_pos,
                                  (uint32_t*)g.out_len.p, d_stats, s))
             return rc;
     }
@@ -727,6 +776,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
                                                                       (char*)g.out_compact.p, n_win);
     G.launches += 3;
     CUDA_TRY(cudaGetLastError());
+    g.resident_windows = n_win;
     return HYPO_OK;
 }
 
@@ -821,7 +871,9 @@ void release_ctx(Ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->win, &c->arms, &c->packed, &c->out_scratch, &c->out_pos, &c->out_len, &c->out_off,
-                      &c->out_compact, &c->stats, &c->lists, &c->ctrl, &c->H, &c->gws, &c->paths, &c->cub_tmp, &c->gather};
+                      &c->out_compact, &c->stats, &c->lists, &c->ctrl, &c->H, &c->gws, &c->paths, &c->cub_tmp, &c->gather,
+                      &c->st_reg, &c->st_contig, &c->st_draft, &c->st_doff, &c->st_len, &c->st_pos, &c->st_out, &c->st_cons,
+                      &c->st_coff};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_ctrl) cudaFreeHost(c->pinned_ctrl);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1049,7 +1101,7 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
     CUDA_TRY(fetch_ctrl(g, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (int rc = check_bad(g, false)) return rc;
-    return stage_tiers(g, 0, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, d_packed, d_out, d_out_pos,
+    return stage_tiers(g, 0, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, d_packed, packed_bytes, d_out, d_out_pos,
                        d_out_len, (const WinStat*)g.stats.p, s);
 }
 
@@ -1112,6 +1164,100 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
         for (uint64_t w = sh[i].w0; w < sh[i].w1; ++w) out_off[w] += b;
     }
     out_off[n_win] = total;
+    return HYPO_OK;
+}
+
+int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uint64_t* contig_first_region,
+                    uint64_t n_contigs, const uint8_t* drafts, const uint64_t* draft_off, uint64_t draft_bytes,
+                    const char* cons, const uint64_t* cons_off, uint64_t n_win, char* out, uint64_t out_cap,
+                    uint64_t* out_off) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err.clear();
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (!out_off || (!regions && n_regions) || !contig_first_region || (!draft_off && n_contigs))
+        return fail(HYPO_E_ARG, "NULL input buffer");
+    for (uint64_t c = 0; c <= n_contigs; ++c) out_off[c] = 0;
+    if (n_regions == 0 || n_contigs == 0) return HYPO_OK;
+    if (contig_first_region[0] != 0 || contig_first_region[n_contigs] != n_regions)
+        return fail(HYPO_E_ARG, "contig_first_region must run from 0 to n_regions");
+    Ctx& g = *G.dev[0];
+    CUDA_TRY(cudaSetDevice(g.device));
+    cudaStream_t s = g.stream;
+    // host-side validation of the draft ranges + the contig of every region
+    std::vector<uint32_t> reg_contig(n_regions);
+    for (uint64_t c = 0; c < n_contigs; ++c) {
+        if (contig_first_region[c] > contig_first_region[c + 1] || draft_off[c] > draft_bytes)
+            return fail(HYPO_E_ARG, "contig %llu: region / draft offsets out of order", (unsigned long long)c);
+        const uint64_t avail = 2 * (draft_bytes - draft_off[c]);
+        for (uint64_t r = contig_first_region[c]; r < contig_first_region[c + 1]; ++r) {
+            reg_contig[r] = (uint32_t)c;
+            if (regions[r].window == HYPO_REGION_DRAFT && regions[r].src + regions[r].len > avail)
+                return fail(HYPO_E_ARG, "region %llu reads beyond the draft of contig %llu", (unsigned long long)r,
+                            (unsigned long long)c);
+        }
+    }
+    const char* d_cons;
+    const uint64_t* d_coff;
+    if (cons) {
+        if (!cons_off) return fail(HYPO_E_ARG, "cons_off == NULL");
+        CUDA_TRY(g.st_cons.reserve(cons_off[n_win] + 16));
+        CUDA_TRY(g.st_coff.reserve(sizeof(uint64_t) * (n_win + 1)));
+        if (cons_off[n_win]) CUDA_TRY(cudaMemcpyAsync(g.st_cons.p, cons, cons_off[n_win], cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(g.st_coff.p, cons_off, sizeof(uint64_t) * (n_win + 1), cudaMemcpyHostToDevice, s));
+        d_cons = (const char*)g.st_cons.p;
+        d_coff = (const uint64_t*)g.st_coff.p;
+    } else {
+        if (G.n_dev != 1 || g.resident_windows != n_win || n_win == 0)
+            return fail(HYPO_E_ARG, "cons == NULL needs the result of the last hypo_gpu_consensus_batch call (%llu windows, "
+                                    "one driven device) still resident; it holds %llu",
+                        (unsigned long long)n_win, (unsigned long long)g.resident_windows);
+        d_cons = (const char*)g.out_compact.p;
+        d_coff = (const uint64_t*)g.out_off.p;
+    }
+    CUDA_TRY(g.st_reg.reserve(sizeof(RegionDesc) * n_regions));
+    CUDA_TRY(g.st_contig.reserve(sizeof(uint32_t) * n_regions));
+    CUDA_TRY(g.st_draft.reserve(draft_bytes + 16));
+    CUDA_TRY(g.st_doff.reserve(sizeof(uint64_t) * n_contigs));
+    CUDA_TRY(g.st_len.reserve(sizeof(uint64_t) * (n_regions + 1)));
+    CUDA_TRY(g.st_pos.reserve(sizeof(uint64_t) * (n_regions + 1)));
+    CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
+    CUDA_TRY(cudaMemcpyAsync(g.st_reg.p, regions, sizeof(RegionDesc) * n_regions, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.st_contig.p, reg_contig.data(), sizeof(uint32_t) * n_regions, cudaMemcpyHostToDevice, s));
+    if (draft_bytes) CUDA_TRY(cudaMemcpyAsync(g.st_draft.p, drafts, draft_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.st_doff.p, draft_off, sizeof(uint64_t) * n_contigs, cudaMemcpyHostToDevice, s));
+    uint32_t* d_bad = &((DevCtrl*)g.ctrl.p)->bad;
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s));
+    uint64_t* d_len = (uint64_t*)g.st_len.p;
+    uint64_t* d_pos = (uint64_t*)g.st_pos.p;
+    const int tb = 256;
+    region_len_kernel<<<(unsigned)((n_regions + tb - 1) / tb), tb, 0, s>>>((const RegionDesc*)g.st_reg.p, n_regions, d_coff, n_win,
+                                                                         d_len, d_bad);
+    CUDA_TRY(cudaMemsetAsync(d_len + n_regions, 0, sizeof(uint64_t), s));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_pos, n_regions + 1, s));
+    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = g.cub_tmp.cap;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len, d_pos, n_regions + 1, s));
+    uint64_t* h64 = host_words(g);
+    CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_regions, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h64 + 1, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const uint64_t total = h64[0];
+    if (*(uint32_t*)(h64 + 1)) return fail(HYPO_E_ARG, "a region names a window beyond the batch");
+    if (total > out_cap) return fail(HYPO_E_OUT_CAP, "stitched output needs %llu bytes, out_cap is %llu",
+                                     (unsigned long long)total, (unsigned long long)out_cap);
+    CUDA_TRY(g.st_out.reserve(total + 16));
+    stitch_kernel<<<(unsigned)((n_regions * 32 + tb - 1) / tb), tb, 0, s>>>(
+        (const RegionDesc*)g.st_reg.p, n_regions, (const uint32_t*)g.st_contig.p, (const uint8_t*)g.st_draft.p,
+        (const uint64_t*)g.st_doff.p, d_cons, d_coff, d_pos, (char*)g.st_out.p);
+    G.launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (total) CUDA_TRY(cudaMemcpyAsync(out, g.st_out.p, total, cudaMemcpyDeviceToHost, s));
+    // the contigs' starts: position of their first region
+    std::vector<uint64_t> pos_host(n_regions + 1);
+    CUDA_TRY(cudaMemcpyAsync(pos_host.data(), d_pos, sizeof(uint64_t) * (n_regions + 1), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint64_t c = 0; c <= n_contigs; ++c) out_off[c] = pos_host[contig_first_region[c]];
     return HYPO_OK;
 }
 
@@ -1191,7 +1337,7 @@ __global__ void __launch_bounds__(256) issue_kernel(uint32_t* sink, int iters, u
                 else if (kOp == 2) a[k] = (uint32_t)__viaddmax_s32((int)a[k], (int)b, (int)c);
                 else if (kOp == 3) a[k] = __shfl_up_sync(0xffffffffu, a[k], 1);
                 else if (kOp == 4) a[k] = __byte_perm(a[k], b, 0x5432);
-                else a[k] = a[k] + b;
+                else a[k] = a[k] * b + c;
             }
         }
     }

@@ -69,6 +69,7 @@ struct GState {
     uint8_t* gbase;      // tiers L: this warp's arena in global memory
     ArenaLayout L;       // tiers with run-time capacities only
     uint32_t* fail_hist; // diagnostics: why windows were abandoned (may be null)
+    const uint8_t* packed_end;   // end of the readable packed slab (bulk copies stay below it)
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -302,6 +303,12 @@ struct EndCell {
 // rowinfo bits 28-30: every predecessor row lies 1, 2 or 3 rows back (bit d-1 set for distance d;
 // rank 0 without predecessor counts as distance 1: the virtual row 0).  0 = take the general path.
 constexpr int kRowNearShift = 28;
+// How many previous rows the fill keeps in registers (2 or 3).  With two, a pair of rows per trip needs no
+// register rotation at all (row i overwrites the registers of row i-2 after using them).
+#ifndef HYPO_ROW_HIST
+#define HYPO_ROW_HIST 3
+#endif
+constexpr int kRowHist = HYPO_ROW_HIST;
 
 // End cell (reference :276-288,328-340): best last-column score over the candidate rows
 // (NW/ROV: nodes without out-edges, LOV: every node); strictly greater => lowest rank wins.
@@ -417,7 +424,7 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
     } else if (near) {
         if (near & 1u) relax(x, d1.x, d1.left, pf, c.g2);
         if (near & 2u) relax(x, d2.x, d2.left, pf, c.g2);
-        if (near & 4u) relax(x, d3.x, d3.left, pf, c.g2);
+        if (kRowHist >= 3 && (near & 4u)) relax(x, d3.x, d3.left, pf, c.g2);
     } else {
         const uint2 q = relax_far<kSmem, kMulti>(prows, info, rk, Hl, d1, pf, c, bnd_prev);
         x[0] = q.x; x[1] = q.y;
@@ -483,10 +490,15 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
             ri += 8;
             info = M::ld32(ri);
             if (kMulti && bnd_prev) { s1 = bcast16(bnd_prev[rk + 2]); seed = bcast16(bnd_prev[rk + 3]); }
+#if HYPO_ROW_HIST == 2
+            dp_row<kSmem, kMulti>(i0, rk, A, B, B, c, prows, Hl, Hrow, s0, bnd_prev, bnd_next);       // new row -> B
+            dp_row<kSmem, kMulti>(i1, rk + 1, B, A, A, c, prows, Hl, Hrow, s1, bnd_prev, bnd_next);   // new row -> A
+#else
             dp_row<kSmem, kMulti>(i0, rk, A, B, C, c, prows, Hl, Hrow, s0, bnd_prev, bnd_next);       // new row -> C
             dp_row<kSmem, kMulti>(i1, rk + 1, C, A, B, c, prows, Hl, Hrow, s1, bnd_prev, bnd_next);   // new row -> B
             const RowRegs r = A;
             A = B; B = C; C = r;
+#endif
         }
 #else
 #pragma unroll 1
@@ -1109,7 +1121,7 @@ __device__ __noinline__ void build_rows(const GState& st) {
                 if (k == off) first = prow;
                 g.prows[k++] = (uint16_t)prow;
                 const int dist = r + 1 - prow;
-                if (dist >= 1 && dist <= 3) near |= 1u << (dist - 1); else far = true;
+                if (dist >= 1 && dist <= kRowHist) near |= 1u << (dist - 1); else far = true;
             }
             if (far) near = 0u;
             g.fp[r + 1] = (uint16_t)first;
@@ -1258,6 +1270,75 @@ __device__ __forceinline__ char code_to_char(int c) {
     return "ACGTNJO"[c];
 }
 
+#ifdef HYPO_TMA_STAGE
+// ------------------------------------------------------------------------------------------
+// TMA staging of read bytes (north_star: "PackedSeq 2-bit read-segment batches staged from HBM to shared
+// memory via TMA").  While read k is aligned, the packed bytes of read k+1 travel from the slab into a
+// per-warp landing buffer with ONE 1-D bulk copy (cp.async.bulk + mbarrier, issued by lane 0 right after
+// read k has been decoded, so the whole alignment of read k hides the copy); read k+1 is then decoded
+// from shared memory.  The copy covers the 16-byte aligned window around the read's bytes.
+// ------------------------------------------------------------------------------------------
+struct StageCtl {
+    unsigned long long mbar;
+    int32_t pending;     // arm index (low 31 bits) whose bytes are in flight / in the buffer, -1 none
+    uint32_t phase;      // parity of the mbarrier phase the next wait completes
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_init(StageCtl* c) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&c->mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    c->pending = -1;
+    c->phase = 0;
+}
+__device__ __forceinline__ void stage_issue(StageCtl* c, uint8_t* buf, const uint8_t* src, uint32_t bytes) {
+    const uint32_t mb = smem_u32(&c->mbar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(buf)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void stage_wait(StageCtl* c, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "STAGE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra STAGE_DONE;\n"
+        "bra STAGE_WAIT;\n"
+        "STAGE_DONE:\n"
+        "}\n" ::"r"(smem_u32(&c->mbar)), "r"(parity) : "memory");
+}
+template <bool kSmem, int kTier>
+__device__ __forceinline__ uint8_t* stage_buf(const GState& st, StageCtl** ctl, uint32_t* cap) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    if constexpr (kSmem && kTier >= 0) {
+        constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
+        uint8_t* base = smem + (threadIdx.x >> 5) * L.total;
+        *ctl = (StageCtl*)(base + L.stage + L.stage_cap);
+        *cap = L.stage_cap;
+        return base + L.stage;
+    } else {
+        *ctl = nullptr;
+        *cap = 0;
+        return nullptr;
+    }
+}
+// A window starts: a copy the previous window left in flight (it was abandoned, or its last read was
+// longer than the tier) must have landed before the buffer and the barrier are used again.
+template <bool kSmem, int kTier>
+__device__ __forceinline__ void stage_drain(const GState& st) {
+    StageCtl* c; uint32_t cap;
+    if (stage_buf<kSmem, kTier>(st, &c, &cap) == nullptr) return;
+    __syncwarp();
+    if (c->pending >= 0) {
+        stage_wait(c, c->phase);
+        __syncwarp();
+        if (lane_id() == 0) { c->phase ^= 1u; c->pending = -1; }
+    }
+    __syncwarp();
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // One sequence: decode, align, fuse, re-sort.
 // ------------------------------------------------------------------------------------------
@@ -1268,6 +1349,12 @@ struct SeqSrc {
     int nb;                 // 2 or 4 bits per base
     bool head, tail;        // J / O markers
     int type;
+#ifdef HYPO_TMA_STAGE
+    int64_t arm_idx;        // identity of this read (index in the arm table), -1 if it is not an arm
+    int64_t next_idx;       // the read that follows in the window's order (-1: none): staged by TMA
+    const uint8_t* next_bytes;
+    int next_len;
+#endif
 };
 
 template <bool kSmem, bool kOneTile, int kTier, bool kWide>
@@ -1279,6 +1366,32 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
     const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
     if (len > caps.lcap) return give_up(st, kFailLen);
     uint8_t* dst = g.seq + (s.head ? 1 : 0);
+#ifdef HYPO_TMA_STAGE
+    StageCtl* sctl; uint32_t scap;
+    uint8_t* const sbuf = stage_buf<kSmem, kTier>(st, &sctl, &scap);
+    if (sbuf && s.bytes && s.nb == 2) {
+        const int32_t id = (int32_t)(s.arm_idx & 0x7fffffff);
+        if (s.arm_idx >= 0 && sctl->pending == id) {
+            stage_wait(sctl, sctl->phase);   // the bytes were put on their way while the previous read was aligned
+            __syncwarp();
+            decode2(sbuf + ((uintptr_t)s.bytes & 15u), s.len, dst);
+            __syncwarp();
+            if (lane == 0) { sctl->phase ^= 1u; sctl->pending = -1; }
+        } else {
+            decode2(s.bytes, s.len, dst);
+        }
+        __syncwarp();
+        // the read after this one: one bulk copy of the aligned window around its bytes
+        if (s.next_idx >= 0 && lane == 0 && sctl->pending < 0) {
+            const uintptr_t a0 = (uintptr_t)s.next_bytes & ~(uintptr_t)15;
+            const uint32_t nbytes = (uint32_t)((((uintptr_t)s.next_bytes + (uint32_t)(s.next_len + 3) / 4 + 15) & ~(uintptr_t)15) - a0);
+            if (nbytes <= scap && a0 + nbytes <= (uintptr_t)st.packed_end) {
+                stage_issue(sctl, sbuf, (const uint8_t*)a0, nbytes);
+                sctl->pending = (int32_t)(s.next_idx & 0x7fffffff);
+            }
+        }
+    } else
+#endif
     if (s.bytes) {
         if (s.nb == 2) decode2(s.bytes, s.len, dst); else decode4(s.bytes, s.len, dst);
     } else {
@@ -1428,12 +1541,42 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     __syncwarp();
     SeqSrc s;
     s.ascii = nullptr;
+#ifdef HYPO_TMA_STAGE
+    stage_drain<kSmem, kTier>(g);
+    s.arm_idx = -1; s.next_idx = -1; s.next_bytes = nullptr; s.next_len = 0;
+#endif
     if (w.n_internal == 0) {   // draft as backbone only without internal arms (:95-101)
         s.bytes = P.packed + w.draft_off; s.len = w.draft_len; s.nb = 4;
         s.head = true; s.tail = true; s.type = kNW;
         if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     s.nb = 2;
+#ifdef HYPO_TMA_STAGE
+    {
+        // one loop over the reference's order - internal arms (:102-110), prefix arms last to first
+        // (:112-121, kLOV), suffix arms (:123-132, kROV) - so that every read knows its successor
+        const int ni = (int)w.n_internal, np = (int)w.n_pre;
+        auto arm_at = [&](int j) { return j < ni ? j : j < ni + np ? ni + (ni + np - 1 - j) : j; };
+        auto next_nonempty = [&](int j) { while (j < n_arms && a[arm_at(j)].len == 0) ++j; return j; };
+        int j = next_nonempty(0);
+#pragma unroll 1
+        while (j < n_arms) {
+            const int jn = next_nonempty(j + 1);
+            const int k = arm_at(j);
+            s.bytes = P.packed + a[k].off; s.len = a[k].len;
+            s.head = k < ni + np; s.tail = k < ni || k >= ni + np;
+            s.type = k < ni ? kNW : k < ni + np ? kLOV : kROV;
+            s.arm_idx = (int64_t)(w.first_arm + k);
+            s.next_idx = -1;
+            if (jn < n_arms) {
+                const int kn = arm_at(jn);
+                s.next_idx = (int64_t)(w.first_arm + kn); s.next_bytes = P.packed + a[kn].off; s.next_len = a[kn].len;
+            }
+            if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
+            j = jn;
+        }
+    }
+#else
 #pragma unroll 1
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
@@ -1454,6 +1597,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
         if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
+#endif
     // The heaviest bundle rarely depends on WHICH valid order the ranks are in; only then is spoa's
     // exact order derived first.
     if (!bundle_fits(g, ws)) return -2;
@@ -1616,6 +1760,14 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     (void)arena_bytes;
     g.gbase = kSmem ? nullptr : (P.gws + (size_t)gwarp * P.g_slot);
     g.fail_hist = P.fail_hist;
+    g.packed_end = P.packed + P.packed_end;
+#ifdef HYPO_TMA_STAGE
+    {
+        StageCtl* sctl; uint32_t scap;
+        if (stage_buf<kSmem, kTier>(g, &sctl, &scap) && lane == 0) stage_init(sctl);
+        __syncwarp();
+    }
+#endif
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 

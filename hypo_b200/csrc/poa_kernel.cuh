@@ -110,6 +110,7 @@ struct Params {
     uint64_t p_slot;             // elements per slot
     Caps caps;
     int sr_m, sr_n, sr_g, lr_m, lr_n, lr_g;
+    uint64_t packed_end;         // bytes of `packed` that may be read (bulk copies never reach beyond it)
 };
 
 __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -145,6 +146,9 @@ struct ArenaLayout {
     // per-read scratch
     uint32_t colseq;    // u8  [tiles*128] letter code of DP column j (= seq[j-1]); 7 = matches nothing
     uint32_t cur;       // u16 [lcap+1] per position: aligned / resolved node
+    uint32_t stage;     // HYPO_TMA_STAGE: landing buffer of the bulk copy of the NEXT read's packed bytes
+                        // (16-byte aligned window around them), then mbarrier (8), pending arm (4), phase (4)
+    uint32_t stage_cap; // bytes of the landing buffer
     uint32_t total;
     int alslots;
 };
@@ -199,6 +203,13 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     k.o = end;
     L.colseq = k.take((uint32_t)c.tiles * kTileCols);
     L.cur = k.take(2u * (c.lcap + 1));
+#ifdef HYPO_TMA_STAGE
+    L.stage_cap = ((uint32_t)(c.lcap + 3) / 4 + 15u + 15u) & ~15u;   // ceil(lcap / 4) bytes at any alignment
+    L.stage = k.take(L.stage_cap + 16u);
+#else
+    L.stage_cap = 0;
+    L.stage = k.o;
+#endif
     L.total = (k.o + 15u) & ~15u;
     return L;
 }

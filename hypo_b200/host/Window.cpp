@@ -43,9 +43,7 @@ std::ostream& operator<<(std::ostream& os, const Window& wnd) {
     os << wnd._num_internal << "\t" << wnd._num_pre << "\t" << wnd._num_suf << "\t" << wnd._num_empty << std::endl;
     os << "++\t" << wnd._draft.unpack() << std::endl;
     os << "++\t" << wnd._consensus << std::endl;
-    for (const auto& a : wnd._internal_arms) os << a.unpack() << std::endl;
-    for (const auto& a : wnd._pre_arms) os << a.unpack() << std::endl;
-    for (const auto& a : wnd._suf_arms) os << a.unpack() << std::endl;
+    wnd.for_each_arm([&](const BYTE* p, UINT32 n) { os << ArmStore::unpack(p, n) << std::endl; });
     return os;
 }
 
@@ -82,9 +80,8 @@ void measure(Window* const* ws, size_t n, int threads, std::vector<uint64_t>& ar
 #pragma omp parallel for schedule(static, 512) num_threads(threads)
     for (size_t i = 0; i < n; ++i) {
         const Window* w = ws[i];
-        uint64_t bytes = w->draft().data_size();
-        uint64_t arms = 0;
-        w->for_each_arm([&](const PackedSeq<2>& a) { bytes += a.data_size(); ++arms; });
+        uint64_t bytes = w->draft().data_size(), arms = 0;
+        for (int k = 0; k < 3; ++k) { bytes += w->arms(k).bytes.size(); arms += w->arms(k).size(); }
         arm0[i + 1] = arms;
         byte0[i + 1] = bytes;
     }
@@ -92,9 +89,11 @@ void measure(Window* const* ws, size_t n, int threads, std::vector<uint64_t>& ar
 }
 
 // Every window fills its own slice (arms in container order: internal, prefix, suffix).
-void fill(Window* const* ws, size_t n, int threads, const std::vector<uint64_t>& arm0, const std::vector<uint64_t>& byte0,
-          HypoWindowDesc* win, HypoArmDesc* arms, uint8_t* slab) {
-#pragma omp parallel for schedule(static, 512) num_threads(threads)
+// Returns the sum of the windows' output bounds (the rule of hypo_gpu_window_bounds).
+uint64_t fill(Window* const* ws, size_t n, int threads, const std::vector<uint64_t>& arm0, const std::vector<uint64_t>& byte0,
+              HypoWindowDesc* win, HypoArmDesc* arms, uint8_t* slab) {
+    uint64_t bound = 0;
+#pragma omp parallel for schedule(static, 512) num_threads(threads) reduction(+ : bound)
     for (size_t i = 0; i < n; ++i) {
         const Window* w = ws[i];
         uint64_t pos = byte0[i];
@@ -108,16 +107,25 @@ void fill(Window* const* ws, size_t n, int threads, const std::vector<uint64_t>&
         w->counts(d.n_internal, d.n_pre, d.n_suf, d.n_empty);
         d.wtype = w->get_type() == WindowType::LONG ? HYPO_WINDOW_LONG : HYPO_WINDOW_SHORT;
         HypoArmDesc* ad = arms + arm0[i];
-        w->for_each_arm([&](const PackedSeq<2>& a) {
-            ad->off = pos;
-            ad->len = (uint32_t)a.get_seq_size();
-            ad->reserved = 0;
-            memcpy(slab + pos, a.data(), a.data_size());
-            pos += a.data_size();
-            ++ad;
-        });
+        uint64_t bases = 0;
+        for (int k = 0; k < 3; ++k) {   // one copy per kind; the descriptors follow from the lengths
+            const ArmStore& st = w->arms(k);
+            if (st.empty()) continue;
+            memcpy(slab + pos, st.bytes.data(), st.bytes.size());
+            for (UINT32 len : st.len) {
+                ad->off = pos;
+                ad->len = len;
+                ad->reserved = 0;
+                pos += ArmStore::arm_bytes(len);
+                bases += len;
+                ++ad;
+            }
+        }
         win[i] = d;
+        const uint64_t n_arms = arm0[i + 1] - arm0[i];
+        bound += d.wtype == HYPO_WINDOW_LONG ? 2 * bases + d.draft_len + 2 : bases + 2 * n_arms + d.draft_len + 2;
     }
+    return bound;
 }
 
 template <class T>
@@ -155,13 +163,13 @@ void WindowBatch::pack_chunk(Slot& s, size_t first, size_t n, int threads) {
     grow(s.arms, s.arms_cap, (size_t)arm0[n] + 1);
     grow(s.packed, s.packed_cap, (size_t)byte0[n] + 16);
     grow(s.off, s.off_cap, n + 1);
-    fill(_windows.data() + first, n, threads, arm0, byte0, s.win, s.arms, s.packed);
+    const uint64_t bound = fill(_windows.data() + first, n, threads, arm0, byte0, s.win, s.arms, s.packed);
     s.first = first; s.n_win = n; s.n_arms = arm0[n]; s.n_bytes = byte0[n];
-    grow(s.out, s.out_cap, (size_t)hypo_gpu_out_bound(s.win, n, s.arms, s.n_arms) + 16);
+    grow(s.out, s.out_cap, (size_t)bound + 16);
 }
 
-void WindowBatch::scatter_chunk(const Slot& s) {
-#pragma omp parallel for schedule(static, 512)
+void WindowBatch::scatter_chunk(const Slot& s, int threads) {
+#pragma omp parallel for schedule(static, 512) num_threads(threads)
     for (size_t i = 0; i < s.n_win; ++i)
         _windows[s.first + i]->set_consensus(std::string(s.out + s.off[i], s.out + s.off[i + 1]));
 }
@@ -172,9 +180,28 @@ void WindowBatch::run(size_t chunk_windows) {
     if (n == 0) return;
     const double t_begin = omp_get_wtime();
     const int threads = omp_get_max_threads();
-    if (chunk_windows == 0) chunk_windows = (size_t)131072 * (size_t)std::max(1, hypo_gpu_device_count());
-    const size_t n_chunks = (n + chunk_windows - 1) / chunk_windows;
-    auto chunk_lo = [&](size_t k) { return std::min(n, k * chunk_windows); };
+    const int threads_ov = std::max(1, threads - 1);   // while the device thread spins in its synchronisations
+    // Chunk boundaries.  A batch of fewer than 128 K windows per driven device goes in one piece (cutting it
+    // starves the persistent kernels: a few windows per warp leave a long tail).  Otherwise a small first
+    // chunk (64 K windows per device - its pack is the only host work the device cannot hide, 3 ms), then
+    // equal chunks of at most 512 K windows per device, at least two: packing a million windows takes 45 ms
+    // on 16 threads against 540 ms of kernels, so few large chunks keep the per-call costs (copy of a head,
+    // compaction, result copy, kernel tails) small (measured: tools/chunk_sweep.py, profiles/).
+    const size_t ndev = (size_t)std::max(1, hypo_gpu_device_count());
+    std::vector<size_t> cut{0};
+    if (chunk_windows) {
+        while (cut.back() < n) cut.push_back(std::min(n, cut.back() + chunk_windows));
+    } else if (n < 131072 * ndev) {
+        cut.push_back(n);
+    } else {
+        const size_t first = 65536 * ndev;
+        cut.push_back(first);
+        const size_t rest = n - first;
+        const size_t k = rest < 131072 * ndev ? 1 : std::max<size_t>(2, (rest + 524288 * ndev - 1) / (524288 * ndev));
+        for (size_t i = 1; i <= k; ++i) cut.push_back(first + rest * i / k);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    auto chunk_lo = [&](size_t k) { return cut[std::min(k, n_chunks)]; };
 
     double t0 = omp_get_wtime();
     pack_chunk(_slot[0], 0, chunk_lo(1), threads);
@@ -195,12 +222,12 @@ void WindowBatch::run(size_t chunk_windows) {
         // ... while this thread scatters chunk k-1 and then packs chunk k+1 into the slot that frees
         if (k > 0) {
             t0 = omp_get_wtime();
-            scatter_chunk(_slot[(k - 1) & 1]);
+            scatter_chunk(_slot[(k - 1) & 1], threads_ov);
             _timing.scatter += omp_get_wtime() - t0;
         }
         if (k + 1 < n_chunks) {
             t0 = omp_get_wtime();
-            pack_chunk(_slot[(k + 1) & 1], chunk_lo(k + 1), chunk_lo(k + 2) - chunk_lo(k + 1), threads);
+            pack_chunk(_slot[(k + 1) & 1], chunk_lo(k + 1), chunk_lo(k + 2) - chunk_lo(k + 1), threads_ov);
             _timing.pack += omp_get_wtime() - t0;
         }
         worker.join();
@@ -211,7 +238,7 @@ void WindowBatch::run(size_t chunk_windows) {
         }
     }
     t0 = omp_get_wtime();
-    scatter_chunk(_slot[(n_chunks - 1) & 1]);
+    scatter_chunk(_slot[(n_chunks - 1) & 1], threads);
     _timing.scatter += omp_get_wtime() - t0;
     _timing.chunks = n_chunks;
     _timing.total = omp_get_wtime() - t_begin;

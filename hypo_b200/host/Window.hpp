@@ -36,6 +36,31 @@ enum class WindowType : UINT8 { SHORT, LONG };
 class WindowBatch;
 class WindowStream;
 
+// Arms of one kind (internal / prefix / suffix) of one window: PackedSeq<2> bytes back to back + lengths.
+struct ArmStore {
+    std::vector<BYTE> bytes;
+    std::vector<UINT32> len;   // bases per arm
+    size_t size() const { return len.size(); }
+    bool empty() const { return len.empty(); }
+    void add(const PackedSeq<2>& ps) {
+        bytes.insert(bytes.end(), ps.data(), ps.data() + ps.data_size());
+        len.push_back((UINT32)ps.get_seq_size());
+    }
+    void clear() { bytes.clear(); len.clear(); bytes.shrink_to_fit(); len.shrink_to_fit(); }
+    static size_t arm_bytes(UINT32 n) { return (n + 3) / 4; }
+    // f(pointer to the arm's packed bytes, length in bases) for every arm in insertion order
+    template <class F>
+    void for_each(F&& f) const {
+        const BYTE* p = bytes.data();
+        for (UINT32 n : len) { f(p, n); p += arm_bytes(n); }
+    }
+    static std::string unpack(const BYTE* p, UINT32 n) {   // PackedSeq<2>::unpack (reference src/PackedSeq.cpp:231-262)
+        std::string s(n, 'A');
+        for (UINT32 i = 0; i < n; ++i) s[i] = "ACGT"[(p[i >> 2] >> (6 - 2 * (i & 3))) & 3];
+        return s;
+    }
+};
+
 class Window {
 public:
     Window() : _wtype(WindowType::SHORT), _num_internal(0), _num_pre(0), _num_suf(0), _num_empty(0),
@@ -84,19 +109,19 @@ public:
         UINT arm_len = (UINT)ps.get_seq_size();
         ++_num_pre;
         if (arm_len > _longest_pre_len) _longest_pre_len = arm_len;
-        _pre_arms.emplace_back(ps);
+        _pre_arms.add(ps);
     }
     void add_suffix(const PackedSeq<2>& ps) {
         if (!accept(ps)) return;
         UINT arm_len = (UINT)ps.get_seq_size();
         ++_num_suf;
         if (arm_len > _longest_suf_len) _longest_suf_len = arm_len;
-        _suf_arms.emplace_back(ps);
+        _suf_arms.add(ps);
     }
     void add_internal(const PackedSeq<2>& ps) {
         if (!accept(ps)) return;
         ++_num_internal;
-        _internal_arms.emplace_back(ps);
+        _internal_arms.add(ps);
     }
     void add_empty() { ++_num_empty; }
 
@@ -111,19 +136,19 @@ public:
         _num_suf = 0;
         _pre_arms.clear();
         _suf_arms.clear();
-        _pre_arms.shrink_to_fit();
-        _suf_arms.shrink_to_fit();
     }
     WindowType get_type() const { return _wtype; }
     const PackedSeq<4>& draft() const { return _draft; }
     // Read-only views for the batch packer (the reference keeps these containers private,
     // include/Window.hpp:130-134; INTEGRATION.md lists the accessors its Window needs).
+    // f(packed bytes, length in bases) for every arm, container order: internal, prefix, suffix
     template <class F>
-    void for_each_arm(F&& f) const {   // container order: internal, prefix, suffix
-        for (const auto& a : _internal_arms) f(a);
-        for (const auto& a : _pre_arms) f(a);
-        for (const auto& a : _suf_arms) f(a);
+    void for_each_arm(F&& f) const {
+        _internal_arms.for_each(f);
+        _pre_arms.for_each(f);
+        _suf_arms.for_each(f);
     }
+    const ArmStore& arms(int kind) const { return kind == 0 ? _internal_arms : kind == 1 ? _pre_arms : _suf_arms; }
     void counts(uint32_t& n_internal, uint32_t& n_pre, uint32_t& n_suf, uint32_t& n_empty) const {
         n_internal = (uint32_t)_internal_arms.size(); n_pre = (uint32_t)_pre_arms.size();
         n_suf = (uint32_t)_suf_arms.size(); n_empty = _num_empty;
@@ -143,9 +168,13 @@ private:
     UINT32 _num_internal, _num_pre, _num_suf, _num_empty;
     UINT32 _longest_pre_len, _longest_suf_len;
     PackedSeq<4> _draft;
-    std::vector<PackedSeq<2>> _internal_arms;
-    std::vector<PackedSeq<2>> _pre_arms;
-    std::vector<PackedSeq<2>> _suf_arms;
+    // The reference keeps a std::vector<PackedSeq<2>> per kind (include/Window.hpp:131-133): one heap block
+    // per arm.  Here the packed bytes of a kind's arms lie back to back in one block (exactly the bytes the
+    // PackedSeq<2> objects held, in insertion order), so the batch packer copies a window with three
+    // memcpys instead of chasing 30 pointers - that is what lets one host feed several GPUs.
+    ArmStore _internal_arms;
+    ArmStore _pre_arms;
+    ArmStore _suf_arms;
     std::string _consensus;
     mutable std::unique_ptr<MinimizerFilter> _ref_filter;   // LONG windows, use_reference_long_filter only
     static ArmFilter _long_filter;

@@ -51,7 +51,7 @@ public:
     void pack(int threads = 0);
     // Chunked pack -> hypo_gpu_consensus_batch -> scatter into Window::_consensus, double-buffered.
     // On failure prints "[Hypo::GPU] Error: ..." and exits(1), the reference's convention.
-    // chunk_windows = 0: 131072 windows per driven device.
+    // chunk_windows = 0: chosen from the batch size and the number of driven devices (see run()).
     void run(size_t chunk_windows = 0);
     const Timing& last_timing() const { return _timing; }
 
@@ -73,7 +73,7 @@ private:
         void release();
     };
     void pack_chunk(Slot& s, size_t first, size_t n, int threads);
-    void scatter_chunk(const Slot& s);
+    void scatter_chunk(const Slot& s, int threads);
 
     std::vector<Window*> _windows;
     std::vector<HypoWindowDesc> _win;

@@ -1,7 +1,10 @@
 // WindowStream.cpp — see WindowStream.hpp.
 #include "WindowStream.hpp"
 
+#include "../../include/hypo_b200.h"
+
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <istream>
 #include <ostream>
@@ -150,6 +153,47 @@ std::string WindowStream::stitched() const {
     std::string s;
     for (const Region& r : regions) s += r.window < 0 ? r.text : windows[r.window]->get_consensus();
     return s;
+}
+
+std::string WindowStream::stitched_on_device(bool resident) const {
+    // the contig's draft as one PackedSeq<4> (what Contig::_pseq holds): every region's draft bases in order
+    std::string draft;
+    std::vector<HypoRegionDesc> reg;
+    reg.reserve(regions.size());
+    for (const Region& r : regions) {
+        HypoRegionDesc d;
+        d.src = draft.size();
+        if (r.window < 0) {
+            d.len = (uint32_t)r.text.size();
+            d.window = HYPO_REGION_DRAFT;
+            draft += r.text;
+        } else {
+            d.len = 0;
+            d.window = (uint32_t)r.window;
+            draft += windows[r.window]->draft().unpack();
+        }
+        reg.push_back(d);
+    }
+    const PackedSeq<4> pseq(draft);
+    std::string cons;
+    std::vector<uint64_t> off(windows.size() + 1, 0);
+    for (size_t i = 0; i < windows.size(); ++i) {
+        cons += windows[i]->get_consensus();
+        off[i + 1] = cons.size();
+    }
+    const uint64_t first[2] = {0, reg.size()};
+    const uint64_t doff[1] = {0};
+    std::string out(draft.size() + cons.size() + 16, '\0');
+    uint64_t out_off[2] = {0, 0};
+    const int rc = hypo_gpu_stitch(reg.data(), reg.size(), first, 1, pseq.data(), doff, pseq.data_size(),
+                                   resident ? nullptr : cons.data(), resident ? nullptr : off.data(), windows.size(),
+                                   &out[0], out.size(), out_off);
+    if (rc != HYPO_OK) {
+        fprintf(stderr, "[Hypo::GPU] Error: stitching: %s\n", hypo_gpu_last_error());
+        exit(1);
+    }
+    out.resize(out_off[1]);
+    return out;
 }
 
 uint64_t WindowStream::polished_bp() const {

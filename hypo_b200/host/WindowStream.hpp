@@ -48,6 +48,12 @@ public:
     // regions verbatim, windows replaced by their consensus.
     std::string stitched() const;
 
+    // The same contig stitched on the device by hypo_gpu_stitch (the contig writer over the consensus slab,
+    // SURVEY.md §8f N4): the regions become HypoRegionDesc records over the contig's PackedSeq<4> draft.
+    // resident = true: the consensus bytes are not sent again - the result of the batch call that replay()
+    // just made is still on the device (single-chunk batches on one device only).
+    std::string stitched_on_device(bool resident) const;
+
     uint64_t polished_bp() const;   // sum of Window::get_window_len()
 
     std::string contig;

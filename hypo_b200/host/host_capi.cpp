@@ -478,4 +478,19 @@ int64_t hypo_host_inspect_replay(void* h, const int8_t scores[6], int device, do
     return (int64_t)bad;
 }
 
+// The stream's contig stitched (Contig::operator<<, reference src/Contig.cpp:345-366) from the windows'
+// current consensus strings: mode 0 on the host, 1 by hypo_gpu_stitch, 2 by hypo_gpu_stitch from the device-
+// resident result of the replay that just ran, 3 on the host from the RECORDED consensus strings.  Returns the length (nothing is written beyond out_cap).
+uint64_t hypo_host_inspect_stitch(void* h, int mode, char* out, uint64_t out_cap) {
+    hypo::WindowStream& ws = *static_cast<hypo::WindowStream*>(h);
+    std::string s;
+    if (mode == 3) {   // from the consensus strings the stream RECORDED (no device involved)
+        for (const auto& r : ws.regions) s += r.window < 0 ? r.text : ws.recorded[r.window];
+    } else {
+        s = mode == 0 ? ws.stitched() : ws.stitched_on_device(mode == 2);
+    }
+    if (out && s.size() <= out_cap) memcpy(out, s.data(), s.size());
+    return s.size();
+}
+
 }  // extern "C"

@@ -57,6 +57,8 @@ def lib():
         L.hypo_host_inspect_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.hypo_host_inspect_fill.restype = None
         L.hypo_host_inspect_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hypo_host_inspect_stitch.restype = C.c_uint64
+        L.hypo_host_inspect_stitch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.hypo_host_inspect_replay.restype = C.c_int64
         L.hypo_host_inspect_replay.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.POINTER(C.c_double),
                                                C.c_char_p]
@@ -215,6 +217,18 @@ class InspectStream:
         sc = (C.c_int8 * 6)(*[int(x) for x in scores])
         bad = lib().hypo_host_inspect_replay(self._h, sc, device, C.byref(sec), out_path.encode())
         return int(bad), float(sec.value)
+
+    def stitched(self, mode: int = 0) -> str:
+        """The polished contig (Contig::operator<<) from the windows' current consensus strings: mode 0 on
+        the host, 1 on the device (hypo_gpu_stitch), 2 on the device from the still resident result of
+        the replay that just ran, 3 on the host from the RECORDED consensus strings."""
+        n = int(lib().hypo_host_inspect_stitch(self._h, mode, None, 0)) if mode in (0, 3) else self.n_bases_bound()
+        buf = C.create_string_buffer(n + 16)
+        n = int(lib().hypo_host_inspect_stitch(self._h, mode, buf, n + 16))
+        return buf.raw[:n].decode()
+
+    def n_bases_bound(self) -> int:
+        return int(lib().hypo_host_inspect_stitch(self._h, 3, None, 0)) * 2 + 1024
 
     def close(self):
         if self._h:

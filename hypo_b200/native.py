@@ -27,6 +27,7 @@ ABI_SYMBOLS = (
     "hypo_gpu_last_fail_hist",
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
+    "hypo_gpu_stitch",
     "hypo_gpu_last_cells",
     "hypo_gpu_issue_rate",
     "hypo_gpu_launch_count",
@@ -189,7 +190,7 @@ def last_cells() -> int:
     return int(lib().hypo_gpu_last_cells())
 
 
-ISSUE_OPS = ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "VIADDMNMX.S32", "SHFL.UP", "PRMT", "IADD")
+ISSUE_OPS = ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "VIADDMNMX.S32", "SHFL.UP", "PRMT", "IMAD")
 
 
 def issue_rate(op: int) -> float:

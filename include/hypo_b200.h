@@ -199,13 +199,40 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]);
 
 /*
+ * Output stitching: the step after the path.  Replaces the region loop of Contig::operator<<
+ * (reference src/Contig.cpp:345-366): the polished contig is its regions in order - a strong region
+ * (or a window nobody polished) is copied from the contig's PackedSeq<4> draft, a polished window is
+ * replaced by its consensus.  One region per HypoRegionDesc:
+ *   window == HYPO_REGION_DRAFT : bases [src, src + len) of the contig's draft (unpacked: nibble codes
+ *                                 A0 C1 G2 T3, anything else 'N', reference include/PackedSeq.hpp:54-72)
+ *   otherwise                   : the consensus of window `window` of the batch (src / len ignored)
+ * regions of contig c are [contig_first_region[c], contig_first_region[c+1]); its draft starts at byte
+ * draft_off[c] of `drafts`.  cons / cons_off: the consensus bytes and n_win+1 offsets as returned by
+ * hypo_gpu_consensus_batch - or cons == NULL to stitch straight from the result of the most recent
+ * hypo_gpu_consensus_batch call, which is still resident on the device (one driven device only).
+ * out receives the contigs' polished sequences back to back, out_off[c] their starts (n_contigs+1).
+ * All pointers are host pointers.
+ */
+#define HYPO_REGION_DRAFT 0xffffffffu
+typedef struct HypoRegionDesc {
+    uint64_t src;
+    uint32_t len;
+    uint32_t window;
+} HypoRegionDesc;          /* 16 bytes */
+int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions,
+                    const uint64_t* contig_first_region, uint64_t n_contigs,
+                    const uint8_t* drafts, const uint64_t* draft_off, uint64_t draft_bytes,
+                    const char* cons, const uint64_t* cons_off, uint64_t n_win,
+                    char* out, uint64_t out_cap, uint64_t* out_off);
+
+/*
  * Measurement hooks for the compute roofline: the DP cells of the most recent batch
  * call - sum over windows and reads of (nodes + 1) x (read length + 1), the size of the matrix the
  * reference fills for that read (external/spoa/src/sisd_alignment_engine.cpp:52-75) - and the rate the
  * device sustains for one instruction of the fill's inner loop, measured on the spot in 10^9 warp
  * instructions per second over the whole GPU:
  *   op 0 VIADDMNMX.S16x2 (__viaddmax_s16x2)   1 VIMNMX3.S16x2 (__vimax3_s16x2)   2 VIADDMNMX.S32
- *      3 SHFL.UP                              4 PRMT                             5 IADD
+ *      3 SHFL.UP                              4 PRMT                             5 IMAD
  */
 uint64_t hypo_gpu_last_cells(void);
 int hypo_gpu_issue_rate(int op, double* g_warp_instr_per_s);

@@ -13,3 +13,5 @@ python "$ROOT/tools/capture/make_dataset.py" "$W/long" --size 60000 --cov 30 --l
 "$ROOT/tools/capture/capture.sh" "$W/long" 8
 gzip -9 -n -c "$W/short/aux/inspect_ctg1.txt" > "$HERE/cli_short_60kb.inspect.gz"
 gzip -9 -n -c "$W/long/aux/inspect_ctg1.txt" > "$HERE/cli_long_60kb.inspect.gz"
+gzip -9 -n -c "$W/short/polished.fa" > "$HERE/cli_short_60kb.polished.fa.gz"   # the reference CLI's own output
+gzip -9 -n -c "$W/long/polished.fa" > "$HERE/cli_long_60kb.polished.fa.gz"

@@ -87,6 +87,37 @@ def test_cli_captured_streams_pin_the_oracle(tmp_path, name, n_regions, n_window
     assert got == s.recorded
 
 
+def _polished(name):
+    """The sequence line of the reference CLI's own output FASTA for the captured run."""
+    txt = gzip.open(os.path.join(HERE, "golden", name.replace(".inspect.gz", ".polished.fa.gz"))).read().decode()
+    lines = txt.split("\n")
+    assert lines[0] == ">ctg1"
+    return lines[1]
+
+
+@pytest.mark.parametrize("name,n_regions,n_windows,n_long", CLI_STREAMS)
+def test_cli_captured_streams_stitch_to_the_reference_output(tmp_path, name, n_regions, n_windows, n_long):
+    """Regions + recorded consensus strings, stitched like Contig::operator<< (reference src/Contig.cpp:345-366),
+    give exactly the polished FASTA the reference CLI wrote in the same run."""
+    s = InspectStream(_cli_path(tmp_path, name))
+    assert s.stitched(3) == _polished(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_regions,n_windows,n_long", CLI_STREAMS)
+def test_device_stitching_reproduces_the_reference_cli_output(tmp_path, name, n_regions, n_windows, n_long):
+    """windows polished on the GPU, contig stitched on the GPU (hypo_gpu_stitch) - from
+    consensus bytes sent back in, and straight from the result still resident on the device - equals the
+    reference CLI's polished FASTA byte for byte."""
+    s = InspectStream(_cli_path(tmp_path, name))
+    bad, _ = s.replay(DEFAULT_SCORES, 0)
+    assert bad == 0
+    want = _polished(name)
+    assert s.stitched(0) == want
+    assert s.stitched(1) == want
+    assert s.stitched(2) == want
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n_regions,n_windows,n_long", CLI_STREAMS)
 def test_replay_cli_captured_streams_on_the_gpu(tmp_path, name, n_regions, n_windows, n_long):
