@@ -1655,6 +1655,10 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         uint32_t used = 0;
         SeqSrc s;
         s.head = false; s.tail = false; s.type = kNW;
+#ifdef HYPO_TMA_STAGE
+        stage_drain<kSmem, kTier>(g);
+        s.arm_idx = -1; s.next_idx = -1; s.next_bytes = nullptr; s.next_len = 0;
+#endif
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return give_up(g, kFailPaths);
             if (lane == 0) pstart[ws->n_seq] = used;
@@ -1674,6 +1678,12 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         for (int k = 0; k < n_arms; ++k) {   // :180-207 (container order, engine stays kNW)
             if (a[k].len == 0) continue;
             s.bytes = P.packed + a[k].off; s.len = a[k].len;
+#ifdef HYPO_TMA_STAGE
+            s.arm_idx = (int64_t)(w.first_arm + k);
+            s.next_idx = -1;
+            for (int kn = k + 1; kn < n_arms; ++kn)
+                if (a[kn].len) { s.next_idx = (int64_t)(w.first_arm + kn); s.next_bytes = P.packed + a[kn].off; s.next_len = a[kn].len; break; }
+#endif
             if (!add(s)) return -2;
         }
         if (lane == 0) pstart[ws->n_seq] = used;
