@@ -162,11 +162,14 @@ struct RouteCfg {
 struct Options {
     int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it)
     int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
+    int probe = 1;        // shared-memory tiers probe long lists before running them (see stage_tiers)
     int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
                           // 2 = NCCL send/recv to device 0 over NVLink, then one device-to-host copy
 };
 
 constexpr int kPasses = 2;   // head and tail of the pipelined host-buffer path
+constexpr uint32_t kProbe = 4096;            // windows of a tier's list that run first, alone ...
+constexpr uint32_t kProbeMin = 4 * kProbe;   // ... when the list holds at least this many
 
 struct Ctx {
     int device = -1;
@@ -186,6 +189,7 @@ struct Ctx {
     uint32_t tier_windows[8] = {0};
     uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
     unsigned long long cells = 0;                // DP cells of the last batch call
+    uint64_t rerouted = 0;                       // windows a probe sent on without trying them in a tier
     std::string err;             // message of a failure on this device's worker thread
 };
 
@@ -455,6 +459,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         memset(g.tier_windows, 0, sizeof(g.tier_windows));
         memset(g.fail_hist, 0, sizeof(g.fail_hist));
         g.cells = 0;
+        g.rerouted = 0;
     }
     if (n_win == 0) return HYPO_OK;
     DevCtrl* const d_ctrl = (DevCtrl*)g.ctrl.p;
@@ -582,6 +587,51 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
         P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
         CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
+        // Probe (shared-memory tiers with a long list): static routing knows the windows' sizes, not their
+        // reads' error rate, and a tier that most of its windows outgrow does its work twice.  So the first
+        // kProbe windows of the list run alone; if a quarter of them leave the tier, the rest of the list is
+        // handed to the successor without being tried here.  Only where windows run changes, never a result.
+        if (!T.from_bounds && nx < kNumTiers && G.opt.probe && work_ub >= kProbeMin) {
+            if (!counts_fresh) {
+                CUDA_TRY(fetch_ctrl(g, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                counts_fresh = true;
+            }
+            const uint32_t n = h->tmax[t].count;
+            if (n >= kProbeMin) {
+                uint32_t* hw = (uint32_t*)(host_words(g) + 8);   // page-locked words the async copies read
+                const uint32_t next_before = h->tmax[nx].count;
+                hw[0] = kProbe; hw[1] = 0;
+                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[8], hw, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                Params Q = P;
+                Q.n_work = &d_ctrl->queue[8]; Q.queue = &d_ctrl->queue[9];
+                const int pb = std::min<int>(blocks, (int)((kProbe + wpb - 1) / wpb));
+                CUDA_TRY(launch_poa(Q, t, T.smem_graph, wide, pb, wpb, smem, stream));
+                ++G.launches;
+                CUDA_TRY(fetch_ctrl(g, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                const uint32_t failed = h->tmax[nx].count - next_before;
+                if (failed * 4 >= kProbe) {
+                    const uint32_t rest = n - kProbe, at = h->tmax[nx].count;
+                    CUDA_TRY(cudaMemcpyAsync(d_lists + (uint64_t)nx * n_win + at, d_lists + (uint64_t)t * n_win + kProbe,
+                                             sizeof(uint32_t) * rest, cudaMemcpyDeviceToDevice, stream));
+                    hw[2] = at + rest; hw[3] = kProbe;
+                    CUDA_TRY(cudaMemcpyAsync(&d_ctrl->tmax[nx].count, hw + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                    CUDA_TRY(cudaMemcpyAsync(&d_ctrl->tmax[t].count, hw + 3, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                    CUDA_TRY(cudaEventRecord(g.tev1[pass][t], stream));
+                    CUDA_TRY(cudaStreamSynchronize(stream));   // (hw is reused by the next tier)
+                    h->tmax[nx].count = at + rest;
+                    h->tmax[t].count = kProbe;
+                    g.rerouted += rest;
+                    launched[t] = true;
+                    continue;
+                }
+                // the tier holds: the rest of its list
+                hw[4] = n - kProbe; hw[5] = 0;
+                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[10], hw + 4, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                P.work += kProbe; P.n_work = &d_ctrl->queue[10]; P.queue = &d_ctrl->queue[11];
+            }
+        }
         CUDA_TRY(launch_poa(P, t, T.smem_graph, wide, blocks, wpb, smem, stream));
         CUDA_TRY(cudaEventRecord(g.tev1[pass][t], stream));
         ++G.launches;
@@ -1051,6 +1101,9 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "scap")) {
         if (value < 0 || value > 65534) return fail(HYPO_E_ARG, "scap must be 0..65534");
         G.opt.scap = (int)value;
+    } else if (!strcmp(name, "probe")) {
+        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "probe must be 0 or 1");
+        G.opt.probe = (int)value;
     } else if (!strcmp(name, "gather")) {
         if (value != 0 && value != 2) return fail(HYPO_E_ARG, "gather must be 0 (direct) or 2 (NCCL to device 0)");
         G.opt.gather = (int)value;
@@ -1305,6 +1358,12 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
     if (poa_launches) *poa_launches = n;
     if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = tw[t];
     return HYPO_OK;
+}
+
+uint64_t hypo_gpu_last_rerouted(void) {
+    uint64_t c = 0;
+    for (int i = 0; i < G.n_dev; ++i) c += G.dev[i]->rerouted;
+    return c;
 }
 
 uint64_t hypo_gpu_last_cells(void) {

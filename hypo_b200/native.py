@@ -28,6 +28,7 @@ ABI_SYMBOLS = (
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
     "hypo_gpu_stitch",
+    "hypo_gpu_last_rerouted",
     "hypo_gpu_last_cells",
     "hypo_gpu_issue_rate",
     "hypo_gpu_launch_count",
@@ -85,6 +86,7 @@ def lib():
                                               C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
         L.hypo_gpu_last_timing.restype = C.c_int
         L.hypo_gpu_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.hypo_gpu_last_rerouted.restype = C.c_uint64
         L.hypo_gpu_last_cells.restype = C.c_uint64
         L.hypo_gpu_issue_rate.restype = C.c_int
         L.hypo_gpu_issue_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -183,6 +185,11 @@ def last_timing() -> Tuple[float, int, List[int]]:
     tiers = (C.c_uint32 * 8)()
     lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
     return float(ms.value), int(n.value), [int(x) for x in tiers]
+
+
+def last_rerouted() -> int:
+    """Windows the tier probes of the last batch call handed to a later tier untried."""
+    return int(lib().hypo_gpu_last_rerouted())
 
 
 def last_cells() -> int:

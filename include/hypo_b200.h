@@ -118,6 +118,9 @@ int hypo_gpu_device_count(void);
  * Knobs for tests and measurements (the defaults are what production uses):
  *   "first_tier" 0..7  routing starts at this capacity tier (7 = the bound-driven last tier)
  *   "scap"       n     DFS-stack entries of the bound-driven tiers except the last (0 = from bounds)
+ *   "probe"      0|1   a shared-memory tier whose list holds >= 16384 windows runs the first 4096 alone and,
+ *                      if a quarter of them outgrow the tier, hands the rest of the list to the successor tier
+ *                      untried (default 1; only changes where windows run)
  *   "gather"     0|2   multi-device result gather: 0 every device copies its bytes to the host
  *                      itself, 2 NCCL send/recv to device 0 over NVLink, then one copy
  * Returns HYPO_E_ARG for an unknown name or a value out of range.
@@ -236,6 +239,9 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions,
  */
 uint64_t hypo_gpu_last_cells(void);
 int hypo_gpu_issue_rate(int op, double* g_warp_instr_per_s);
+
+/* Windows the tier probes of the most recent batch call sent on without trying them in a tier. */
+uint64_t hypo_gpu_last_rerouted(void);
 
 /* Number of kernel launches issued by this library since hypo_gpu_init. */
 uint64_t hypo_gpu_launch_count(void);

@@ -252,3 +252,21 @@ def test_one_process_many_devices_same_bytes(gather):
         got = native.consensus(b.select(perm))
         assert got == [want[i] for i in perm]
     native.set_option("gather", 0)
+
+
+def test_probe_reroutes_a_list_its_tier_cannot_hold():
+    """30 x 120 bp at 5 % error per edit type: the static estimate routes the windows to the compact tier,
+    whose DAG capacity almost none of them fits.  The launcher runs the first 4096 alone, sees them leave, and
+    hands the rest to the successor untried (which probes again).  Same bytes as without probing."""
+    b = synth_batch(170, 24000, 120, 30, "internal", 0.05)
+    native.set_option("probe", 0)
+    plain = native.consensus(b)
+    _, _, tiers0 = native.last_timing()
+    native.set_option("probe", 1)
+    probed = native.consensus(b)
+    _, _, tiers1 = native.last_timing()
+    assert probed == plain
+    assert native.last_rerouted() > 0 and tiers1[0] == 4096 and tiers0[0] == b.n_win
+    idx = np.arange(0, b.n_win, 97)
+    want, _ = oracle_consensus(b.select(idx))
+    assert [probed[i] for i in idx] == want

@@ -41,10 +41,13 @@ def main():
     ap.add_argument("--budget", type=float, default=2.5e11, help="DP cells per shape (bounds the window count)")
     ap.add_argument("--max-windows", type=int, default=200000)
     ap.add_argument("--long", action="store_true", help="also run LONG windows (lr scores, two rounds) for 30 arms")
-    ap.add_argument("--check", type=int, default=48, help="windows compared with the CPU oracle per shape")
+    ap.add_argument("--check", type=int, default=512, help="windows compared with the CPU oracle per shape (at most)")
+    ap.add_argument("--check-cells", type=float, default=2e10, help="DP cells the oracle may spend per shape")
     a = ap.parse_args()
     native.init(SCORES, 0)
     peak = peak_gbs()
+    dpx = native.issue_rate(0)   # measured VIADDMNMX.S16x2 rate, 10^9 warp instructions / s
+    dpx_peak_gcups = dpx * 32.0  # bench.py: roofline.compute.peak_definition
     shapes = [(int(r), int(l), float(e), 0) for e in a.errs.split(",") for r in a.arms.split(",")
               for l in a.lengths.split(",")]
     if a.long:
@@ -61,16 +64,23 @@ def main():
         dt = time.perf_counter() - t0
         k_ms, launches, tiers = native.last_timing()
         total = int(off[batch.n_win])
-        k = min(a.check if cells < 5e7 else 8, batch.n_win)
-        got = split_consensus(out, off)[:k]
-        want, _ = oracle_consensus(batch.select(np.arange(k)), SCORES)
+        # windows checked against the oracle: a strided sample over the whole batch, as many as the budget allows
+        k = int(max(8, min(a.check, batch.n_win, a.check_cells / max(cells, 1.0))))
+        idx = np.unique(np.linspace(0, batch.n_win - 1, k).astype(np.int64))
+        allc = split_consensus(out, off)
+        got = [allc[i] for i in idx]
+        want, _ = oracle_consensus(batch.select(idx), SCORES)
+        k = len(idx)
         alg = batch.algorithmic_bytes(total)
+        dev_cells = native.last_cells()
         line = {
             "shape": {"arms": arms, "length": length, "err": err, "wtype": "LONG" if wtype else "SHORT"},
             "windows": n, "nodes_avg": float(st[:, 0].mean()), "cells_per_window": cells,
             "kernel_ms": k_ms, "mbp_per_s_kernel": batch.polished_bp / 1e6 / (k_ms / 1e3),
             "mbp_per_s_e2e": batch.polished_bp / 1e6 / dt, "windows_per_s": n / (k_ms / 1e3),
-            "gcups": cells * n / 1e9 / (k_ms / 1e3),
+            "gcups": dev_cells / 1e9 / (k_ms / 1e3), "cells_counted_on_device": dev_cells,
+            "dpx_peak_gcups": dpx_peak_gcups, "frac_of_dpx_peak": dev_cells / 1e9 / (k_ms / 1e3) / dpx_peak_gcups,
+            "rerouted_by_probe": native.last_rerouted(),
             "hbm_gbs_algorithmic": alg / 1e9 / (k_ms / 1e3), "hbm_frac_of_measured_peak": alg / 1e9 / (k_ms / 1e3) / peak,
             "tier_windows": tiers[:8], "abandoned_by_reason": native.last_fail_hist()[1:12],
             "bit_exact_checked": k, "bit_exact": got == want,
