@@ -255,10 +255,10 @@ def test_one_process_many_devices_same_bytes(gather):
 
 
 def test_probe_reroutes_a_list_its_tier_cannot_hold():
-    """30 x 120 bp at 5 % error per edit type: the static estimate routes the windows to the compact tier,
+    """30 x 100 bp at 5 % error per edit type: the static estimate routes the windows to the compact tier,
     whose DAG capacity almost none of them fits.  The launcher runs the first 4096 alone, sees them leave, and
     hands the rest to the successor untried (which probes again).  Same bytes as without probing."""
-    b = synth_batch(170, 24000, 120, 30, "internal", 0.05)
+    b = synth_batch(170, 24000, 100, 30, "internal", 0.05)
     native.set_option("probe", 0)
     plain = native.consensus(b)
     _, _, tiers0 = native.last_timing()
