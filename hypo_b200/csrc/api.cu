@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -193,10 +194,18 @@ struct Ctx {
     std::string err;             // message of a failure on this device's worker thread
 };
 
+// Two "lanes" per device: independent contexts (streams, buffers, control blocks), so that two host threads
+// can each have a batch call in flight.  The second call's copies and classification run while the first
+// call's kernels do, its CTAs fill the SMs the first call's persistent kernel frees in its tail, and the first
+// call's compaction and result copy hide behind the second call's kernels (WindowBatch::run drives them so).
+constexpr int kLanes = 2;
 struct Global {
     bool init = false;
     int n_dev = 0;
-    Ctx* dev[HYPO_MAX_DEVICES] = {nullptr};
+    Ctx* lane[kLanes][HYPO_MAX_DEVICES] = {{nullptr}};
+    Ctx** dev = lane[0];      // lane 0: what the single-call entry points use
+    std::atomic<int> last{0}; // lane of the most recent batch call (measurement hooks, resident result)
+    std::atomic<int> probe_skip[16] = {};   // per tier: probes to skip after one that found the tier holds
     int8_t scores[6] = {0};
     Options opt;
     std::atomic<uint64_t> launches{0};
@@ -206,7 +215,24 @@ struct Global {
     bool comms_ready = false;
 } G;
 
-std::mutex g_mu;
+std::shared_mutex g_state_mu;      // init / shutdown / options exclusively, everything else shared
+std::mutex g_lane_mu[kLanes];      // one batch call per lane
+std::mutex g_nccl_mu;              // the communicators are shared by the lanes
+
+// Shared state lock + a free lane (lane 0 if both are busy: wait for it).
+struct LaneLock {
+    std::shared_lock<std::shared_mutex> state{g_state_mu};
+    int lane = 0;
+    explicit LaneLock(bool any_lane) {
+        if (any_lane) {
+            for (int l = 0; l < kLanes; ++l)
+                if (g_lane_mu[l].try_lock()) { lane = l; return; }
+        }
+        g_lane_mu[0].lock();
+        lane = 0;
+    }
+    ~LaneLock() { g_lane_mu[lane].unlock(); }
+};
 
 // ---------------------------------------------------------------------------------------
 // Small helper kernels
@@ -591,7 +617,9 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         // reads' error rate, and a tier that most of its windows outgrow does its work twice.  So the first
         // kProbe windows of the list run alone; if a quarter of them leave the tier, the rest of the list is
         // handed to the successor without being tried here.  Only where windows run changes, never a result.
-        if (!T.from_bounds && nx < kNumTiers && G.opt.probe && work_ub >= kProbeMin) {
+        if (!T.from_bounds && nx < kNumTiers && G.opt.probe && work_ub >= kProbeMin &&
+            G.probe_skip[t].fetch_sub(1) <= 0) {
+            G.probe_skip[t] = 0;
             if (!counts_fresh) {
                 CUDA_TRY(fetch_ctrl(g, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -626,7 +654,9 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
                     launched[t] = true;
                     continue;
                 }
-                // the tier holds: the rest of its list
+                // the tier holds: the rest of its list.  A data set's error profile does not change from one
+                // pass to the next: after a clean probe (< 5 % left) the next 15 passes of this tier skip theirs
+                if (failed * 20 < kProbe) G.probe_skip[t] = 15;
                 hw[4] = n - kProbe; hw[5] = 0;
                 CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[10], hw + 4, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
                 P.work += kProbe; P.n_work = &d_ctrl->queue[10]; P.queue = &d_ctrl->queue[11];
@@ -677,7 +707,8 @@ struct CopyGuard {
     ~CopyGuard() { if (armed) cudaStreamSynchronize(c); }
 };
 
-int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t* packed, Shard& sh) {
+int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t* packed, Shard& sh,
+                  bool other_lane_busy) {
     CUDA_TRY(cudaSetDevice(g.device));
     cudaStream_t s = g.stream;
     const uint64_t n_win = sh.w1 - sh.w0;
@@ -709,6 +740,10 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
     // ---- split: head = first ~1/8 of the windows, copied first and run while the tail crosses PCIe -----
     const WinDesc* hw = win + sh.w0;
     uint64_t w_s = 0, a_s = 0, b_s = 0;
+    // (measured: keeping the split while the other lane has a call in flight is faster than dropping it -
+    // a lane's small kernels cannot start anyway while the other lane's persistent kernel fills the SMs, so
+    // an early head is what gets this call's first kernel queued in time)
+    (void)other_lane_busy;
     bool piped = n_win >= 65536 && n_arms > 0 && n_bytes > 0;
     if (piped) {
         w_s = std::max<uint64_t>(32768, n_win / 8);
@@ -898,9 +933,10 @@ int nccl_comms() {
 
 // The final consensus gather of SURVEY.md §8e over NVLink: every device sends its compacted bytes to
 // device 0 (grouped ncclSend / ncclRecv, single process), which then makes the one copy to the host.
-int gather_nccl(std::vector<Shard>& sh, const std::vector<uint64_t>& base, uint64_t total, char* out) {
+int gather_nccl(Ctx** dev, std::vector<Shard>& sh, const std::vector<uint64_t>& base, uint64_t total, char* out) {
+    std::lock_guard<std::mutex> nk(g_nccl_mu);
     if (int rc = nccl_comms()) return rc;
-    Ctx& g0 = *G.dev[0];
+    Ctx& g0 = *dev[0];
     CUDA_TRY(cudaSetDevice(g0.device));
     CUDA_TRY(g0.gather.reserve(total + 16));
     if (sh[0].total)
@@ -908,12 +944,16 @@ int gather_nccl(std::vector<Shard>& sh, const std::vector<uint64_t>& base, uint6
     NCCL_TRY(nccl.GroupStart());
     for (int i = 1; i < G.n_dev; ++i) {
         if (!sh[i].total) continue;
-        NCCL_TRY(nccl.Send(G.dev[i]->out_compact.p, sh[i].total, /*ncclChar*/ 0, 0, G.comms[i], G.dev[i]->stream));
+        NCCL_TRY(nccl.Send(dev[i]->out_compact.p, sh[i].total, /*ncclChar*/ 0, 0, G.comms[i], dev[i]->stream));
         NCCL_TRY(nccl.Recv((char*)g0.gather.p + base[i], sh[i].total, 0, i, G.comms[0], g0.stream));
     }
     NCCL_TRY(nccl.GroupEnd());
     CUDA_TRY(cudaSetDevice(g0.device));
     if (total) CUDA_TRY(cudaMemcpyAsync(out, g0.gather.p, total, cudaMemcpyDeviceToHost, g0.stream));
+    for (int i = 0; i < G.n_dev; ++i) {   // the communicators are free again when this returns
+        CUDA_TRY(cudaSetDevice(dev[i]->device));
+        CUDA_TRY(cudaStreamSynchronize(dev[i]->stream));
+    }
     return HYPO_OK;
 }
 
@@ -943,7 +983,8 @@ void shutdown_locked() {
         for (int i = 0; i < G.n_dev; ++i) if (G.comms[i]) nccl.CommDestroy(G.comms[i]);
     G.comms_ready = false;
     memset(G.comms, 0, sizeof(G.comms));
-    for (int i = 0; i < HYPO_MAX_DEVICES; ++i) { release_ctx(G.dev[i]); G.dev[i] = nullptr; }
+    for (int l = 0; l < kLanes; ++l)
+        for (int i = 0; i < HYPO_MAX_DEVICES; ++i) { release_ctx(G.lane[l][i]); G.lane[l][i] = nullptr; }
     G.n_dev = 0;
     G.init = false;
 }
@@ -1002,12 +1043,14 @@ int init_devices(const int8_t scores[6], const int* devices, int n) {
     if (!same) {
         shutdown_locked();
         for (int i = 0; i < n; ++i) {
-            const int rc = create_ctx(devices[i], &G.dev[i]);
+            int rc = create_ctx(devices[i], &G.lane[0][i]);
+            if (!rc) rc = create_ctx(devices[i], &G.lane[1][i]);
             G.n_dev = i + 1;
             if (rc) { const std::string keep = g_err; shutdown_locked(); g_err = keep; return rc; }
         }
     }
     memcpy(G.scores, scores, 6);
+    for (auto& p : G.probe_skip) p = 0;
     G.launches = 0;
     G.init = true;
     return HYPO_OK;
@@ -1071,12 +1114,12 @@ uint64_t hypo_gpu_launch_count(void) { return G.launches.load(); }
 int hypo_gpu_device_count(void) { return G.init ? G.n_dev : 0; }
 
 int hypo_gpu_init(const int8_t scores[6], int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state_mu);
     return init_devices(scores, &device, 1);
 }
 
 int hypo_gpu_init_multi(const int8_t scores[6], int n_gpus) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state_mu);
     g_err.clear();
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -1092,7 +1135,7 @@ int hypo_gpu_init_multi(const int8_t scores[6], int n_gpus) {
 }
 
 int hypo_gpu_set_option(const char* name, int64_t value) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state_mu);
     g_err.clear();
     if (!name) return fail(HYPO_E_ARG, "option name == NULL");
     if (!strcmp(name, "first_tier")) {
@@ -1104,6 +1147,7 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "probe")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "probe must be 0 or 1");
         G.opt.probe = (int)value;
+        for (auto& p : G.probe_skip) p = 0;
     } else if (!strcmp(name, "gather")) {
         if (value != 0 && value != 2) return fail(HYPO_E_ARG, "gather must be 0 (direct) or 2 (NCCL to device 0)");
         G.opt.gather = (int)value;
@@ -1139,7 +1183,7 @@ uint64_t hypo_gpu_out_bound(const HypoWindowDesc* win, uint64_t n_win, const Hyp
 int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win, const HypoArmDesc* d_arms,
                                     uint64_t n_arms, const uint8_t* d_packed, uint64_t packed_bytes,
                                     char* d_out, const uint64_t* d_out_pos, uint32_t* d_out_len, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    LaneLock lk(false);
     g_err.clear();
     if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     Ctx& g = *G.dev[0];
@@ -1154,6 +1198,7 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
     CUDA_TRY(fetch_ctrl(g, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (int rc = check_bad(g, false)) return rc;
+    G.last = 0;
     return stage_tiers(g, 0, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, d_packed, packed_bytes, d_out, d_out_pos,
                        d_out_len, (const WinStat*)g.stats.p, s);
 }
@@ -1161,7 +1206,10 @@ int hypo_gpu_consensus_batch_device(const HypoWindowDesc* d_win, uint64_t n_win,
 int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const HypoArmDesc* arms, uint64_t n_arms,
                              const uint8_t* packed, uint64_t packed_bytes, char* out, uint64_t out_cap,
                              uint64_t* out_off) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    LaneLock lk(true);
+    Ctx** const dev = G.lane[lk.lane];
+    bool other_busy = true;   // is a call in flight on the other lane right now?
+    if (g_lane_mu[lk.lane ^ 1].try_lock()) { other_busy = false; g_lane_mu[lk.lane ^ 1].unlock(); }
     g_err.clear();
     if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     if (!out_off) return fail(HYPO_E_ARG, "out_off == NULL");
@@ -1175,7 +1223,7 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     if (n == 1) {
         sh.assign(1, Shard());
         sh[0].w0 = 0; sh[0].w1 = n_win; sh[0].a0 = 0; sh[0].a1 = n_arms; sh[0].b0 = 0; sh[0].b1 = packed_bytes;
-        if (int rc = shard_compute(*G.dev[0], hw, ha, packed, sh[0])) return rc;
+        if (int rc = shard_compute(*dev[0], hw, ha, packed, sh[0], other_busy)) return rc;
     } else {
         // one host thread per device; each runs the single-device pipeline on its range.  A batch whose
         // ranges turn out not to be self-contained (not laid out in window order) is re-run with every
@@ -1187,13 +1235,13 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
             for (int i = 0; i < n; ++i)
                 th.emplace_back([&, i]() {
                     g_err.clear();
-                    sh[i].rc = shard_compute(*G.dev[i], hw, ha, packed, sh[i]);
-                    G.dev[i]->err = g_err;   // (the message is thread-local to this worker)
+                    sh[i].rc = shard_compute(*dev[i], hw, ha, packed, sh[i], other_busy);
+                    dev[i]->err = g_err;   // (the message is thread-local to this worker)
                 });
             for (auto& t : th) t.join();
             int rc = HYPO_OK;
             for (int i = 0; i < n && !rc; ++i)
-                if (sh[i].rc) { g_err = G.dev[i]->err; rc = sh[i].rc; }
+                if (sh[i].rc) { g_err = dev[i]->err; rc = sh[i].rc; }
             if (rc == HYPO_E_ARG && partial && attempt == 0) continue;
             if (rc) return rc;
             break;
@@ -1207,16 +1255,17 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     // gather in window order: shard i's bytes start at base[i]
     const bool via_dev0 = n > 1 && G.opt.gather == 2;
     if (via_dev0)
-        if (int rc = gather_nccl(sh, base, total, out)) return rc;
+        if (int rc = gather_nccl(dev, sh, base, total, out)) return rc;
     for (int i = 0; i < n; ++i)
-        if (int rc = shard_fetch(*G.dev[i], sh[i], out, base[i], out_off, !via_dev0)) return rc;
+        if (int rc = shard_fetch(*dev[i], sh[i], out, base[i], out_off, !via_dev0)) return rc;
     for (int i = 0; i < n; ++i)
-        if (int rc = shard_wait(*G.dev[i])) return rc;
+        if (int rc = shard_wait(*dev[i])) return rc;
     for (int i = 1; i < n; ++i) {
         const uint64_t b = base[i];
         for (uint64_t w = sh[i].w0; w < sh[i].w1; ++w) out_off[w] += b;
     }
     out_off[n_win] = total;
+    G.last = lk.lane;
     return HYPO_OK;
 }
 
@@ -1224,7 +1273,7 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uin
                     uint64_t n_contigs, const uint8_t* drafts, const uint64_t* draft_off, uint64_t draft_bytes,
                     const char* cons, const uint64_t* cons_off, uint64_t n_win, char* out, uint64_t out_cap,
                     uint64_t* out_off) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    LaneLock lk(false);
     g_err.clear();
     if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     if (!out_off || (!regions && n_regions) || !contig_first_region || (!draft_off && n_contigs))
@@ -1234,6 +1283,7 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uin
     if (contig_first_region[0] != 0 || contig_first_region[n_contigs] != n_regions)
         return fail(HYPO_E_ARG, "contig_first_region must run from 0 to n_regions");
     Ctx& g = *G.dev[0];
+    Ctx& gres = *G.lane[G.last.load()][0];   // where the most recent batch call left its result
     CUDA_TRY(cudaSetDevice(g.device));
     cudaStream_t s = g.stream;
     // host-side validation of the draft ranges + the contig of every region
@@ -1260,12 +1310,12 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uin
         d_cons = (const char*)g.st_cons.p;
         d_coff = (const uint64_t*)g.st_coff.p;
     } else {
-        if (G.n_dev != 1 || g.resident_windows != n_win || n_win == 0)
+        if (G.n_dev != 1 || gres.resident_windows != n_win || n_win == 0)
             return fail(HYPO_E_ARG, "cons == NULL needs the result of the last hypo_gpu_consensus_batch call (%llu windows, "
                                     "one driven device) still resident; it holds %llu",
-                        (unsigned long long)n_win, (unsigned long long)g.resident_windows);
-        d_cons = (const char*)g.out_compact.p;
-        d_coff = (const uint64_t*)g.out_off.p;
+                        (unsigned long long)n_win, (unsigned long long)gres.resident_windows);
+        d_cons = (const char*)gres.out_compact.p;   // (same device; that call has completed)
+        d_coff = (const uint64_t*)gres.out_off.p;
     }
     CUDA_TRY(g.st_reg.reserve(sizeof(RegionDesc) * n_regions));
     CUDA_TRY(g.st_contig.reserve(sizeof(uint32_t) * n_regions));
@@ -1317,7 +1367,7 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uin
 int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, const uint32_t* d_out_len,
                             uint64_t n_win, char* d_compact, uint64_t compact_cap, uint64_t* d_off,
                             uint64_t* total, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    LaneLock lk(false);
     g_err.clear();
     if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     Ctx& g = *G.dev[0];
@@ -1349,7 +1399,7 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
     float ms = 0.f;
     uint32_t n = 0, tw[8] = {0};
     for (int i = 0; i < G.n_dev; ++i) {
-        const Ctx& g = *G.dev[i];
+        const Ctx& g = *G.lane[G.last.load()][i];
         ms = std::max(ms, g.poa_ms);   // the devices run side by side
         n += g.poa_launches;
         for (int t = 0; t < 8; ++t) tw[t] += g.tier_windows[t];
@@ -1362,13 +1412,13 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
 
 uint64_t hypo_gpu_last_rerouted(void) {
     uint64_t c = 0;
-    for (int i = 0; i < G.n_dev; ++i) c += G.dev[i]->rerouted;
+    for (int i = 0; i < G.n_dev; ++i) c += G.lane[G.last.load()][i]->rerouted;
     return c;
 }
 
 uint64_t hypo_gpu_last_cells(void) {
     uint64_t c = 0;
-    for (int i = 0; i < G.n_dev; ++i) c += G.dev[i]->cells;
+    for (int i = 0; i < G.n_dev; ++i) c += G.lane[G.last.load()][i]->cells;
     return c;
 }
 
@@ -1410,7 +1460,7 @@ __global__ void __launch_bounds__(256) issue_kernel(uint32_t* sink, int iters, u
 extern "C" {
 
 int hypo_gpu_issue_rate(int op, double* g_warp_instr_per_s) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    LaneLock lk(false);
     g_err.clear();
     if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
     if (op < 0 || op > 5 || !g_warp_instr_per_s) return fail(HYPO_E_ARG, "op must be 0..5");
@@ -1442,7 +1492,7 @@ int hypo_gpu_last_fail_hist(uint32_t reasons[16]) {
     if (!reasons) return HYPO_OK;
     for (int k = 0; k < kNumFailReasons; ++k) {
         reasons[k] = 0;
-        for (int i = 0; i < G.n_dev; ++i) reasons[k] += G.dev[i]->fail_hist[k];
+        for (int i = 0; i < G.n_dev; ++i) reasons[k] += G.lane[G.last.load()][i]->fail_hist[k];
     }
     return HYPO_OK;
 }
@@ -1461,7 +1511,7 @@ void hypo_gpu_host_free(void* p) {
 }
 
 void hypo_gpu_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state_mu);
     shutdown_locked();
 }
 

@@ -48,8 +48,7 @@ std::ostream& operator<<(std::ostream& os, const Window& wnd) {
 }
 
 WindowBatch::~WindowBatch() {
-    _slot[0].release();
-    _slot[1].release();
+    for (Slot& sl : _slot) sl.release();
 }
 
 void WindowBatch::Slot::release() {
@@ -182,11 +181,11 @@ void WindowBatch::run(size_t chunk_windows) {
     const int threads = omp_get_max_threads();
     const int threads_ov = std::max(1, threads - 1);   // while the device thread spins in its synchronisations
     // Chunk boundaries.  A batch of fewer than 128 K windows per driven device goes in one piece (cutting it
-    // starves the persistent kernels: a few windows per warp leave a long tail).  Otherwise a small first
-    // chunk (64 K windows per device - its pack is the only host work the device cannot hide, 3 ms), then
-    // equal chunks of at most 512 K windows per device, at least two: packing a million windows takes 45 ms
-    // on 16 threads against 540 ms of kernels, so few large chunks keep the per-call costs (copy of a head,
-    // compaction, result copy, kernel tails) small (measured: tools/chunk_sweep.py, profiles/).
+    // starves the persistent kernels).  Otherwise a small first chunk (32 K windows per device: its pack is
+    // the only host work the device cannot hide), then equal chunks of at most 256 K windows per device, at
+    // least three: with two calls in flight the per-call costs (copy of a head, compaction, result copy,
+    // kernel tails) hide behind the other call's kernels, so chunks may be small enough to keep the two
+    // lanes' buffers modest (measured: tools/chunk_sweep.py, profiles/).
     const size_t ndev = (size_t)std::max(1, hypo_gpu_device_count());
     std::vector<size_t> cut{0};
     if (chunk_windows) {
@@ -194,52 +193,65 @@ void WindowBatch::run(size_t chunk_windows) {
     } else if (n < 131072 * ndev) {
         cut.push_back(n);
     } else {
-        const size_t first = 65536 * ndev;
+        const size_t first = 32768 * ndev;
         cut.push_back(first);
         const size_t rest = n - first;
-        const size_t k = rest < 131072 * ndev ? 1 : std::max<size_t>(2, (rest + 524288 * ndev - 1) / (524288 * ndev));
+        const size_t k = rest < 196608 * ndev ? 1 : std::max<size_t>(3, (rest + 262144 * ndev - 1) / (262144 * ndev));
         for (size_t i = 1; i <= k; ++i) cut.push_back(first + rest * i / k);
     }
     const size_t n_chunks = cut.size() - 1;
     auto chunk_lo = [&](size_t k) { return cut[std::min(k, n_chunks)]; };
 
+    // Two chunks are in flight at any time (the library runs two calls side by side, one per lane): while
+    // chunk k is on the device, chunk k+1 is already queued behind it - its copies and classification run
+    // during chunk k's kernels, its CTAs fill the SMs chunk k's kernel frees in its tail - and this thread
+    // packs chunk k+2 into the third slot, then scatters chunk k-1... in short: the device never waits.
+    struct Flight {
+        std::thread th;
+        int rc = HYPO_OK;
+        std::string err;
+        double sec = 0;
+    };
+    std::vector<Flight> fl(n_chunks);
+    auto start = [&](size_t k) {
+        Slot& cur = _slot[k % 3];
+        Flight& f = fl[k];
+        f.th = std::thread([&cur, &f]() {
+            const double d0 = omp_get_wtime();
+            f.rc = hypo_gpu_consensus_batch(cur.win, cur.n_win, cur.arms, cur.n_arms, cur.packed, cur.n_bytes, cur.out,
+                                            cur.out_cap, cur.off);
+            if (f.rc != HYPO_OK) f.err = hypo_gpu_last_error();
+            f.sec = omp_get_wtime() - d0;
+        });
+    };
     double t0 = omp_get_wtime();
     pack_chunk(_slot[0], 0, chunk_lo(1), threads);
     _timing.pack += omp_get_wtime() - t0;
+    start(0);
+    if (n_chunks > 1) {
+        t0 = omp_get_wtime();
+        pack_chunk(_slot[1], chunk_lo(1), chunk_lo(2) - chunk_lo(1), threads_ov);
+        _timing.pack += omp_get_wtime() - t0;
+        start(1);
+    }
     for (size_t k = 0; k < n_chunks; ++k) {
-        Slot& cur = _slot[k & 1];
-        int rc = HYPO_OK;
-        std::string err;
-        double dev_sec = 0;
-        // the device call of chunk k on its own thread ...
-        std::thread worker([&]() {
-            const double d0 = omp_get_wtime();
-            rc = hypo_gpu_consensus_batch(cur.win, cur.n_win, cur.arms, cur.n_arms, cur.packed, cur.n_bytes, cur.out,
-                                          cur.out_cap, cur.off);
-            if (rc != HYPO_OK) err = hypo_gpu_last_error();
-            dev_sec = omp_get_wtime() - d0;
-        });
-        // ... while this thread scatters chunk k-1 and then packs chunk k+1 into the slot that frees
-        if (k > 0) {
-            t0 = omp_get_wtime();
-            scatter_chunk(_slot[(k - 1) & 1], threads_ov);
-            _timing.scatter += omp_get_wtime() - t0;
-        }
-        if (k + 1 < n_chunks) {
-            t0 = omp_get_wtime();
-            pack_chunk(_slot[(k + 1) & 1], chunk_lo(k + 1), chunk_lo(k + 2) - chunk_lo(k + 1), threads_ov);
-            _timing.pack += omp_get_wtime() - t0;
-        }
-        worker.join();
-        _timing.device += dev_sec;
-        if (rc != HYPO_OK) {
-            fprintf(stderr, "[Hypo::GPU] Error: POA of windows: %s\n", err.c_str());
+        fl[k].th.join();
+        _timing.device += fl[k].sec;
+        if (fl[k].rc != HYPO_OK) {
+            for (size_t j = k + 1; j < n_chunks; ++j) if (fl[j].th.joinable()) fl[j].th.join();
+            fprintf(stderr, "[Hypo::GPU] Error: POA of windows: %s\n", fl[k].err.c_str());
             exit(1);
         }
+        if (k + 2 < n_chunks) {   // slot (k+2) % 3 == (k-1) % 3 was scattered one iteration ago
+            t0 = omp_get_wtime();
+            pack_chunk(_slot[(k + 2) % 3], chunk_lo(k + 2), chunk_lo(k + 3) - chunk_lo(k + 2), threads_ov);
+            _timing.pack += omp_get_wtime() - t0;
+            start(k + 2);
+        }
+        t0 = omp_get_wtime();
+        scatter_chunk(_slot[k % 3], k + 1 < n_chunks ? threads_ov : threads);
+        _timing.scatter += omp_get_wtime() - t0;
     }
-    t0 = omp_get_wtime();
-    scatter_chunk(_slot[(n_chunks - 1) & 1], threads);
-    _timing.scatter += omp_get_wtime() - t0;
     _timing.chunks = n_chunks;
     _timing.total = omp_get_wtime() - t_begin;
 }

@@ -23,10 +23,11 @@ namespace hypo {
 // thread count (a million 30-arm windows are 31 M small copies: ~1 s on one thread, which would be
 // twice the GPU's time for them).  The scatter of the consensus strings is parallel as well.
 //
-// run() streams: the windows are cut into chunks, and while chunk k is on the device(s) - a worker
-// thread sits in hypo_gpu_consensus_batch - the calling thread packs chunk k+1 into the other of two
-// page-locked buffer sets and scatters the consensus strings of chunk k-1 into their Window objects.
-// Packing, copies and scatter hide behind the kernels as long as the host keeps up.
+// run() streams: the windows are cut into chunks and TWO chunks are in flight at a time (the library runs two
+// batch calls side by side, one per lane; a worker thread sits in hypo_gpu_consensus_batch for each) while
+// the calling thread packs the next chunk into the third of three page-locked buffer sets and scatters the
+// consensus strings of the chunk that just finished into their Window objects.  Packing, copies, compaction,
+// result copies and scatter hide behind the kernels as long as the host keeps up.
 class WindowBatch {
 public:
     struct Timing {
@@ -81,7 +82,7 @@ private:
     std::unique_ptr<uint8_t[]> _packed;   // (not a vector: no zero-fill of a slab that is overwritten anyway)
     size_t _packed_bytes = 0;
     size_t _n_packed = 0;                 // windows covered by the buffers above
-    Slot _slot[2];
+    Slot _slot[3];   // one being packed / scattered, two in flight
     Timing _timing;
     uint64_t _bp = 0;
 };
