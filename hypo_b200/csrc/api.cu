@@ -1269,6 +1269,48 @@ int hypo_gpu_consensus_batch(const HypoWindowDesc* win, uint64_t n_win, const Hy
     return HYPO_OK;
 }
 
+// The device part of the stitcher: region lengths, positions, copies, result to the host.
+static int stitch_core(Ctx& g, const RegionDesc* d_reg, uint64_t n_regions, const uint32_t* d_reg_contig,
+                       const uint8_t* d_drafts, const uint64_t* d_doff, const char* d_cons, const uint64_t* d_coff,
+                       uint64_t n_win, const uint64_t* contig_first_region, uint64_t n_contigs, char* out,
+                       uint64_t out_cap, uint64_t* out_off, cudaStream_t s) {
+    CUDA_TRY(g.st_len.reserve(sizeof(uint64_t) * (n_regions + 1)));
+    CUDA_TRY(g.st_pos.reserve(sizeof(uint64_t) * (n_regions + 1)));
+    CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
+    uint32_t* d_bad = &((DevCtrl*)g.ctrl.p)->bad;
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s));
+    uint64_t* d_len = (uint64_t*)g.st_len.p;
+    uint64_t* d_pos = (uint64_t*)g.st_pos.p;
+    const int tb = 256;
+    region_len_kernel<<<(unsigned)((n_regions + tb - 1) / tb), tb, 0, s>>>(d_reg, n_regions, d_coff, n_win, d_len, d_bad);
+    CUDA_TRY(cudaMemsetAsync(d_len + n_regions, 0, sizeof(uint64_t), s));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_pos, n_regions + 1, s));
+    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = g.cub_tmp.cap;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len, d_pos, n_regions + 1, s));
+    uint64_t* h64 = host_words(g);
+    CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_regions, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h64 + 1, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const uint64_t total = h64[0];
+    if (*(uint32_t*)(h64 + 1)) return fail(HYPO_E_ARG, "a region names a window beyond the batch");
+    if (total > out_cap) return fail(HYPO_E_OUT_CAP, "stitched output needs %llu bytes, out_cap is %llu",
+                                     (unsigned long long)total, (unsigned long long)out_cap);
+    CUDA_TRY(g.st_out.reserve(total + 16));
+    stitch_kernel<<<(unsigned)((n_regions * 32 + tb - 1) / tb), tb, 0, s>>>(d_reg, n_regions, d_reg_contig, d_drafts, d_doff,
+                                                                          d_cons, d_coff, d_pos, (char*)g.st_out.p);
+    G.launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (total) CUDA_TRY(cudaMemcpyAsync(out, g.st_out.p, total, cudaMemcpyDeviceToHost, s));
+    // the contigs' starts: position of their first region
+    std::vector<uint64_t> pos_host(n_regions + 1);
+    CUDA_TRY(cudaMemcpyAsync(pos_host.data(), d_pos, sizeof(uint64_t) * (n_regions + 1), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint64_t c = 0; c <= n_contigs; ++c) out_off[c] = pos_host[contig_first_region[c]];
+    return HYPO_OK;
+}
+
 int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uint64_t* contig_first_region,
                     uint64_t n_contigs, const uint8_t* drafts, const uint64_t* draft_off, uint64_t draft_bytes,
                     const char* cons, const uint64_t* cons_off, uint64_t n_win, char* out, uint64_t out_cap,
@@ -1321,47 +1363,92 @@ int hypo_gpu_stitch(const HypoRegionDesc* regions, uint64_t n_regions, const uin
     CUDA_TRY(g.st_contig.reserve(sizeof(uint32_t) * n_regions));
     CUDA_TRY(g.st_draft.reserve(draft_bytes + 16));
     CUDA_TRY(g.st_doff.reserve(sizeof(uint64_t) * n_contigs));
-    CUDA_TRY(g.st_len.reserve(sizeof(uint64_t) * (n_regions + 1)));
-    CUDA_TRY(g.st_pos.reserve(sizeof(uint64_t) * (n_regions + 1)));
-    CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
     CUDA_TRY(cudaMemcpyAsync(g.st_reg.p, regions, sizeof(RegionDesc) * n_regions, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(g.st_contig.p, reg_contig.data(), sizeof(uint32_t) * n_regions, cudaMemcpyHostToDevice, s));
     if (draft_bytes) CUDA_TRY(cudaMemcpyAsync(g.st_draft.p, drafts, draft_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(g.st_doff.p, draft_off, sizeof(uint64_t) * n_contigs, cudaMemcpyHostToDevice, s));
-    uint32_t* d_bad = &((DevCtrl*)g.ctrl.p)->bad;
-    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s));
-    uint64_t* d_len = (uint64_t*)g.st_len.p;
-    uint64_t* d_pos = (uint64_t*)g.st_pos.p;
-    const int tb = 256;
-    region_len_kernel<<<(unsigned)((n_regions + tb - 1) / tb), tb, 0, s>>>((const RegionDesc*)g.st_reg.p, n_regions, d_coff, n_win,
-                                                                         d_len, d_bad);
-    CUDA_TRY(cudaMemsetAsync(d_len + n_regions, 0, sizeof(uint64_t), s));
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_pos, n_regions + 1, s));
-    CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
-    tmp_bytes = g.cub_tmp.cap;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len, d_pos, n_regions + 1, s));
-    uint64_t* h64 = host_words(g);
-    CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_regions, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h64 + 1, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    const uint64_t total = h64[0];
-    if (*(uint32_t*)(h64 + 1)) return fail(HYPO_E_ARG, "a region names a window beyond the batch");
-    if (total > out_cap) return fail(HYPO_E_OUT_CAP, "stitched output needs %llu bytes, out_cap is %llu",
-                                     (unsigned long long)total, (unsigned long long)out_cap);
-    CUDA_TRY(g.st_out.reserve(total + 16));
-    stitch_kernel<<<(unsigned)((n_regions * 32 + tb - 1) / tb), tb, 0, s>>>(
-        (const RegionDesc*)g.st_reg.p, n_regions, (const uint32_t*)g.st_contig.p, (const uint8_t*)g.st_draft.p,
-        (const uint64_t*)g.st_doff.p, d_cons, d_coff, d_pos, (char*)g.st_out.p);
-    G.launches += 3;
-    CUDA_TRY(cudaGetLastError());
-    if (total) CUDA_TRY(cudaMemcpyAsync(out, g.st_out.p, total, cudaMemcpyDeviceToHost, s));
-    // the contigs' starts: position of their first region
-    std::vector<uint64_t> pos_host(n_regions + 1);
-    CUDA_TRY(cudaMemcpyAsync(pos_host.data(), d_pos, sizeof(uint64_t) * (n_regions + 1), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    for (uint64_t c = 0; c <= n_contigs; ++c) out_off[c] = pos_host[contig_first_region[c]];
-    return HYPO_OK;
+    const int rc = stitch_core(g, (const RegionDesc*)g.st_reg.p, n_regions, (const uint32_t*)g.st_contig.p,
+                               (const uint8_t*)g.st_draft.p, (const uint64_t*)g.st_doff.p, d_cons, d_coff, n_win,
+                               contig_first_region, n_contigs, out, out_cap, out_off, s);
+    if (rc == HYPO_OK) CUDA_TRY(cudaStreamSynchronize(s));   // (reg_contig lives on this stack frame)
+    return rc;
+}
+
+// ---- internal entry points for arms.cu (same library; not part of the ABI) ------------------------------------
+int hypo_internal_fail(int code, const char* msg) {
+    g_err = msg ? msg : "";
+    return code;
+}
+
+int hypo_internal_primary_device(void) {
+    std::shared_lock<std::shared_mutex> lk(g_state_mu);
+    return G.init ? G.dev[0]->device : -1;
+}
+
+// A device-resident batch -> consensus of every window -> contigs stitched from device-resident region
+// descriptors; only the polished contigs travel to the host.
+int hypo_internal_polish_device(const HypoWindowDesc* d_win, uint64_t n_win, const HypoArmDesc* d_arms, uint64_t n_arms,
+                                const uint8_t* d_packed, uint64_t packed_bytes, const HypoRegionDesc* d_regions,
+                                const uint32_t* d_reg_contig, uint64_t n_regions, const uint64_t* contig_first_region,
+                                uint64_t n_contigs, const uint8_t* d_drafts, const uint64_t* d_draft_off, char* out,
+                                uint64_t out_cap, uint64_t* out_off, void* /*stream*/) {
+    LaneLock lk(false);
+    if (!G.init) return fail(HYPO_E_NOT_INIT, "hypo_gpu_init has not been called");
+    if (G.n_dev != 1) return fail(HYPO_E_ARG, "hypo_gpu_polish_alignments drives one device");
+    Ctx& g = *G.dev[0];
+    CUDA_TRY(cudaSetDevice(g.device));
+    cudaStream_t s = g.stream;
+    for (uint64_t c = 0; c <= n_contigs; ++c) out_off[c] = 0;
+    if (n_regions == 0 || n_contigs == 0) return HYPO_OK;
+    g.resident_windows = 0;
+    CUDA_TRY(g.out_off.reserve(sizeof(uint64_t) * (n_win + 2)));
+    uint64_t* d_off = (uint64_t*)g.out_off.p;
+    if (n_win) {
+        CUDA_TRY(g.out_pos.reserve(sizeof(uint64_t) * (n_win + 1)));
+        CUDA_TRY(g.out_len.reserve(sizeof(uint32_t) * n_win));
+        CUDA_TRY(g.stats.reserve(sizeof(WinStat) * n_win + 128));
+        uint64_t* d_bound = d_off;
+        uint64_t* d_pos = (uint64_t*)g.out_pos.p;
+        uint64_t* h64 = host_words(g);
+        size_t tmp_bytes = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+        CUDA_TRY(g.cub_tmp.reserve(tmp_bytes + 256));
+        tmp_bytes = g.cub_tmp.cap;
+        if (int rc = stage_classify(g, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, 0, n_arms, 0, packed_bytes,
+                                    (WinStat*)g.stats.p, d_bound, s))
+            return rc;
+        CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, n_win + 1, s));
+        ++G.launches;
+        CUDA_TRY(cudaMemcpyAsync(h64, d_pos + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(fetch_ctrl(g, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (int rc = check_bad(g, false)) return rc;
+        CUDA_TRY(g.out_scratch.reserve(*h64 + 16));
+        CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
+        G.last = 0;
+        if (int rc = stage_tiers(g, 0, (const WinDesc*)d_win, n_win, (const ArmDesc*)d_arms, d_packed, packed_bytes,
+                                 (char*)g.out_scratch.p, d_pos, (uint32_t*)g.out_len.p, (const WinStat*)g.stats.p, s))
+            return rc;
+        uint64_t* d_len64 = (uint64_t*)g.lists.p;
+        const int tb = 256;
+        widen_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, s>>>((const uint32_t*)g.out_len.p, d_len64, n_win);
+        CUDA_TRY(cudaMemsetAsync(d_len64 + n_win, 0, sizeof(uint64_t), s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_len64, d_off, n_win + 1, s));
+        CUDA_TRY(cudaMemcpyAsync(h64, d_off + n_win, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(g.out_compact.reserve(*h64 + 16));
+        gather_kernel<<<(unsigned)((n_win * 32 + tb - 1) / tb), tb, 0, s>>>((const char*)g.out_scratch.p, d_pos,
+                                                                          (const uint32_t*)g.out_len.p, d_off,
+                                                                          (char*)g.out_compact.p, n_win);
+        G.launches += 3;
+        g.resident_windows = n_win;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_off, 0, sizeof(uint64_t) * 2, s));
+        CUDA_TRY(g.out_compact.reserve(16));
+    }
+    return stitch_core(g, (const RegionDesc*)d_regions, n_regions, d_reg_contig, d_drafts, d_draft_off,
+                       (const char*)g.out_compact.p, d_off, n_win, contig_first_region, n_contigs, out, out_cap, out_off, s);
 }
 
 int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, const uint32_t* d_out_len,

@@ -27,6 +27,8 @@ ABI_SYMBOLS = (
     "hypo_gpu_last_fail_hist",
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
+    "hypo_gpu_extract_arms",
+    "hypo_gpu_polish_alignments",
     "hypo_gpu_stitch",
     "hypo_gpu_last_rerouted",
     "hypo_gpu_last_cells",
@@ -131,6 +133,60 @@ def window_bounds(batch: WindowBatch) -> np.ndarray:
     _check(lib().hypo_gpu_window_bounds(batch.win.ctypes.data, batch.n_win, batch.arms.ctypes.data, batch.n_arms,
                                         b.ctypes.data))
     return b
+
+
+REGION_DTYPE = np.dtype([("key0", "<u8"), ("key1", "<u8"), ("start", "<u4"), ("type", "<u4")])
+CONTIG_DTYPE = np.dtype([("first_region", "<u8"), ("draft_off", "<u8"), ("n_regions", "<u4"), ("len", "<u4")])
+ALN_DTYPE = np.dtype([("cigar_off", "<u8"), ("seq_off", "<u8"), ("contig", "<u4"), ("pos", "<u4"), ("n_cigar", "<u4"),
+                      ("l_qseq", "<u4")])
+REGION_TYPES = {"SR": 0, "MSR": 1, "SWS": 2, "WS": 3, "SW": 4, "MWM": 5, "WM": 6, "MW": 7, "SWM": 8, "MWS": 9, "OTH": 10}
+assert REGION_DTYPE.itemsize == 24 and CONTIG_DTYPE.itemsize == 24 and ALN_DTYPE.itemsize == 32
+
+
+def extract_arms(contigs, regions, drafts, alns, cigar, seqs, k: int):
+    """hypo_gpu_extract_arms: alignments + region tables -> (WindowBatch, win_region)."""
+    from .batch import ARM_DTYPE, WIN_DTYPE
+    L = lib()
+    L.hypo_gpu_extract_arms.restype = C.c_int
+    sizes = (C.c_uint64 * 3)()
+    win_cap, arm_cap, byte_cap = len(regions) + 1, int(max(1, cigar.size * 0 + 1)), 1
+    # first call with empty buffers reports the sizes
+    for attempt in range(2):
+        win = np.zeros(win_cap, WIN_DTYPE)
+        win_region = np.zeros(win_cap, np.uint64)
+        arms = np.zeros(arm_cap, ARM_DTYPE)
+        packed = np.zeros(byte_cap + 16, np.uint8)
+        rc = L.hypo_gpu_extract_arms(
+            C.c_void_p(contigs.ctypes.data), C.c_uint64(len(contigs)), C.c_void_p(regions.ctypes.data),
+            C.c_uint64(len(regions)), C.c_void_p(drafts.ctypes.data), C.c_uint64(drafts.size),
+            C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)), C.c_void_p(cigar.ctypes.data), C.c_uint64(cigar.size),
+            C.c_void_p(seqs.ctypes.data), C.c_uint64(seqs.size), C.c_uint32(k),
+            C.c_void_p(win.ctypes.data), C.c_uint64(win_cap), C.byref(sizes, 0), C.c_void_p(win_region.ctypes.data),
+            C.c_void_p(arms.ctypes.data), C.c_uint64(arm_cap), C.byref(sizes, 8),
+            C.c_void_p(packed.ctypes.data), C.c_uint64(byte_cap), C.byref(sizes, 16))
+        n_win, n_arms, n_bytes = int(sizes[0]), int(sizes[1]), int(sizes[2])
+        if rc == 4 and attempt == 0:   # HYPO_E_OUT_CAP: now the sizes are known
+            win_cap, arm_cap, byte_cap = max(n_win, 1), max(n_arms, 1), max(n_bytes, 1)
+            continue
+        _check(rc)
+        break
+    return WindowBatch(win[:n_win].copy(), arms[:n_arms].copy(), packed[: n_bytes + 16].copy(), {}), win_region[:n_win].copy()
+
+
+def polish_alignments(contigs, regions, drafts, alns, cigar, seqs, k: int) -> List[str]:
+    """hypo_gpu_polish_alignments: alignments + region tables -> polished contigs."""
+    L = lib()
+    L.hypo_gpu_polish_alignments.restype = C.c_int
+    cap = int(contigs["len"].astype(np.int64).sum()) * 2 + 1024
+    out = np.zeros(cap, np.uint8)
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    _check(L.hypo_gpu_polish_alignments(
+        C.c_void_p(contigs.ctypes.data), C.c_uint64(len(contigs)), C.c_void_p(regions.ctypes.data),
+        C.c_uint64(len(regions)), C.c_void_p(drafts.ctypes.data), C.c_uint64(drafts.size),
+        C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)), C.c_void_p(cigar.ctypes.data), C.c_uint64(cigar.size),
+        C.c_void_p(seqs.ctypes.data), C.c_uint64(seqs.size), C.c_uint32(k),
+        C.c_void_p(out.ctypes.data), C.c_uint64(cap), C.c_void_p(off.ctypes.data)))
+    return split_consensus(out, off)
 
 
 def shutdown() -> None:

@@ -202,6 +202,89 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
 int hypo_gpu_last_fail_hist(uint32_t reasons[16]);
 
 /*
+ * Arm extraction: the step that FEEDS the path.  Replaces, for short reads,
+ *     Alignment::initialise_pos / copy_data        reference src/Alignment.cpp:513-576
+ *     Alignment::find_short_arms / find_bp         reference src/Alignment.cpp:222-259,321-404
+ *     Alignment::prepare_short_arm                 reference src/Alignment.cpp:406-509
+ *     Alignment::add_arms + the pruning rules of Contig::fill_short_windows
+ *                                                  reference src/Alignment.cpp:299-318, src/Contig.cpp:249-289
+ * and the host batch packer: the reads' bases go from the BAM records straight into the packed slab of the
+ * batch, on the device.  Inputs are what the reference holds at that point of Hypo::polish
+ * (src/Hypo.cpp:196-232), all host pointers:
+ *   contigs / regions : the region table of every contig (Contig::_reg_pos / _reg_type / _reg_info /
+ *                       _anchor_kmers): regions of contig c are [first_region, first_region + n_regions),
+ *                       sorted by start; a strong region carries the k-mers at its first and last k bases
+ *                       (src/Contig.cpp:128-129), a minimiser region the minimiser (:596,614)
+ *   drafts            : the contigs' PackedSeq<4> bytes (Contig::_pseq), contig c at draft_off
+ *   alns / cigar / seqs : the alignments the reference keeps (src/Hypo.cpp:296-300), in file order:
+ *                       core.pos, the BAM CIGAR words (len << 4 | op) and bam_get_seq() bytes verbatim
+ *                       (two bases per byte, high nibble first, A1 C2 G4 T8); soft clips are cut off on the
+ *                       device, a read with another base in its aligned part is dropped like the reference
+ *                       drops it (PackedSeq<2> cannot hold it, src/Alignment.cpp:556-571)
+ *   k                 : the solid k-mer length (anchors); the minimiser length is 10 (src/main.cpp:86)
+ * Outputs (host): the batch exactly as WindowBatch::pack would lay it out for the windows the reference
+ * ends up with - dropped windows are absent, prefix / suffix arms already cleared where the reference
+ * clears them, arms in alignment order - plus win_region[w], the region (batch-wide index) window w polishes.
+ * *n_win / *n_arms / *packed_bytes report the sizes; HYPO_E_OUT_CAP if a capacity is too small (sizes are
+ * still reported).
+ */
+#define HYPO_REG_SR  0u
+#define HYPO_REG_MSR 1u
+#define HYPO_REG_SWS 2u
+#define HYPO_REG_WS  3u
+#define HYPO_REG_SW  4u
+#define HYPO_REG_MWM 5u
+#define HYPO_REG_WM  6u
+#define HYPO_REG_MW  7u
+#define HYPO_REG_SWM 8u
+#define HYPO_REG_MWS 9u
+#define HYPO_REG_OTHER 10u
+typedef struct HypoRegionRec {
+    uint64_t key0;         /* strong region: its first k-mer (2 bits per base, first base highest); minimiser region: the minimiser */
+    uint64_t key1;         /* strong region: its last k-mer                                        */
+    uint32_t start;        /* first base of the region on its contig                               */
+    uint32_t type;         /* HYPO_REG_*                                                           */
+} HypoRegionRec;           /* 24 bytes */
+typedef struct HypoContigDesc {
+    uint64_t first_region; /* index of the contig's first region in `regions`                      */
+    uint64_t draft_off;    /* byte offset of the contig's PackedSeq<4> draft in `drafts`           */
+    uint32_t n_regions;
+    uint32_t len;          /* contig length in bases                                               */
+} HypoContigDesc;          /* 24 bytes */
+typedef struct HypoAlnDesc {
+    uint64_t cigar_off;    /* index of the first CIGAR word of this alignment in `cigar`           */
+    uint64_t seq_off;      /* byte offset of bam_get_seq() of this read in `seqs`                  */
+    uint32_t contig;
+    uint32_t pos;          /* core.pos (0-based)                                                   */
+    uint32_t n_cigar;
+    uint32_t l_qseq;
+} HypoAlnDesc;             /* 32 bytes */
+int hypo_gpu_extract_arms(const HypoContigDesc* contigs, uint64_t n_contigs,
+                          const HypoRegionRec* regions, uint64_t n_regions,
+                          const uint8_t* drafts, uint64_t draft_bytes,
+                          const HypoAlnDesc* alns, uint64_t n_alns,
+                          const uint32_t* cigar, uint64_t n_cigar,
+                          const uint8_t* seqs, uint64_t seq_bytes, uint32_t k,
+                          HypoWindowDesc* win, uint64_t win_cap, uint64_t* n_win, uint64_t* win_region,
+                          HypoArmDesc* arms, uint64_t arm_cap, uint64_t* n_arms,
+                          uint8_t* packed, uint64_t packed_cap, uint64_t* packed_bytes);
+
+/*
+ * The fused step: alignments in, polished contigs out - arm extraction, the POA consensus of every window
+ * and the stitching of the contigs without the batch or the consensus strings ever visiting the host
+ * (Hypo::polish from "Short arms computing" to "Writing results", reference src/Hypo.cpp:196-267, for short
+ * reads).  Same inputs as hypo_gpu_extract_arms; out receives the polished contigs back to back, out_off
+ * (n_contigs + 1 entries) their starts.  One driven device.
+ */
+int hypo_gpu_polish_alignments(const HypoContigDesc* contigs, uint64_t n_contigs,
+                               const HypoRegionRec* regions, uint64_t n_regions,
+                               const uint8_t* drafts, uint64_t draft_bytes,
+                               const HypoAlnDesc* alns, uint64_t n_alns,
+                               const uint32_t* cigar, uint64_t n_cigar,
+                               const uint8_t* seqs, uint64_t seq_bytes, uint32_t k,
+                               char* out, uint64_t out_cap, uint64_t* out_off);
+
+/*
  * Output stitching: the step after the path.  Replaces the region loop of Contig::operator<<
  * (reference src/Contig.cpp:345-366): the polished contig is its regions in order - a strong region
  * (or a window nobody polished) is copied from the contig's PackedSeq<4> draft, a polished window is

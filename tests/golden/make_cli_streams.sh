@@ -15,3 +15,4 @@ gzip -9 -n -c "$W/short/aux/inspect_ctg1.txt" > "$HERE/cli_short_60kb.inspect.gz
 gzip -9 -n -c "$W/long/aux/inspect_ctg1.txt" > "$HERE/cli_long_60kb.inspect.gz"
 gzip -9 -n -c "$W/short/polished.fa" > "$HERE/cli_short_60kb.polished.fa.gz"   # the reference CLI's own output
 gzip -9 -n -c "$W/long/polished.fa" > "$HERE/cli_long_60kb.polished.fa.gz"
+gzip -9 -n -c "$W/short/sr.sam" > "$HERE/cli_short_60kb.sam.gz"   # the alignments the run read (input of arm extraction)
