@@ -29,6 +29,8 @@ ABI_SYMBOLS = (
     "hypo_gpu_last_timing",
     "hypo_gpu_extract_arms",
     "hypo_gpu_polish_alignments",
+    "hypo_gpu_solid_kmer_support",
+    "hypo_gpu_minimiser_support",
     "hypo_gpu_stitch",
     "hypo_gpu_last_rerouted",
     "hypo_gpu_last_cells",
@@ -171,6 +173,35 @@ def extract_arms(contigs, regions, drafts, alns, cigar, seqs, k: int):
         _check(rc)
         break
     return WindowBatch(win[:n_win].copy(), arms[:n_arms].copy(), packed[: n_bytes + 16].copy(), {}), win_region[:n_win].copy()
+
+
+def solid_kmer_support(contig_first_kmer, solid_pos, kmer_id, alns, cigar, seqs, k: int):
+    """hypo_gpu_solid_kmer_support -> (coverage, support) per solid k-mer."""
+    L = lib()
+    L.hypo_gpu_solid_kmer_support.restype = C.c_int
+    n = int(solid_pos.size)
+    cov, sup = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+    _check(L.hypo_gpu_solid_kmer_support(
+        C.c_void_p(contig_first_kmer.ctypes.data), C.c_uint64(len(contig_first_kmer) - 1), C.c_void_p(solid_pos.ctypes.data),
+        C.c_void_p(kmer_id.ctypes.data), C.c_uint64(n), C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)),
+        C.c_void_p(cigar.ctypes.data), C.c_uint64(cigar.size), C.c_void_p(seqs.ctypes.data), C.c_uint64(seqs.size),
+        C.c_uint32(k), C.c_void_p(cov.ctypes.data), C.c_void_p(sup.ctypes.data)))
+    return cov[:n], sup[:n]
+
+
+def minimiser_support(contig_first_bound, contig_even, bounds, region_first_mini, mini_pos, mini_val, alns, cigar, seqs):
+    """hypo_gpu_minimiser_support -> (coverage, support) per minimiser."""
+    L = lib()
+    L.hypo_gpu_minimiser_support.restype = C.c_int
+    n = int(mini_pos.size)
+    cov, sup = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+    _check(L.hypo_gpu_minimiser_support(
+        C.c_void_p(contig_first_bound.ctypes.data), C.c_void_p(contig_even.ctypes.data), C.c_uint64(len(contig_even)),
+        C.c_void_p(bounds.ctypes.data), C.c_uint64(bounds.size), C.c_void_p(region_first_mini.ctypes.data),
+        C.c_void_p(mini_pos.ctypes.data), C.c_void_p(mini_val.ctypes.data), C.c_uint64(n),
+        C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)), C.c_void_p(cigar.ctypes.data), C.c_uint64(cigar.size),
+        C.c_void_p(seqs.ctypes.data), C.c_uint64(seqs.size), C.c_void_p(cov.ctypes.data), C.c_void_p(sup.ctypes.data)))
+    return cov[:n], sup[:n]
 
 
 def polish_alignments(contigs, regions, drafts, alns, cigar, seqs, k: int) -> List[str]:

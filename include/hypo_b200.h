@@ -285,6 +285,48 @@ int hypo_gpu_polish_alignments(const HypoContigDesc* contigs, uint64_t n_contigs
                                char* out, uint64_t out_cap, uint64_t* out_off);
 
 /*
+ * Support counting: the step before windowing.  Replaces the two OpenMP loops of
+ * Hypo::polish over the alignments of a contig batch (reference src/Hypo.cpp:135-171):
+ *     Alignment::update_solidkmers_support      reference src/Alignment.cpp:65-131
+ *     Alignment::update_minimisers_support      reference src/Alignment.cpp:133-220
+ * The reference increments 16-bit counters under a mutex per k-mer / per region (include/Contig.hpp:40-52,
+ * 207-214); here one thread per alignment adds to 32-bit counters with device atomics (identical values as
+ * long as no counter passes 65 535).  Alignments are given as for hypo_gpu_extract_arms (position, BAM CIGAR
+ * words, bam_get_seq() bytes; soft clips are cut off, reads with a base other than A/C/G/T in the aligned
+ * part are skipped like the reference drops them).  All pointers are host pointers.
+ *
+ * hypo_gpu_solid_kmer_support:
+ *   contig_first_kmer[c] .. [c+1] : the solid k-mers of contig c (Contig::_solid_pos / _kmerinfo,
+ *                                   src/Contig.cpp:40-74), sorted by position: solid_pos[] and kmer_id[]
+ *                                   (the k-mer, 2 bits per base, first base highest)
+ *   coverage[i] / support[i]      : out, per solid k-mer (KmerInfo::coverage / support)
+ * hypo_gpu_minimiser_support (after Contig::prepare_for_division, src/Contig.cpp:75-186):
+ *   contig_first_bound[c] .. [c+1]: the boundaries between strong regions and the regions in between of
+ *                                   contig c (set bits of Contig::_reg_pos at that stage, 0 and the contig
+ *                                   length included), bounds[]
+ *   contig_even[c]                : Contig::_is_win_even (the regions with even index are the weak ones)
+ *   region_first_mini[r] .. [r+1] : the minimisers of the region that starts at bounds[r] (none for strong
+ *                                   regions): mini_pos[] absolute positions, mini_val[] the minimisers
+ *                                   (MWMinimiserInfo::rel_pos accumulated / ::minimisers); one entry per
+ *                                   bound plus the end
+ *   coverage[i] / support[i]      : out, per minimiser (MWMinimiserInfo::coverage / support)
+ */
+int hypo_gpu_solid_kmer_support(const uint64_t* contig_first_kmer, uint64_t n_contigs,
+                                const uint32_t* solid_pos, const uint64_t* kmer_id, uint64_t n_kmers,
+                                const HypoAlnDesc* alns, uint64_t n_alns,
+                                const uint32_t* cigar, uint64_t n_cigar,
+                                const uint8_t* seqs, uint64_t seq_bytes, uint32_t k,
+                                uint32_t* coverage, uint32_t* support);
+int hypo_gpu_minimiser_support(const uint64_t* contig_first_bound, const uint8_t* contig_even, uint64_t n_contigs,
+                               const uint32_t* bounds, uint64_t n_bounds,
+                               const uint64_t* region_first_mini,
+                               const uint32_t* mini_pos, const uint32_t* mini_val, uint64_t n_minis,
+                               const HypoAlnDesc* alns, uint64_t n_alns,
+                               const uint32_t* cigar, uint64_t n_cigar,
+                               const uint8_t* seqs, uint64_t seq_bytes,
+                               uint32_t* coverage, uint32_t* support);
+
+/*
  * Output stitching: the step after the path.  Replaces the region loop of Contig::operator<<
  * (reference src/Contig.cpp:345-366): the polished contig is its regions in order - a strong region
  * (or a window nobody polished) is copied from the contig's PackedSeq<4> draft, a polished window is

@@ -16,3 +16,7 @@ gzip -9 -n -c "$W/long/aux/inspect_ctg1.txt" > "$HERE/cli_long_60kb.inspect.gz"
 gzip -9 -n -c "$W/short/polished.fa" > "$HERE/cli_short_60kb.polished.fa.gz"   # the reference CLI's own output
 gzip -9 -n -c "$W/long/polished.fa" > "$HERE/cli_long_60kb.polished.fa.gz"
 gzip -9 -n -c "$W/short/sr.sam" > "$HERE/cli_short_60kb.sam.gz"   # the alignments the run read (input of arm extraction)
+# support counters of the same run (tools/capture: hypo_dump2 = the dump-enabled CLI + two more dumps)
+(cd "$W/short" && printf 'a b c 1\n' > aux/stage.txt && /tmp/hypo_cli/hypo_dump2 -r reads.fq -d draft.fa -b sr.sam $(cat cli_args.txt) -t 8 -i -o polished_dump2.fa > hypo_dump2.log 2>&1 && cmp polished.fa polished_dump2.fa)
+gzip -9 -n -c "$W/short/aux/kmer_support_ctg1.txt" > "$HERE/cli_short_60kb.kmer_support.gz"
+gzip -9 -n -c "$W/short/aux/minimiser_support_ctg1.txt" > "$HERE/cli_short_60kb.minimiser_support.gz"
