@@ -33,6 +33,26 @@ def main():
     extract = (time.perf_counter() - t0) / steps
     ref = meta["reference_phase_s"]
     ref_sum = sum(ref[p] for p in meta["replaced_phases"])
+    n2 = None
+    if "spos" in z:   # support counting (N2) on the same alignments, against the counters the reference dumped
+        a3 = (z["alns"], z["cigar"], z["seqs"])
+        c, s = native.solid_kmer_support(z["kfirst"], z["spos"], z["kid"], *a3, int(meta["k"]))
+        ok_k = bool((c == z["kcov"]).all() and (s == z["ksup"]).all())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            native.solid_kmer_support(z["kfirst"], z["spos"], z["kid"], *a3, int(meta["k"]))
+        t_k = (time.perf_counter() - t0) / steps
+        c, s = native.minimiser_support(z["bfirst"], z["even"], z["bounds"], z["rfirst"], z["mpos"], z["mval"], *a3)
+        ok_m = bool((c == z["mcov"]).all() and (s == z["msup"]).all())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            native.minimiser_support(z["bfirst"], z["even"], z["bounds"], z["rfirst"], z["mpos"], z["mval"], *a3)
+        t_m = (time.perf_counter() - t0) / steps
+        n2 = {"solid_kmers": int(z["spos"].size), "minimisers": int(z["mpos"].size),
+              "solid_kmer_support_s": t_k, "minimiser_support_s": t_m,
+              "counters_identical_to_reference_cli": {"solid_kmers": ok_k, "minimisers": ok_m},
+              "reference_cli_s": {"Solid kmers support update": ref.get("Solid kmers support update"),
+                                  "Minimisers support update": ref.get("Minimisers support update")}}
     h2d = sum(int(a.nbytes) for a in args[:6])
     print(json.dumps({
         "input": os.path.basename(sys.argv[1]), "alignments": int(len(z["alns"])), "regions": int(len(z["regions"])),
@@ -42,7 +62,7 @@ def main():
         "h2d_bytes": h2d, "polished_contigs_identical_to_reference_cli": bool(same),
         "reference_cli": {"threads": meta["reference_cli_threads"], "phases_s": {p: ref[p] for p in meta["replaced_phases"]},
                           "sum_s": ref_sum, "host": "authoring container, 8 vCPU"},
-        "speedup_vs_reference_phases": ref_sum / fused}))
+        "speedup_vs_reference_phases": ref_sum / fused, "support_counting": n2}))
 
 
 if __name__ == "__main__":

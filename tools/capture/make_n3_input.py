@@ -63,13 +63,42 @@ def main():
         b = (nb[0::2] << 4 | nb[1::2]).astype(np.uint8)
         seqs.append(b)
         spos += b.size
+    # support-counting tables and the reference's counters (hypo_dump2), if that run was made
+    n2 = {}
+    if all(os.path.exists(os.path.join(d, "aux", f"kmer_support_{nm}.txt")) for nm in names):
+        from oracle import support_oracle as so
+        kfirst, spos, kid, kcov, ksup = [0], [], [], [], []
+        bfirst, even, bounds, rfirst, mpos, mval, mcov, msup = [0], [], [], [], [], [], [], []
+        for nm in names:
+            a, b, c, e = so.read_kmer_dump(open(os.path.join(d, "aux", f"kmer_support_{nm}.txt")))
+            spos += a; kid += b; kcov += c; ksup += e
+            kfirst.append(len(spos))
+            ev, bd, minfo, mc, ms = so.read_minimiser_dump(open(os.path.join(d, "aux", f"minimiser_support_{nm}.txt")))
+            even.append(1 if ev else 0)
+            for i in range(len(bd)):
+                rfirst.append(len(mpos))
+                is_win = (i % 2 == 0) if ev else (i % 2 == 1)
+                m = i // 2 if ev else (i - 1) // 2
+                if is_win and 0 <= m < len(minfo):
+                    pp = bd[i]
+                    for j, (rel, v) in enumerate(minfo[m]):
+                        pp += rel
+                        mpos.append(pp); mval.append(v); mcov.append(mc[m][j]); msup.append(ms[m][j])
+            bounds += bd
+            bfirst.append(len(bounds))
+        rfirst.append(len(mpos))
+        n2 = dict(kfirst=np.array(kfirst, np.uint64), spos=np.array(spos, np.uint32), kid=np.array(kid, np.uint64),
+                  kcov=np.array(kcov, np.uint32), ksup=np.array(ksup, np.uint32), bfirst=np.array(bfirst, np.uint64),
+                  even=np.array(even, np.uint8), bounds=np.array(bounds, np.uint32), rfirst=np.array(rfirst, np.uint64),
+                  mpos=np.array(mpos, np.uint32), mval=np.array(mval, np.uint32), mcov=np.array(mcov, np.uint32),
+                  msup=np.array(msup, np.uint32))
     log = open(os.path.join(d, "hypo.log")).read()
     times = {m.group(1).strip(): float(m.group(2)) for m in re.finditer(r"\[Hypo:Hypo\]: ([^)]*?)\. \): TIME= ([0-9.e+-]+)", log)}
     meta = {"k": k, "reference_cli_threads": 8, "reference_phase_s": times,
             "replaced_phases": ["Short arms computing", "Short arms filling", "POA of windows", "Writing results"]}
     np.savez_compressed(out, contigs=contigs, regions=np.concatenate(regs), drafts=np.concatenate(drafts + [np.zeros(16, np.uint8)]),
                         alns=alns, cigar=np.array(cig, np.uint32), seqs=np.concatenate(seqs + [np.zeros(16, np.uint8)]),
-                        polished=np.array(polished), meta=np.array(json.dumps(meta)))
+                        polished=np.array(polished), meta=np.array(json.dumps(meta)), **n2)
     print(out, os.path.getsize(out) / 1e6, "MB;", len(recs), "alignments;", meta["reference_phase_s"])
 
 
