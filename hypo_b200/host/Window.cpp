@@ -190,8 +190,14 @@ void WindowBatch::run(size_t chunk_windows) {
     std::vector<size_t> cut{0};
     if (chunk_windows) {
         while (cut.back() < n) cut.push_back(std::min(n, cut.back() + chunk_windows));
-    } else if (n < 131072 * ndev) {
+    } else if (n < 131072 * ndev && !(threads <= 8 && n >= 49152 * ndev)) {
         cut.push_back(n);
+    } else if (n < 131072 * ndev) {
+        // few host threads (several ranks share the host): packing is a visible part of the call, so even a
+        // medium batch is cut - a small first chunk, then three equal ones - to overlap it with the device
+        const size_t first = std::max<size_t>(8192, n / 8);
+        cut.push_back(first);
+        for (size_t i = 1; i <= 3; ++i) cut.push_back(first + (n - first) * i / 3);
     } else {
         const size_t first = 32768 * ndev;
         cut.push_back(first);

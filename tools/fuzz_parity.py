@@ -20,8 +20,12 @@ while time.time() < t_end:
     n_arms = int(rng.choice([rng.integers(2, 12), rng.integers(12, 45), rng.integers(45, 130)], p=[0.3, 0.55, 0.15]))
     kind = str(rng.choice(["internal", "backbone", "prefix", "suffix", "mixed"]))
     err = float(rng.choice([0.0, 0.01, 0.03, 0.08, 0.15]))
-    if rng.random() < 0.6:
+    u = rng.random()
+    if u < 0.55:
         scores = (5, -4, -8, 3, -5, -4)
+    elif u < 0.62:   # beyond the 16-bit DP range: the 32-bit fill of the last tier
+        scores = (int(rng.integers(40, 128)), -int(rng.integers(40, 129)), -int(rng.integers(40, 129)),
+                  int(rng.integers(40, 128)), -int(rng.integers(40, 129)), -int(rng.integers(40, 129)))
     else:
         scores = (int(rng.integers(1, 9)), -int(rng.integers(1, 9)), -int(rng.integers(0, 10)),
                   int(rng.integers(1, 6)), -int(rng.integers(1, 8)), -int(rng.integers(0, 8)))
@@ -29,6 +33,7 @@ while time.time() < t_end:
     n_win = int(max(8, min(4000, 6e8 / max(cells, 1))))
     b = synth_batch(int(rng.integers(1, 1 << 30)), n_win, length, n_arms, kind, err, wtype=wtype)
     native.init(scores, 0)
+    native.set_option("first_tier", int(rng.choice([0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7])))   # every tier gets its share
     try:
         got = native.consensus(b)
     except native.HypoGpuError as e:

@@ -22,4 +22,25 @@ got = native.consensus(b)
 want, _ = oracle_consensus(b)
 bad = sum(a != c for a, c in zip(got, want))
 print(f"sanitize_run: {b.n_win} windows, {bad} mismatches, tiers {native.last_timing()[2]}")
+# the 32-bit fill of the last tier
+sc = (127, -128, -128, 127, -128, -128)
+native.init(sc, 0)
+small = build_batch(specs[:40])
+got = native.consensus(small)
+want, _ = oracle_consensus(small, sc)
+bad += sum(a != c for a, c in zip(got, want))
+print(f"sanitize_run: 32-bit tier, {small.n_win} windows, tiers {native.last_timing()[2]}")
+# arm extraction, the fused call and support counting on a slice of the captured run
+native.init(DEFAULT_SCORES, 0)
+from tests.arms_util import device_inputs, load_capture
+regions, clen, dumped, recs = load_capture()
+args = device_inputs(regions, clen, recs[:1500])
+batch, win_region = native.extract_arms(*args, 9)
+out = native.polish_alignments(*args, 9)
+print(f"sanitize_run: extract_arms {batch.n_win} windows {batch.n_arms} arms, fused contig {len(out[0])} bp")
+import gzip
+from oracle import support_oracle as so
+spos, kid, _, _ = so.read_kmer_dump(gzip.open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cli_short_60kb.kmer_support.gz"), "rt"))
+c, s_ = native.solid_kmer_support(np.array([0, len(spos)], np.uint64), np.array(spos, np.uint32), np.array(kid, np.uint64), args[3], args[4], args[5], 9)
+print(f"sanitize_run: solid k-mer support, coverage sum {int(c.sum())} support sum {int(s_.sum())}")
 sys.exit(1 if bad else 0)
