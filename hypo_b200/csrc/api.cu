@@ -31,6 +31,8 @@
 #include "poa_kernel.cuh"
 
 namespace hypo_b200 {
+cudaError_t launch_poa_group(const Params& P, int tier, int blocks, int warps_per_block, size_t smem_bytes,
+                             cudaStream_t stream);
 cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream);
 }
@@ -103,6 +105,7 @@ struct Tier {
     int warps_per_block, blocks_per_sm;
     uint32_t est_cap;   // static routing: windows whose estimated node count exceeds this start in a later tier
     int next;           // tier that re-runs the windows overflowing this one (skips tiers that cannot help)
+    int groups = 1;     // windows per warp (group tiers: 4 x 8 lanes, 2 x 16 lanes)
 };
 
 // Tc : SHORT windows whose sequences fit one 128-column tile and whose DAG stays small (the
@@ -133,9 +136,17 @@ const Tier kTiers[] = {
     {true, false, true, false, 640, 1152, 512, 2048, 511, 4, 2, 608, 5},
     {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 6},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 4, 0xffffffffu, 7},
-    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 8},
+    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 10},
+    // Group tiers (poa_group.cu): several small SHORT windows per warp in lock-step.  They run FIRST
+    // (kTierOrder) and overflow into Tc; they sit at the end of the table so that tiers 0..7 keep their numbers.
+    // Tq: <= 31 symbols, 8 lanes per window, 4 windows per warp;  Th: <= 63 symbols, 16 lanes, 2 per warp.
+    {true, true, false, false, 64, 112, 48, 256, 31, 8, 2, 58, 0, 4},
+    {true, true, false, false, 128, 208, 96, 512, 63, 8, 2, 118, 0, 2},
 };
 constexpr int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
+constexpr int kLastTier = 7;                  // the bound-driven tier that never refuses a window
+constexpr int kTierOrder[] = {kTierQuad, kTierHalf, 0, 1, 2, 3, 4, 5, 6, 7};   // launch order (a tier's successor comes later)
+static_assert(sizeof(kTierOrder) / sizeof(kTierOrder[0]) == kNumTiers && kNumTiers == 10, "tier order");
 // Static routing sends only LONG windows to T1: at 5 warps/SM it is slower than T2 at 16 for SHORT windows
 // (30 x 500 bp: 19 vs 36 Mbp/s), while a LONG window's bound-driven capacities in T2 (the round-2 backbone
 // is bounded by the node count) blow up the DP workspace and with it shrink the grid (5.7 vs 2.0 Mbp/s).
@@ -148,7 +159,7 @@ struct DevCtrl {
     TierMax tmax[kNumTiers + 2];      // [t].count = length of tier t's list; the fields before it: maxima of
                                       // the windows ROUTED there; [kNumTiers].count = windows no tier could
                                       // hold; [kNumTiers + 1] = scratch of listmax_kernel
-    uint32_t queue[16];               // work-queue heads of the tier launches
+    uint32_t queue[32];               // [t]: work-queue head of tier t's launch; [16..19]: the probe's counters
     uint32_t fail[kNumFailReasons];   // why windows were abandoned (diagnostics)
     uint32_t bad;                     // malformed descriptors
     uint32_t pad[3];
@@ -158,10 +169,13 @@ struct DevCtrl {
 struct RouteCfg {
     uint32_t lcap[kNumTiers], flags[kNumTiers], est_cap[kNumTiers];
     int first_tier;
+    int group_mode;   // SHORT windows that fit a group tier start there: 0 = never, 1 = Tq then Th, 2 = Th only
 };
 
 struct Options {
-    int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it)
+    int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it; 8 / 9 = the
+                          // group tiers: windows that do not fit them are routed as from tier 0)
+    int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp)
     int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
     int probe = 1;        // shared-memory tiers probe long lists before running them (see stage_tiers)
     int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
@@ -187,7 +201,7 @@ struct Ctx {
     void* pinned_ctrl = nullptr;                 // DevCtrl mirror + a few words
     float poa_ms = 0.f;          // device time of the POA kernels of the last batch call
     uint32_t poa_launches = 0;
-    uint32_t tier_windows[8] = {0};
+    uint32_t tier_windows[16] = {0};
     uint32_t fail_hist[kNumFailReasons] = {0};   // why windows left a tier in the last batch call
     unsigned long long cells = 0;                // DP cells of the last batch call
     uint64_t rerouted = 0;                       // windows a probe sent on without trying them in a tier
@@ -307,10 +321,14 @@ __global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* 
             const bool is_long = d.wtype == 1;
             const uint64_t est = max_len + sum_len * (is_long ? 8u : 15u) / 1000u;
             t = cfg.first_tier;
-            while (t < kNumTiers - 1 &&
+            while (t < kLastTier &&
                    (max_len > cfg.lcap[t] || (is_long ? !(cfg.flags[t] & 1u) : (cfg.flags[t] & 2u) != 0) ||
                     est > cfg.est_cap[t]))
                 ++t;
+            if (!is_long && cfg.group_mode != 0) {
+                if (cfg.group_mode == 1 && max_len <= cfg.lcap[kTierQuad] && est <= cfg.est_cap[kTierQuad]) t = kTierQuad;
+                else if (max_len <= cfg.lcap[kTierHalf] && est <= cfg.est_cap[kTierHalf]) t = kTierHalf;
+            }
             atomicMax(&smax[t][0], s.max_len);
             atomicMax(&smax[t][1], s.bound_len);
             atomicMax(&smax[t][2], s.sum_len);
@@ -445,6 +463,9 @@ int stage_classify(Ctx& g, const WinDesc* d_win, uint64_t n_win, const ArmDesc* 
         cfg.est_cap[t] = kTiers[t].est_cap;
     }
     cfg.first_tier = std::min(std::max(G.opt.first_tier, 0), kNumTiers - 1);
+    cfg.group_mode = cfg.first_tier == kTierQuad ? 1 : cfg.first_tier == kTierHalf ? 2
+                     : (cfg.first_tier == 0 && G.opt.group_tiers) ? 1 : 0;
+    if (cfg.first_tier > kLastTier) cfg.first_tier = 0;
     const int tb = 128;
     classify_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_arms, n_win, a_lo, a_hi, b_lo, b_hi,
                                                                         d_stats, d_bound, cfg, d_lists,
@@ -498,7 +519,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
     TierMax eff[kNumTiers + 1];
     memset(eff, 0, sizeof(eff));
     bool launched[kNumTiers] = {false};
-    for (int t = 0; t < kNumTiers; ++t) {
+    for (int t : kTierOrder) {
         ub[t] += h->tmax[t].count;
         merge_max(eff[t], h->tmax[t]);
         if (ub[t] == 0) continue;
@@ -511,7 +532,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
     const int tb = 256;
 
     bool counts_fresh = true;   // h->tmax[].count is exact for the tiers not yet launched
-    for (int t = 0; t < kNumTiers; ++t) {
+    for (int t : kTierOrder) {
         const Tier& T = kTiers[t];
         if (ub[t] == 0) continue;
         TierMax M = eff[t];
@@ -538,7 +559,8 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
 
         Caps caps;
         caps.ncap = T.ncap; caps.ecap = T.ecap; caps.acap = T.acap; caps.scap = T.scap; caps.lcap = T.lcap;
-        caps.alslots = t < kNumFixedTiers ? fixed_caps(t).alslots : kAlSlotsMax;
+        caps.alslots = is_fixed_tier(t) ? fixed_caps(t).alslots : kAlSlotsMax;
+        caps.tilecols = is_group_tier(t) ? 4 * group_lanes(t) : kTileCols;
         const bool need_paths = T.long_ok && M.any_long != 0;
         if (T.from_bounds) {
             uint32_t lc = std::min<uint32_t>(std::max<uint32_t>(M.bound_len, 1), (uint32_t)T.lcap);
@@ -547,43 +569,45 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
             // Sizing the columns (hence the DP slot, hence how many warps fit the workspace) for that
             // bound starves the grid, so every bound-driven tier but the last sizes them for twice the
             // longest input; a backbone beyond that leaves the tier with kFailLen and runs in the next.
-            if (t + 1 < kNumTiers) lc = std::min<uint32_t>(lc, std::max<uint32_t>(2 * M.max_len + 64, 1023));
+            if (t < kLastTier) lc = std::min<uint32_t>(lc, std::max<uint32_t>(2 * M.max_len + 64, 1023));
             caps.lcap = (int)lc;
             const uint32_t nb = std::max<uint32_t>(M.sum_len + 2, 64);
             caps.ncap = (int)std::min<uint32_t>(nb, (uint32_t)T.ncap);
             caps.ecap = (int)std::min<uint32_t>(nb + 64, (uint32_t)T.ecap);
             caps.acap = (int)std::min<uint32_t>(nb, (uint32_t)T.acap);
             caps.scap = (int)std::min<uint32_t>(2 * nb + 64, (uint32_t)T.scap);
-            if (G.opt.scap > 0 && t + 1 < kNumTiers) caps.scap = G.opt.scap;
+            if (G.opt.scap > 0 && t < kLastTier) caps.scap = G.opt.scap;
         }
         if (M.n_seq > 32000)
             return fail(HYPO_E_CAPACITY, "window with %u sequences exceeds 16-bit edge weights", M.n_seq);
         caps.tiles = T.one_tile ? 1 : (caps.lcap + 1 + kTileCols - 1) / kTileCols;
+        const uint64_t tcols = (uint64_t)caps.tilecols;
         const ArenaLayout L = arena_layout(caps);
 
         int wpb = T.warps_per_block;
         const int bps = T.blocks_per_sm;
         size_t smem = 0;
         if (T.smem_graph) {
-            smem = (size_t)L.total * wpb;
-            while (smem > (size_t)g.smem_optin && wpb > 1) { wpb /= 2; smem = (size_t)L.total * wpb; }
+            smem = (size_t)L.total * wpb * T.groups;
+            while (smem > (size_t)g.smem_optin && wpb > 1) { wpb /= 2; smem = (size_t)L.total * wpb * T.groups; }
             if (smem > (size_t)g.smem_optin) return fail(HYPO_E_CAPACITY, "tier %d does not fit shared memory", t);
         }
         int blocks = g.sms * bps;
-        uint64_t warps = (uint64_t)blocks * wpb;
-        if (warps > work_ub) { blocks = (int)((work_ub + wpb - 1) / wpb); warps = (uint64_t)blocks * wpb; }
+        const uint64_t wpb_slots = (uint64_t)wpb * T.groups;   // windows in flight per block (one slot each)
+        uint64_t warps = (uint64_t)blocks * wpb_slots;        // = slots: one per warp, or per group of a warp
+        if (warps > work_ub) { blocks = (int)((work_ub + wpb_slots - 1) / wpb_slots); warps = (uint64_t)blocks * wpb_slots; }
         // matrix rows (+ spare) and, behind them, the two boundary arrays of the multi-tile fill; the last
         // tier doubles the slot when a window may need 32-bit cells (same test as the kernel's guard, on
         // the upper bounds)
-        const bool wide = t == kNumTiers - 1;
-        uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
+        const bool wide = t == kLastTier;
+        uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * tcols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
         if (wide) {
             const uint64_t cols = (uint64_t)caps.tiles * kTileCols;
             if ((uint64_t)S * ((uint64_t)caps.ncap + 1 + cols) > (uint64_t)kMaxH16 || 2ull * S * cols > (uint64_t)kMaxH16)
                 h_slot = (2 * (uint64_t)(caps.ncap + 4) * caps.tiles * kTileCols + 63) & ~63ull;
         }
         // keep the DP workspace bounded: shrink the grid if the slots would exceed ~24 GB
-        while (warps * h_slot * 2 > (24ull << 30) && blocks > 1) { blocks = (blocks + 1) / 2; warps = (uint64_t)blocks * wpb; }
+        while (warps * h_slot * 2 > (24ull << 30) && blocks > 1) { blocks = (blocks + 1) / 2; warps = (uint64_t)blocks * wpb_slots; }
         CUDA_TRY(g.H.reserve(warps * h_slot * sizeof(int16_t)));
         uint64_t g_slot = 0, p_slot = 0;
         if (!T.smem_graph) {
@@ -630,11 +654,12 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
                 uint32_t* hw = (uint32_t*)(host_words(g) + 8);   // page-locked words the async copies read
                 const uint32_t next_before = h->tmax[nx].count;
                 hw[0] = kProbe; hw[1] = 0;
-                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[8], hw, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[16], hw, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
                 Params Q = P;
-                Q.n_work = &d_ctrl->queue[8]; Q.queue = &d_ctrl->queue[9];
-                const int pb = std::min<int>(blocks, (int)((kProbe + wpb - 1) / wpb));
-                CUDA_TRY(launch_poa(Q, t, T.smem_graph, wide, pb, wpb, smem, stream));
+                Q.n_work = &d_ctrl->queue[16]; Q.queue = &d_ctrl->queue[17];
+                const int pb = std::min<int>(blocks, (int)((kProbe + wpb_slots - 1) / wpb_slots));
+                CUDA_TRY(is_group_tier(t) ? launch_poa_group(Q, t, pb, wpb, smem, stream)
+                                          : launch_poa(Q, t, T.smem_graph, wide, pb, wpb, smem, stream));
                 ++G.launches;
                 CUDA_TRY(fetch_ctrl(g, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -658,11 +683,12 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
                 // pass to the next: after a clean probe (< 5 % left) the next 15 passes of this tier skip theirs
                 if (failed * 20 < kProbe) G.probe_skip[t] = 15;
                 hw[4] = n - kProbe; hw[5] = 0;
-                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[10], hw + 4, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-                P.work += kProbe; P.n_work = &d_ctrl->queue[10]; P.queue = &d_ctrl->queue[11];
+                CUDA_TRY(cudaMemcpyAsync(&d_ctrl->queue[18], hw + 4, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                P.work += kProbe; P.n_work = &d_ctrl->queue[18]; P.queue = &d_ctrl->queue[19];
             }
         }
-        CUDA_TRY(launch_poa(P, t, T.smem_graph, wide, blocks, wpb, smem, stream));
+        CUDA_TRY(is_group_tier(t) ? launch_poa_group(P, t, blocks, wpb, smem, stream)
+                                  : launch_poa(P, t, T.smem_graph, wide, blocks, wpb, smem, stream));
         CUDA_TRY(cudaEventRecord(g.tev1[pass][t], stream));
         ++G.launches;
         launched[t] = true;
@@ -1029,7 +1055,8 @@ int init_devices(const int8_t scores[6], const int* devices, int n) {
     for (int i = 0; i < n; ++i)
         if (devices[i] < 0 || devices[i] >= n_dev)
             return fail(HYPO_E_ARG, "device %d out of range (0..%d)", devices[i], n_dev - 1);
-    for (int t = 0; t < kNumFixedTiers; ++t) {   // the table must agree with the kernels' constants
+    for (int t = 0; t < kNumTiers; ++t) {   // the table must agree with the kernels' constants
+        if (!is_fixed_tier(t)) continue;
         const Caps c = fixed_caps(t);
         const Tier& T = kTiers[t];
         if (c.ncap != T.ncap || c.ecap != T.ecap || c.acap != T.acap || c.scap != T.scap || c.lcap != T.lcap ||
@@ -1141,6 +1168,9 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "first_tier")) {
         if (value < 0 || value >= kNumTiers) return fail(HYPO_E_ARG, "first_tier must be 0..%d", kNumTiers - 1);
         G.opt.first_tier = (int)value;
+    } else if (!strcmp(name, "group_tiers")) {
+        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_tiers must be 0 or 1");
+        G.opt.group_tiers = (int)value;
     } else if (!strcmp(name, "scap")) {
         if (value < 0 || value > 65534) return fail(HYPO_E_ARG, "scap must be 0..65534");
         G.opt.scap = (int)value;
@@ -1494,6 +1524,17 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
     if (poa_kernel_ms) *poa_kernel_ms = ms;
     if (poa_launches) *poa_launches = n;
     if (tier_windows) for (int t = 0; t < 8; ++t) tier_windows[t] = tw[t];
+    return HYPO_OK;
+}
+
+int hypo_gpu_last_tier_windows(uint32_t* tier_windows, int n) {
+    if (!tier_windows || n < 0) return fail(HYPO_E_ARG, "NULL buffer");
+    for (int t = 0; t < n; ++t) {
+        uint32_t c = 0;
+        if (t < kNumTiers)
+            for (int i = 0; i < G.n_dev; ++i) c += G.lane[G.last.load()][i]->tier_windows[t];
+        tier_windows[t] = c;
+    }
     return HYPO_OK;
 }
 

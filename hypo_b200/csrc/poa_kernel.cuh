@@ -83,6 +83,7 @@ struct Caps {
     int alslots;   // slots per aligned-list block: a clique of more than alslots+1 nodes overflows the
                    // tier (6 always suffices; the small tiers trade slots for blocks: cliques beyond
                    // A/C/G/T need N or a marker letter aligned to bases)
+    int tilecols = kTileCols;   // DP columns per tile: 4 per lane of the group that owns the window
 };
 
 struct Params {
@@ -201,7 +202,7 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
     L.cons = k.take(2u * c.ncap);
     if (k.o > end) end = k.o;
     k.o = end;
-    L.colseq = k.take((uint32_t)c.tiles * kTileCols);
+    L.colseq = k.take((uint32_t)c.tiles * (uint32_t)c.tilecols);
     L.cur = k.take(2u * (c.lcap + 1));
 #ifdef HYPO_TMA_STAGE
     L.stage_cap = ((uint32_t)(c.lcap + 3) / 4 + 15u + 15u) & ~15u;   // ceil(lcap / 4) bytes at any alignment
@@ -219,6 +220,14 @@ __host__ __device__ constexpr ArenaLayout arena_layout(const Caps& c) {
 // Growth projection (add_sequence): from this many sequences in the graph on.
 constexpr int kProjectFrom = 6;
 constexpr int kNumFixedTiers = 6;
+// Group tiers (poa_group.cu): several windows per warp, a group of 8 / 16 lanes each, for the small
+// windows the pipeline mostly produces (median draft length 9 bp).  They sit behind the
+// bound-driven tiers in the table so that the tier numbers of round 1 keep their meaning.
+constexpr int kTierQuad = 8;   // Tq: 8 lanes per window, <= 31 symbols
+constexpr int kTierHalf = 9;   // Th: 16 lanes per window, <= 63 symbols
+__host__ __device__ constexpr bool is_group_tier(int tier) { return tier == kTierQuad || tier == kTierHalf; }
+__host__ __device__ constexpr bool is_fixed_tier(int tier) { return (tier >= 0 && tier < kNumFixedTiers) || is_group_tier(tier); }
+__host__ __device__ constexpr int group_lanes(int tier) { return tier == kTierQuad ? 8 : tier == kTierHalf ? 16 : 32; }
 __host__ __device__ constexpr Caps fixed_caps(int tier) {
     // (scap, the DFS stack of the exact sort, aliases the row records and costs no extra memory)
     //                 ncap  ecap  acap  scap  lcap  tiles alslots
@@ -227,6 +236,8 @@ __host__ __device__ constexpr Caps fixed_caps(int tier) {
          : tier == 2 ? Caps{512, 1024, 384, 2048, 127, 1, 6}    // Tw : one tile, many reads per window
          : tier == 3 ? Caps{384, 768, 384, 1536, 255, 2, 6}     // T0b: two tiles
          : tier == 4 ? Caps{640, 1152, 512, 2048, 511, 4, 4}    // T1m: four tiles (500-bp windows), 8 warps / SM
+         : tier == kTierQuad ? Caps{64, 112, 48, 256, 31, 1, 3, 32}    // Tq : four windows per warp
+         : tier == kTierHalf ? Caps{128, 208, 96, 512, 63, 1, 3, 64}   // Th : two windows per warp
                      : Caps{1024, 1920, 1024, 4096, 1023, 8, 4}; // T1 : eight tiles, medium DAG
 }
 

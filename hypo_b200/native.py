@@ -27,6 +27,7 @@ ABI_SYMBOLS = (
     "hypo_gpu_last_fail_hist",
     "hypo_gpu_compact_device",
     "hypo_gpu_last_timing",
+    "hypo_gpu_last_tier_windows",
     "hypo_gpu_extract_arms",
     "hypo_gpu_polish_alignments",
     "hypo_gpu_solid_kmer_support",
@@ -42,6 +43,10 @@ ABI_SYMBOLS = (
     "hypo_gpu_shutdown",
     "hypo_gpu_abi_version",
 )
+
+
+N_TIERS = 10          # capacity tiers of the library (hypo_gpu_last_tier_windows)
+TIER_QUAD, TIER_HALF = 8, 9
 
 
 class HypoGpuError(RuntimeError):
@@ -90,6 +95,8 @@ def lib():
                                               C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
         L.hypo_gpu_last_timing.restype = C.c_int
         L.hypo_gpu_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.hypo_gpu_last_tier_windows.restype = C.c_int
+        L.hypo_gpu_last_tier_windows.argtypes = [C.POINTER(C.c_uint32), C.c_int]
         L.hypo_gpu_last_rerouted.restype = C.c_uint64
         L.hypo_gpu_last_cells.restype = C.c_uint64
         L.hypo_gpu_issue_rate.restype = C.c_int
@@ -271,7 +278,10 @@ def last_timing() -> Tuple[float, int, List[int]]:
     n = C.c_uint32(0)
     tiers = (C.c_uint32 * 8)()
     lib().hypo_gpu_last_timing(C.byref(ms), C.byref(n), tiers)
-    return float(ms.value), int(n.value), [int(x) for x in tiers]
+    # all tiers: 0..7 as in hypo_gpu_last_timing, 8 / 9 = the group tiers (several windows per warp)
+    all_tiers = (C.c_uint32 * N_TIERS)()
+    lib().hypo_gpu_last_tier_windows(all_tiers, N_TIERS)
+    return float(ms.value), int(n.value), [int(x) for x in all_tiers]
 
 
 def last_rerouted() -> int:

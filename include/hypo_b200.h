@@ -116,7 +116,10 @@ int hypo_gpu_device_count(void);
 
 /*
  * Knobs for tests and measurements (the defaults are what production uses):
- *   "first_tier" 0..7  routing starts at this capacity tier (7 = the bound-driven last tier)
+ *   "first_tier" 0..9  routing starts at this capacity tier (7 = the bound-driven last tier; 8 / 9 = the
+ *                      group tiers Tq / Th: windows that do not fit them are routed as from tier 0)
+ *   "group_tiers" 0|1  small SHORT windows (<= 63 symbols) start in the group tiers, several windows per
+ *                      warp (default 1; only changes where windows run)
  *   "scap"       n     DFS-stack entries of the bound-driven tiers except the last (0 = from bounds)
  *   "probe"      0|1   a shared-memory tier whose list holds >= 16384 windows runs the first 4096 alone and,
  *                      if a quarter of them outgrow the tier, hands the rest of the list to the successor tier
@@ -189,6 +192,13 @@ int hypo_gpu_compact_device(const char* d_scratch, const uint64_t* d_out_pos, co
  * POA kernels of the most recent batch call, and how many windows each capacity tier ran.
  */
 int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t tier_windows[8]);
+
+/*
+ * The tier histogram of the most recent batch call for ALL capacity tiers: entries 0..7 as above,
+ * 8 = Tq and 9 = Th, the group tiers that run several small SHORT windows per warp (4 x 8 lanes for
+ * windows of <= 31 symbols, 2 x 16 lanes for <= 63 symbols); entries beyond the last tier are 0.
+ */
+int hypo_gpu_last_tier_windows(uint32_t* tier_windows, int n);
 
 /*
  * Diagnostic hook: how many times windows were abandoned in a capacity tier during the most recent
