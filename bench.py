@@ -68,6 +68,8 @@ def parse():
     ap.add_argument("--stream", nargs="+", default=[],
                     help="inspect files (optionally .gz) captured from the reference CLI; replaces the synthetic set")
     ap.add_argument("--repeat", type=int, default=1, help="--stream: use the captured set this many times over")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="hypo_gpu_set_option knob for A/B measurements (e.g. group_tiers=0); recorded in config")
     return ap.parse_args()
 
 
@@ -280,6 +282,9 @@ def main():
         # (torchrun presets OMP_NUM_THREADS=1; libhypo_host.so reads it when it is first loaded, below)
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     native.init(SCORES, local)
+    for kv in a.option:
+        name, _, val = kv.partition("=")
+        native.set_option(name, int(val))
 
     # ---- the window set (identical on every rank) and this rank's range of it ----------------
     full = make_batch(a, a.seed)
@@ -537,7 +542,7 @@ def main():
                          "inputs (%.0f MB/GPU) fit the L2: every step re-reads them from a cold HBM copy only if evicted; "
                          "the DP workspace written in between (> 200 MB) flushes them" %
                          ((batch.win.nbytes + batch.arms.nbytes + batch.packed.nbytes) / 1e6),
-                   "tier_windows": tiers, "reference_capture": meta},
+                   "tier_windows": tiers, "options": list(a.option), "reference_capture": meta},
         "clocks": clk, "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu, "cpu_baseline_as_shipped": cpu_static,
         "parity_spot_check": ok, "same_bytes_as_one_gpu": same_as_single,

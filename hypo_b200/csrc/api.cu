@@ -11,6 +11,7 @@
 // into G contiguous window ranges of equal estimated cost, one host thread per device runs the same
 // single-device pipeline on its range, and the consensus bytes are gathered in window order - directly
 // per device, or through device 0 over NVLink (NCCL send/recv) when option "gather" is 2.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <dlfcn.h>
@@ -140,8 +141,8 @@ const Tier kTiers[] = {
     // Group tiers (poa_group.cu): several small SHORT windows per warp in lock-step.  They run FIRST
     // (kTierOrder) and overflow into Tc; they sit at the end of the table so that tiers 0..7 keep their numbers.
     // Tq: <= 31 symbols, 8 lanes per window, 4 windows per warp;  Th: <= 63 symbols, 16 lanes, 2 per warp.
-    {true, true, false, false, 64, 112, 48, 256, 31, 8, 2, 58, 0, 4},
-    {true, true, false, false, 128, 208, 96, 512, 63, 8, 2, 118, 0, 2},
+    {true, true, false, false, 56, 96, 40, 224, 31, 8, 3, 51, 0, 4},
+    {true, true, false, false, 120, 192, 80, 448, 63, 8, 3, 110, 0, 2},
 };
 constexpr int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 constexpr int kLastTier = 7;                  // the bound-driven tier that never refuses a window
@@ -176,6 +177,7 @@ struct Options {
     int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it; 8 / 9 = the
                           // group tiers: windows that do not fit them are routed as from tier 0)
     int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp)
+    int group_sort = 1;   // the group tiers' lists are ordered by window size (a warp's windows run in lock-step)
     int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
     int probe = 1;        // shared-memory tiers probe long lists before running them (see stage_tiers)
     int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
@@ -195,7 +197,7 @@ struct Ctx {
     cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
     cudaEvent_t tev0[kPasses][kNumTiers] = {}, tev1[kPasses][kNumTiers] = {};
     DevBuf win, arms, packed, out_scratch, out_pos, out_len, out_off, out_compact;
-    DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp, gather;
+    DevBuf stats, lists, ctrl, H, gws, paths, cub_tmp, gather, sort;
     DevBuf st_reg, st_contig, st_draft, st_doff, st_len, st_pos, st_out, st_cons, st_coff;   // output stitching
     uint64_t resident_windows = 0;               // out_compact / out_off hold the result of this many windows
     void* pinned_ctrl = nullptr;                 // DevCtrl mirror + a few words
@@ -354,6 +356,17 @@ __global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* 
         const uint32_t v = (&smax[0][0])[i];
         if (v) atomicMax(&ctrl->tmax[i / kMaxFields].max_len + (i % kMaxFields), v);
     }
+}
+
+// Sort key of a group tier's list: the windows of a warp run in lock-step, so a warp should hold windows of
+// one size - longest sequences first, then most reads first (ascending key; the big ones early also shortens
+// the launch's tail).
+__global__ void group_key_kernel(const WinStat* __restrict__ st, const uint32_t* __restrict__ list, uint32_t n,
+                                 uint32_t* __restrict__ key) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const WinStat s = st[list[i]];
+    key[i] = ((63u - (s.max_len > 63u ? 63u : s.max_len)) << 8) | (255u - (s.n_seq > 255u ? 255u : s.n_seq));
 }
 
 // Maxima over the windows actually on a bound-driven tier's list (sizes its workspace).
@@ -637,6 +650,28 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
         P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
         CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
+        if (is_group_tier(t) && G.opt.group_sort && counts_fresh) {
+            // group tiers: order the list by window size (behind the part a probe would run first, which has
+            // to stay a fair sample)
+            const uint32_t n_all = h->tmax[t].count;
+            const uint32_t s0 = n_all >= kProbeMin ? kProbe : 0u;
+            const uint32_t n = n_all - s0;
+            if (n > 256) {
+                uint32_t* list = d_lists + (uint64_t)t * n_win + s0;
+                size_t tmp_bytes = 0;
+                CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 14, stream));
+                const size_t tmp_al = (tmp_bytes + 255) & ~(size_t)255;
+                CUDA_TRY(g.sort.reserve(tmp_al + 3ull * sizeof(uint32_t) * n));
+                uint32_t* k_in = (uint32_t*)((char*)g.sort.p + tmp_al);
+                uint32_t* k_out = k_in + n;
+                uint32_t* v_out = k_out + n;
+                group_key_kernel<<<(n + tb - 1) / tb, tb, 0, stream>>>(d_stats, list, n, k_in);
+                CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.sort.p, tmp_bytes, k_in, k_out, list, v_out, (int)n, 0, 14, stream));
+                CUDA_TRY(cudaMemcpyAsync(list, v_out, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
+                G.launches += 3;
+            }
+        }
         // Probe (shared-memory tiers with a long list): static routing knows the windows' sizes, not their
         // reads' error rate, and a tier that most of its windows outgrow does its work twice.  So the first
         // kProbe windows of the list run alone; if a quarter of them leave the tier, the rest of the list is
@@ -987,7 +1022,7 @@ void release_ctx(Ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->win, &c->arms, &c->packed, &c->out_scratch, &c->out_pos, &c->out_len, &c->out_off,
-                      &c->out_compact, &c->stats, &c->lists, &c->ctrl, &c->H, &c->gws, &c->paths, &c->cub_tmp, &c->gather,
+                      &c->out_compact, &c->stats, &c->lists, &c->ctrl, &c->H, &c->gws, &c->paths, &c->cub_tmp, &c->gather, &c->sort,
                       &c->st_reg, &c->st_contig, &c->st_draft, &c->st_doff, &c->st_len, &c->st_pos, &c->st_out, &c->st_cons,
                       &c->st_coff};
     for (DevBuf* b : bufs) b->release();
@@ -1171,6 +1206,9 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "group_tiers")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_tiers must be 0 or 1");
         G.opt.group_tiers = (int)value;
+    } else if (!strcmp(name, "group_sort")) {
+        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_sort must be 0 or 1");
+        G.opt.group_sort = (int)value;
     } else if (!strcmp(name, "scap")) {
         if (value < 0 || value > 65534) return fail(HYPO_E_ARG, "scap must be 0..65534");
         G.opt.scap = (int)value;

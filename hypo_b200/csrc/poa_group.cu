@@ -111,9 +111,10 @@ __device__ __noinline__ EndCell fill_g(bool act, int16_t* __restrict__ H, int le
     const int gl = Grp<G>::lane();
     const int n = act ? g.n_nodes : 0;
     const int nmax = warp_max(n);
-    const uint32_t g2 = bcast16(sc.g), mm2 = bcast16(sc.m - sc.g), nn2 = bcast16(sc.n - sc.g);
-    const uint32_t neg2 = kNegInf2;
-    const uint32_t lane0 = gl == 0 ? 1u : 0u;
+    // (loop constants are made opaque so that ptxas keeps them in registers instead of re-deriving them per row)
+    const uint32_t g2 = opaque(bcast16(sc.g)), mm2 = opaque(bcast16(sc.m - sc.g)), nn2 = opaque(bcast16(sc.n - sc.g));
+    const uint32_t neg2 = opaque(kNegInf2);
+    const uint32_t lane0 = opaque(gl == 0 ? 1u : 0u);
     const uint32_t row0_left = gl == 0 ? kNegInf2 : 0u;
     const uint32_t xinit0 = (type == kROV && gl == 0) ? (kNegInf2 & 0xffff0000u) : kNegInf2;
     uint32_t let4 = 0x07070707u;
@@ -855,7 +856,7 @@ __device__ __noinline__ bool seq_step(bool act, uint32_t* fail_hist, int16_t* H,
 // (:134-149) for the groups whose window is complete.
 // ------------------------------------------------------------------------------------------
 template <int kTier>
-__global__ void __launch_bounds__(256, 2) poa_group_kernel(const Params P) {
+__global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
     constexpr int G = group_lanes(kTier);
     constexpr int NG = 32 / G;
     const int gl = Grp<G>::lane();

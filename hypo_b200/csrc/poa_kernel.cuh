@@ -236,8 +236,8 @@ __host__ __device__ constexpr Caps fixed_caps(int tier) {
          : tier == 2 ? Caps{512, 1024, 384, 2048, 127, 1, 6}    // Tw : one tile, many reads per window
          : tier == 3 ? Caps{384, 768, 384, 1536, 255, 2, 6}     // T0b: two tiles
          : tier == 4 ? Caps{640, 1152, 512, 2048, 511, 4, 4}    // T1m: four tiles (500-bp windows), 8 warps / SM
-         : tier == kTierQuad ? Caps{64, 112, 48, 256, 31, 1, 3, 32}    // Tq : four windows per warp
-         : tier == kTierHalf ? Caps{128, 208, 96, 512, 63, 1, 3, 64}   // Th : two windows per warp
+         : tier == kTierQuad ? Caps{56, 96, 40, 224, 31, 1, 3, 32}    // Tq : four windows per warp
+         : tier == kTierHalf ? Caps{120, 192, 80, 448, 63, 1, 3, 64}   // Th : two windows per warp
                      : Caps{1024, 1920, 1024, 4096, 1023, 8, 4}; // T1 : eight tiles, medium DAG
 }
 
