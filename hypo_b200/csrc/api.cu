@@ -34,7 +34,7 @@
 namespace hypo_b200 {
 cudaError_t launch_poa_group(const Params& P, int tier, int blocks, int warps_per_block, size_t smem_bytes,
                              cudaStream_t stream);
-cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, int blocks,
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, bool team, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream);
 }
 
@@ -178,6 +178,7 @@ struct Options {
                           // group tiers: windows that do not fit them are routed as from tier 0)
     int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp)
     int group_sort = 1;   // the group tiers' lists are ordered by window size (a warp's windows run in lock-step)
+    int teams = 1;        // bound-driven tiers: four warps per window when a launch has few windows
     int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
     int probe = 1;        // shared-memory tiers probe long lists before running them (see stage_tiers)
     int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
@@ -597,8 +598,12 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         const uint64_t tcols = (uint64_t)caps.tilecols;
         const ArenaLayout L = arena_layout(caps);
 
-        int wpb = T.warps_per_block;
-        const int bps = T.blocks_per_sm;
+        // Teams (four warps fill one window's matrix together): T1 always; a bound-driven tier when its launch
+        // has too few windows to fill the device with one warp each - then a window's latency, not the
+        // device's throughput, decides how long the launch takes.
+        const bool team = T.from_bounds && G.opt.teams && work_ub <= (uint64_t)g.sms * 10;
+        int wpb = team ? 5 : T.warps_per_block;
+        const int bps = team ? 1 : T.blocks_per_sm;
         size_t smem = 0;
         if (T.smem_graph) {
             smem = (size_t)L.total * wpb * T.groups;
@@ -613,7 +618,8 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         // tier doubles the slot when a window may need 32-bit cells (same test as the kernel's guard, on
         // the upper bounds)
         const bool wide = t == kLastTier;
-        uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * tcols + 2ull * (caps.ncap + 4) + 63) & ~63ull;
+        // (behind the matrix: one boundary array of ncap + 4 entries per tile)
+        uint64_t h_slot = ((uint64_t)(caps.ncap + 4) * caps.tiles * tcols + (uint64_t)caps.tiles * (caps.ncap + 4) + 63) & ~63ull;
         if (wide) {
             const uint64_t cols = (uint64_t)caps.tiles * kTileCols;
             if ((uint64_t)S * ((uint64_t)caps.ncap + 1 + cols) > (uint64_t)kMaxH16 || 2ull * S * cols > (uint64_t)kMaxH16)
@@ -694,7 +700,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
                 Q.n_work = &d_ctrl->queue[16]; Q.queue = &d_ctrl->queue[17];
                 const int pb = std::min<int>(blocks, (int)((kProbe + wpb_slots - 1) / wpb_slots));
                 CUDA_TRY(is_group_tier(t) ? launch_poa_group(Q, t, pb, wpb, smem, stream)
-                                          : launch_poa(Q, t, T.smem_graph, wide, pb, wpb, smem, stream));
+                                          : launch_poa(Q, t, T.smem_graph, wide, team, pb, wpb, smem, stream));
                 ++G.launches;
                 CUDA_TRY(fetch_ctrl(g, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -723,7 +729,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
             }
         }
         CUDA_TRY(is_group_tier(t) ? launch_poa_group(P, t, blocks, wpb, smem, stream)
-                                  : launch_poa(P, t, T.smem_graph, wide, blocks, wpb, smem, stream));
+                                  : launch_poa(P, t, T.smem_graph, wide, team, blocks, wpb, smem, stream));
         CUDA_TRY(cudaEventRecord(g.tev1[pass][t], stream));
         ++G.launches;
         launched[t] = true;
@@ -1206,6 +1212,9 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "group_tiers")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_tiers must be 0 or 1");
         G.opt.group_tiers = (int)value;
+    } else if (!strcmp(name, "teams")) {
+        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "teams must be 0 or 1");
+        G.opt.teams = (int)value;
     } else if (!strcmp(name, "group_sort")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_sort must be 0 or 1");
         G.opt.group_sort = (int)value;

@@ -125,17 +125,17 @@ __device__ __noinline__ EndCell fill_g(bool act, int16_t* __restrict__ H, int le
     GRow A, B, C;
     A.x[0] = A.x[1] = 0u; A.left = row0_left;
     B = A; C = A;
-#pragma unroll 1
-    for (int rk = 0; rk < nmax; ++rk) {
+    // one DP row: d1 / d2 / d3 hold the rows 1 / 2 / 3 ranks back, the new row replaces d3
+    auto dp_row = [&](int rk, const GRow& d1, const GRow& d2, GRow& d3) {
         const bool ra = rk < n;
         const uint32_t info = ra ? g.rowinfo[rk] : (1u << kRowNearShift);
         uint32_t pf[kNR];
         profile_regs(let4, (info >> 24) & 7u, mm2, nn2, pf);
         uint32_t x[kNR] = {xinit0, neg2};
         const uint32_t near = info >> kRowNearShift;
-        if (near & 1u) relax(x, A.x, A.left, pf, g2);
-        if (near & 2u) relax(x, B.x, B.left, pf, g2);
-        if (near & 4u) relax(x, C.x, C.left, pf, g2);
+        if (near & 1u) relax(x, d1.x, d1.left, pf, g2);
+        if (near & 2u) relax(x, d2.x, d2.left, pf, g2);
+        if (near & 4u) relax(x, d3.x, d3.left, pf, g2);
         const bool far = ra && near == 0u;
         if (warp_any(far)) {
             const int np = (int)((info >> 16) & 0xffu);
@@ -156,13 +156,19 @@ __device__ __noinline__ EndCell fill_g(bool act, int16_t* __restrict__ H, int le
             }
         }
         const uint32_t cb = group_excl_max<G>(scan_inlane(x, neg2), lane0, neg2);
-        C.x[0] = __vmaxs2(x[0], cb);
-        C.x[1] = __vmaxs2(x[1], cb);
-        C.left = cb;
+        d3.x[0] = __vmaxs2(x[0], cb);
+        d3.x[1] = __vmaxs2(x[1], cb);
+        d3.left = cb;
         Hrow += kStride;
-        if (ra) stg64(Hrow, C.x[0], C.x[1]);
-        const GRow r = C;
-        C = B; B = A; A = r;
+        if (ra) stg64(Hrow, d3.x[0], d3.x[1]);
+    };
+    // two rows per trip: the register sets are rotated once per pair (an odd row count ends with an idle row)
+#pragma unroll 1
+    for (int rk = 0; rk < nmax; rk += 2) {
+        dp_row(rk, A, B, C);       // new row -> C
+        dp_row(rk + 1, C, A, B);   // new row -> B
+        const GRow r = A;
+        A = B; B = C; C = r;
     }
     __syncwarp();   // end cell and traceback read the matrix across lanes
 

@@ -29,10 +29,20 @@ __device__ __noinline__ bool give_up(const GState& st, int why) {
     return false;
 }
 
-template <bool kSmem>
+// Warps per window ("team"): 1 everywhere except T1m (tier 4: two), T1 (tier 5: four) and the team variant of
+// the bound-driven tiers (kTier == -2: four).  One warp owns the window and runs every phase; all of them fill
+// the DP matrix together, one 128-column tile at a time each (see team_fill).  These are the tiers whose
+// shared-memory footprint (or window count) leaves most warp slots of an SM empty.
+template <int kTier>
+constexpr int kTeamOf = (kTier == 5 || kTier == -2) ? 4 : kTier == 4 ? 2 : 1;
+// the arena (and workspace slot) index of this warp inside its CTA
+template <int kTier>
+__device__ __forceinline__ unsigned arena_slot() { return (threadIdx.x >> 5) / kTeamOf<kTier>; }
+
+template <bool kSmem, int kTier>
 __device__ __forceinline__ Graph bind_graph(const GState& st, const ArenaLayout& L) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* base = kSmem ? (smem + (threadIdx.x >> 5) * L.total) : st.gbase;
+    uint8_t* base = kSmem ? (smem + arena_slot<kTier>() * L.total) : st.gbase;
     return bind_graph_at(base, L);
 }
 
@@ -42,9 +52,9 @@ template <bool kSmem, int kTier>
 __device__ __forceinline__ Graph make_graph(const GState& st) {
     if constexpr (kTier >= 0) {
         constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
-        return bind_graph<kSmem>(st, L);
+        return bind_graph<kSmem, kTier>(st, L);
     } else {
-        return bind_graph<kSmem>(st, st.L);
+        return bind_graph<kSmem, kTier>(st, st.L);
     }
 }
 
@@ -53,9 +63,9 @@ __device__ __forceinline__ WarpState* warp_state(const GState& st) {
     extern __shared__ __align__(16) uint8_t smem[];
     if constexpr (kTier >= 0) {
         constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
-        return (WarpState*)((kSmem ? (smem + (threadIdx.x >> 5) * L.total) : st.gbase) + L.state);
+        return (WarpState*)((kSmem ? (smem + arena_slot<kTier>() * L.total) : st.gbase) + L.state);
     } else {
-        return (WarpState*)((kSmem ? (smem + (threadIdx.x >> 5) * st.L.total) : st.gbase) + st.L.state);
+        return (WarpState*)((kSmem ? (smem + arena_slot<kTier>() * st.L.total) : st.gbase) + st.L.state);
     }
 }
 
@@ -245,11 +255,64 @@ __device__ __forceinline__ void dp_row(uint32_t info, int rk, const RowRegs& d1,
     if (kMulti && bnd_next && lane_id() == 31) bnd_next[rk + 1] = (int16_t)hi16(d3.x[1]);
 }
 
-// `bnd`: two boundary arrays of (n + 2) int16 each behind the matrix (multi-tile tiers only).
-template <bool kSmem, int kTier, bool kMulti>
-__device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restrict__ H, int16_t* __restrict__ bnd,
-                                        int bnd_len, int len, int tiles, int type, Scores sc) {
-    const Graph g = make_graph<kSmem, kTier>(st);
+// ------------------------------------------------------------------------------------------
+// Teams: four warps fill one window's matrix together (T1, and the bound-driven tiers when a launch has
+// fewer windows than warps to put them on).  Warp k of the team takes the tiles k, k + 4, ...; tile t may
+// compute row r once tile t - 1 has left its boundary value of that row, so the warps run as a software
+// pipeline, synchronised every kTeamBlock rows through progress counters in shared memory.  The owner (warp 0)
+// posts the fill in the team's mailbox and runs every other phase alone; the helpers wait for the next fill.
+// ------------------------------------------------------------------------------------------
+constexpr int kTeamBlock = 16;        // rows between two synchronisations of neighbouring tiles
+constexpr int kTeamMaxTiles = 32;     // a read with more tiles (> 4095 symbols) is filled by the owner alone
+constexpr int kTeamsPerCta = 5;
+struct TeamBox {
+    uint32_t seq;                      // bumped by the owner for every command (helpers poll it)
+    uint32_t cmd;                      // 1 = fill, 2 = exit
+    uint32_t err;                      // a wait ran into its time limit (the window is abandoned)
+    uint32_t done;                     // helpers that have finished a command (3 per command)
+    int len, tiles, type, bnd_len;
+    int m, n, g;
+    int16_t* H;
+    int16_t* bnd;
+    uint32_t prog[kTeamMaxTiles];      // rows completed per tile
+};
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// every lane waits until *p >= v (bounded: a wait that takes seconds sets err instead of hanging the device)
+__device__ __forceinline__ bool team_wait_ge(const uint32_t* p, uint32_t v, uint32_t* err) {
+    if (ld_volatile_shared(p) < v) {
+        const long long t0 = clock64();
+#pragma unroll 1
+        while (ld_volatile_shared(p) < v) {
+            __nanosleep(32);
+            if (clock64() - t0 > (8ll << 30) || ld_volatile_shared(err)) { st_volatile_shared(err, 1u); return false; }
+        }
+    }
+    __threadfence_block();
+    return true;
+}
+// the whole warp publishes *p = v after everything it has written so far
+__device__ __forceinline__ void team_publish(uint32_t* p, uint32_t v) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane_id() == 0) st_volatile_shared(p, v);
+}
+
+__shared__ TeamBox g_team_box[kTeamsPerCta];   // (only the team kernels reference it)
+
+// `bnd`: one boundary array of bnd_len int16 per tile behind the matrix (multi-tile tiers only): entry r of
+// tile t's array is the last column of row r of that tile.  Tiles t0, t0 + tstep, ... are filled; `box` is the
+// team's mailbox (progress counters) when several warps share the fill.
+template <bool kSmem, int kTier, bool kMulti, bool kTeamed>
+__device__ __forceinline__ void dp_fill_tiles(const GState& st, const Graph& g, int16_t* __restrict__ H,
+                                              int16_t* __restrict__ bnd, int bnd_len, int len, int tiles, int type,
+                                              Scores sc, int t0, int tstep, TeamBox* box) {
     const int lane = lane_id();
     const int n = g.n_nodes;
     const int ntiles = kMulti ? tiles : 1;
@@ -264,18 +327,19 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
     c.lane0 = opaque(lane == 0 ? 1u : 0u);
     c.stride = (unsigned)ntiles * kTileCols;
     const typename M::addr_t prows = M::addr(g.prows);
-    if (kMulti && lane == 0) { bnd[0] = 0; bnd[bnd_len] = 0; }   // virtual row 0: H^[0][j] = 0
+    const uint32_t n_pad = (uint32_t)(n + 1) & ~1u;   // rows the two-rows-per-trip loop really computes
 
 #pragma unroll 1
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = t0; t < ntiles; t += tstep) {
         const unsigned toff = (unsigned)t * kTileCols;
         c.let4 = opaque(*reinterpret_cast<const uint32_t*>(g.colseq + toff + lane * 4));
         c.row0_left = opaque((lane == 0 && t == 0) ? kNegInf2 : 0u);
         c.xinit0 = opaque((type == kROV && lane == 0 && t == 0) ? (kNegInf2 & 0xffff0000u) : kNegInf2);
         const int16_t* Hl = opaque_ptr(H + toff + lane * 4);
-        const int16_t* bnd_prev = (kMulti && t > 0) ? bnd + ((t - 1) & 1) * bnd_len : nullptr;
-        int16_t* bnd_next = (kMulti && t + 1 < ntiles) ? bnd + (t & 1) * bnd_len : nullptr;
+        const int16_t* bnd_prev = (kMulti && t > 0) ? bnd + (size_t)(t - 1) * bnd_len : nullptr;
+        int16_t* bnd_next = (kMulti && t + 1 < ntiles) ? bnd + (size_t)t * bnd_len : nullptr;
         typename M::addr_t ri = M::addr(g.rowinfo);
+        if (kMulti && bnd_next && lane == 0) bnd_next[0] = 0;   // virtual row 0: H^[0][j] = 0
 
         // row 0: H^[0][j] = 0
         int16_t* Hrow = opaque_ptr(H + toff + lane * 4);
@@ -284,6 +348,7 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
         A.x[0] = A.x[1] = 0u; A.left = c.row0_left;
         B = A; C = A;
 
+        if (kTeamed && t > 0 && !team_wait_ge(&box->prog[t - 1], min((uint32_t)kTeamBlock + 2u, n_pad), &box->err)) return;
         uint32_t info = M::ld32(ri);
         uint32_t seed = (kMulti && bnd_prev) ? bcast16(bnd_prev[1]) : c.neg2;
 #ifndef HYPO_DP_ROLLED
@@ -292,6 +357,12 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
         // are rotated once per pair
 #pragma unroll 1
         for (int rk = 0; rk < n; rk += 2) {
+            if (kTeamed && rk != 0 && (rk & (kTeamBlock - 1)) == 0) {
+                // rows < rk of this tile are complete; the rows of the next block (and the seed read one row
+                // ahead) need the previous tile's boundary values
+                team_publish(&box->prog[t], (uint32_t)rk);
+                if (t > 0 && !team_wait_ge(&box->prog[t - 1], min((uint32_t)(rk + kTeamBlock + 2), n_pad), &box->err)) return;
+            }
             const uint32_t i0 = info, i1 = M::ld32(ri + 4), s0 = seed;
             uint32_t s1 = c.neg2;
             ri += 8;
@@ -308,6 +379,7 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
 #endif
         }
 #else
+        static_assert(!kTeamed, "the team fill is written for the two-rows-per-trip loop");
 #pragma unroll 1
         for (int rk = 0; rk < n; ++rk) {
             const uint32_t i0 = info, s0 = seed;
@@ -319,10 +391,86 @@ __device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restric
             C = B; B = A; A = r;
         }
 #endif
-        __syncwarp();   // the boundary values of this tile are read by every lane in the next one
+        if (kTeamed) team_publish(&box->prog[t], n_pad);
+        else __syncwarp();   // the boundary values of this tile are read by every lane in the next one
     }
-    return end_cell<int16_t>(g, H, n, (int)c.stride, len, type);
 }
+
+template <bool kSmem, int kTier, bool kMulti>
+__device__ __noinline__ EndCell dp_fill_row(const GState& st, int16_t* __restrict__ H, int16_t* __restrict__ bnd,
+                                        int bnd_len, int len, int tiles, int type, Scores sc) {
+    const Graph g = make_graph<kSmem, kTier>(st);
+    dp_fill_tiles<kSmem, kTier, kMulti, false>(st, g, H, bnd, bnd_len, len, tiles, type, sc, 0, 1, nullptr);
+    return end_cell<int16_t>(g, H, g.n_nodes, (kMulti ? tiles : 1) * kTileCols, len, type);
+}
+// Owner side of a team fill: post the command, fill the own tiles, wait for the helpers.  A row of -1 in the
+// result means a wait ran into its time limit.
+template <bool kSmem, int kTier>
+__device__ __noinline__ EndCell team_fill(const GState& st, int16_t* __restrict__ H, int16_t* __restrict__ bnd,
+                                          int bnd_len, int len, int tiles, int type, Scores sc) {
+    constexpr int kTeam = kTeamOf<kTier>;
+    TeamBox* const box = &g_team_box[arena_slot<kTier>()];
+    const Graph g = make_graph<kSmem, kTier>(st);
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int t = lane; t < tiles; t += 32) box->prog[t] = 0;
+    uint32_t seq = 0;
+    if (lane == 0) {
+        box->cmd = 1; box->len = len; box->tiles = tiles; box->type = type; box->bnd_len = bnd_len;
+        box->m = sc.m; box->n = sc.n; box->g = sc.g; box->H = H; box->bnd = bnd;
+        seq = box->seq + 1;
+    }
+    seq = __shfl_sync(kFull, seq, 0);
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) st_volatile_shared(&box->seq, seq);
+    dp_fill_tiles<kSmem, kTier, true, true>(st, g, H, bnd, bnd_len, len, tiles, type, sc, 0, kTeam, box);
+    // every helper reports back before the mailbox may change again (also after a failed wait)
+    bool ok = team_wait_ge(&box->done, (uint32_t)(kTeam - 1) * seq, &box->err);
+    __syncwarp();
+    ok = ok && ld_volatile_shared(&box->err) == 0u;
+    if (!ok) {
+        EndCell bad;
+        bad.row = -1; bad.col = 0; bad.score = 0; bad.tie = false;
+        return bad;
+    }
+    return end_cell<int16_t>(g, H, g.n_nodes, tiles * kTileCols, len, type);
+}
+
+// Helper warps of a team: wait for the owner's commands.
+template <bool kSmem, int kTier>
+__device__ __noinline__ void team_helper(const GState& st, int role) {
+    constexpr int kTeam = kTeamOf<kTier>;
+    TeamBox* const box = &g_team_box[arena_slot<kTier>()];
+    uint32_t last = 0;
+#pragma unroll 1
+    for (;;) {
+        uint32_t s = ld_volatile_shared(&box->seq);
+        if (s == last) {
+            const long long t0 = clock64();
+#pragma unroll 1
+            while ((s = ld_volatile_shared(&box->seq)) == last) {
+                __nanosleep(256);
+                if (clock64() - t0 > (128ll << 30)) return;   // (a minute: the owner is gone)
+            }
+        }
+        __threadfence_block();
+        s = __shfl_sync(kFull, s, 0);
+        last = s;
+        const uint32_t cmd = ld_volatile_shared(&box->cmd);
+        if (cmd == 2u) return;
+        {
+            const Scores sc = {box->m, box->n, box->g};
+            const Graph g = make_graph<kSmem, kTier>(st);
+            dp_fill_tiles<kSmem, kTier, true, true>(st, g, box->H, box->bnd, box->bnd_len, box->len, box->tiles, box->type,
+                                                    sc, role, kTeam, box);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane_id() == 0) atomicAdd(&box->done, 1u);
+    }
+}
+
 // Emitted here (not at its first use) so that the hottest loop of the compact tier sits at the front
 // of the kernel's code: with 27 warps in different phases the placement of the row loop relative
 // to the other per-read phases decides how well the instruction caches hold (measured: 5 %).
@@ -1023,6 +1171,7 @@ __device__ __forceinline__ uint8_t* stage_buf(const GState& st, StageCtl** ctl, 
     extern __shared__ __align__(16) uint8_t smem[];
     if constexpr (kSmem && kTier >= 0) {
         constexpr ArenaLayout L = arena_layout(fixed_caps(kTier));
+        static_assert(kTeamOf<kTier> == 1, "TMA staging is not built for the team tiers");
         uint8_t* base = smem + (threadIdx.x >> 5) * L.total;
         *ctl = (StageCtl*)(base + L.stage + L.stage_cap);
         *cap = L.stage_cap;
@@ -1164,14 +1313,29 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
             // boundary arrays of the multi-tile fill live behind the matrix slot
             const int bnd_len = caps.ncap + 4;
             int16_t* bnd = H + (size_t)(caps.ncap + 4) * (size_t)(caps.tiles * kTileCols);
-            EndCell ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+            // (teams: reads of one tile, or of more tiles than the mailbox has counters, are left to the owner)
+            const bool team = kTeamOf<kTier> > 1 && tiles > 1 && tiles <= kTeamMaxTiles;
+            EndCell ec;
+            if constexpr (kTeamOf<kTier> > 1) {
+                ec = team ? team_fill<kSmem, kTier>(st, H, bnd, bnd_len, len, tiles, s.type, sc)
+                          : dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+                if (ec.row < 0) return give_up(st, kFailTeam);
+            } else {
+                ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+            }
             if (ec.tie && !ws->exact) {
                 // the reference breaks this tie by rank in ITS order: derive it and redo the fill
                 if (!topo_sort<kSmem, kTier>(st, caps)) return false;
                 if (lane == 0) ws->exact = 1;
                 __syncwarp();
                 build_rows<kSmem, kTier>(st);
-                ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+                if constexpr (kTeamOf<kTier> > 1) {
+                    ec = team ? team_fill<kSmem, kTier>(st, H, bnd, bnd_len, len, tiles, s.type, sc)
+                              : dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+                    if (ec.row < 0) return give_up(st, kFailTeam);
+                } else {
+                    ec = dp_fill_row<kSmem, kTier, !kOneTile>(st, H, bnd, bnd_len, len, tiles, s.type, sc);
+                }
             }
             span = traceback_dp<kSmem, kTier, int16_t>(st, H, cols, ec, s.type, sc, nodes_before + len + 4);
             lines = (unsigned)(nodes_before + 1) * (unsigned)cols / 64u;
@@ -1462,11 +1626,14 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
 // kMinBlocks = 3: the compact tier (27 warps / SM, <= 72 registers); 2: every other tier.
 // kWide: reads whose scores x size leave the 16-bit DP range are filled with 32-bit cells (last tier).
 template <bool kSmem, bool kOneTile, bool kLong, int kMinBlocks, int kTier, bool kWide = false>
-__global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
+__global__ void __launch_bounds__(kTeamOf<kTier> == 4 ? 32 * 4 * kTeamsPerCta : 288, kTeamOf<kTier> == 4 ? 1 : kMinBlocks)
+poa_kernel(const Params P) {
+    constexpr int kTeam = kTeamOf<kTier>;
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
-    const int gwarp = blockIdx.x * warps_per_cta + warp_in_cta;
+    // (one workspace slot per window in flight: per warp, or per team of warps)
+    const int gwarp = blockIdx.x * (warps_per_cta / kTeam) + warp_in_cta / kTeam;
     const Caps caps = tier_caps<kTier>(P.caps);
     GState g;
     uint32_t arena_bytes;
@@ -1491,6 +1658,15 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
     int16_t* H = P.H + (size_t)gwarp * P.h_slot;
     uint16_t* paths = P.paths ? P.paths + (size_t)gwarp * P.p_slot : nullptr;
 
+    if constexpr (kTeam > 1) {
+        TeamBox* const box = &g_team_box[warp_in_cta / kTeam];
+        if (warp_in_cta % kTeam == 0 && lane == 0) { box->seq = 0; box->cmd = 0; box->err = 0; box->done = 0; }
+        __syncthreads();
+        if (warp_in_cta % kTeam != 0) {
+            team_helper<kSmem, kTier>(g, warp_in_cta % kTeam);
+            return;
+        }
+    }
     const uint32_t n_work = __ldg(P.n_work);   // complete: only earlier launches append to this tier's list
 #pragma unroll 1
     for (;;) {
@@ -1549,17 +1725,30 @@ __global__ void __launch_bounds__(288, kMinBlocks) poa_kernel(const Params P) {
         }
         __syncwarp();
     }
+    if constexpr (kTeam > 1) {   // the queue is empty: release the helpers
+        TeamBox* const box = &g_team_box[warp_in_cta / kTeam];
+        uint32_t seq = 0;
+        if (lane == 0) { box->cmd = 2; seq = box->seq + 1; }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) st_volatile_shared(&box->seq, seq);
+    }
 }
 
 }  // namespace
 
+int team_size(int tier, bool team_variant) { return tier == 5 || (tier > 5 && team_variant) ? 4 : tier == 4 ? 2 : 1; }
+
 // ------------------------------------------------------------------------------------------
 // Host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, int blocks,
+// `warps_per_block` counts windows in flight per block: warps, or teams of four warps (T1 always; the
+// bound-driven tiers with `team`).
+cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, bool team, int blocks,
                        int warps_per_block, size_t smem_bytes, cudaStream_t stream) {
     void (*k)(const Params) = nullptr;
-    if (warps_per_block * 32 > 288) return cudaErrorInvalidConfiguration;
+    const int tsize = team_size(tier, team);
+    if (tsize == 4 ? warps_per_block > kTeamsPerCta : warps_per_block * tsize * 32 > 288) return cudaErrorInvalidConfiguration;
     // one-tile tiers only ever run SHORT windows (the LONG driver is compiled out of them)
     switch (tier) {
         case 0: k = poa_kernel<true, true, false, 3, 0>; break;    // Tc
@@ -1570,11 +1759,12 @@ cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, in
         case 5: k = poa_kernel<true, false, true, 2, 5>; break;    // T1
         default:                                                   // bound-driven tiers, DAG in global memory
             if (smem_graph) return cudaErrorInvalidConfiguration;
-            k = wide ? poa_kernel<false, false, true, 2, -1, true> : poa_kernel<false, false, true, 2, -1, false>;
+            if (team) k = wide ? poa_kernel<false, false, true, 1, -2, true> : poa_kernel<false, false, true, 1, -2, false>;
+            else k = wide ? poa_kernel<false, false, true, 2, -1, true> : poa_kernel<false, false, true, 2, -1, false>;
     }
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(P);
+    k<<<blocks, warps_per_block * tsize * 32, smem_bytes, stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,7 @@ enum FailReason {
     kFailNoLong = 9,     // LONG window in a tier compiled without the LONG driver
     kFailProjected = 10, // node / edge growth per read extrapolates beyond the tier: handed on early
     kFailForwarded = 11, // an earlier tier's projection exceeds this tier as well: passed on without work
+    kFailTeam = 12,      // a team fill ran into its time limit (never observed; the window is re-run in the next tier)
     kNumFailReasons = 16
 };
 

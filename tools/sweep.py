@@ -43,14 +43,22 @@ def main():
     ap.add_argument("--long", action="store_true", help="also run LONG windows (lr scores, two rounds) for 30 arms")
     ap.add_argument("--check", type=int, default=512, help="windows compared with the CPU oracle per shape (at most)")
     ap.add_argument("--check-cells", type=float, default=2e10, help="DP cells the oracle may spend per shape")
+    ap.add_argument("--only-long", action="store_true", help="LONG rows only")
+    ap.add_argument("--first-tier", type=int, default=0, help="hypo_gpu_set_option('first_tier'): routing starts there")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="hypo_gpu_set_option knob (A/B runs)")
     a = ap.parse_args()
     native.init(SCORES, 0)
+    for kv in a.option:
+        native.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    native.set_option("first_tier", a.first_tier)
     peak = peak_gbs()
     dpx = native.issue_rate(0)   # measured VIADDMNMX.S16x2 rate, 10^9 warp instructions / s
     dpx_peak_gcups = dpx * 32.0  # bench.py: roofline.compute.peak_definition
     shapes = [(int(r), int(l), float(e), 0) for e in a.errs.split(",") for r in a.arms.split(",")
               for l in a.lengths.split(",")]
-    if a.long:
+    if a.only_long:
+        shapes = []
+    if a.long or a.only_long:
         shapes += [(30, int(l), 0.01, 1) for l in a.lengths.split(",")]
     for arms, length, err, wtype in shapes:
         probe = synth_batch(99, 4, length, arms, "internal", err, wtype=wtype)
@@ -82,7 +90,7 @@ def main():
             "dpx_peak_gcups": dpx_peak_gcups, "frac_of_dpx_peak": dev_cells / 1e9 / (k_ms / 1e3) / dpx_peak_gcups,
             "rerouted_by_probe": native.last_rerouted(),
             "hbm_gbs_algorithmic": alg / 1e9 / (k_ms / 1e3), "hbm_frac_of_measured_peak": alg / 1e9 / (k_ms / 1e3) / peak,
-            "tier_windows": tiers[:8], "abandoned_by_reason": native.last_fail_hist()[1:12],
+            "tier_windows": tiers, "abandoned_by_reason": native.last_fail_hist()[1:12],
             "bit_exact_checked": k, "bit_exact": got == want,
         }
         print(json.dumps(line), flush=True)
