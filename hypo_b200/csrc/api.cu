@@ -362,12 +362,18 @@ __global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* 
 // Sort key of a group tier's list: the windows of a warp run in lock-step, so a warp should hold windows of
 // one size - longest sequences first, then most reads first (ascending key; the big ones early also shortens
 // the launch's tail).
+// The one-warp one-tile tiers order theirs by estimated cost, reads x length^2, largest first (24-bit key).
 __global__ void group_key_kernel(const WinStat* __restrict__ st, const uint32_t* __restrict__ list, uint32_t n,
-                                 uint32_t* __restrict__ key) {
+                                 uint32_t* __restrict__ key, int by_cost) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const WinStat s = st[list[i]];
-    key[i] = ((63u - (s.max_len > 63u ? 63u : s.max_len)) << 8) | (255u - (s.n_seq > 255u ? 255u : s.n_seq));
+    if (by_cost) {
+        const uint64_t c = (uint64_t)s.n_seq * (s.max_len + 1ull) * (s.max_len + 1ull);
+        key[i] = 0xffffffu - (uint32_t)(c > 0xffffffull ? 0xffffffull : c);
+    } else {
+        key[i] = ((63u - (s.max_len > 63u ? 63u : s.max_len)) << 8) | (255u - (s.n_seq > 255u ? 255u : s.n_seq));
+    }
 }
 
 // Maxima over the windows actually on a bound-driven tier's list (sizes its workspace).
@@ -656,24 +662,27 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
         P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
         CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
-        if (is_group_tier(t) && G.opt.group_sort && counts_fresh) {
-            // group tiers: order the list by window size (behind the part a probe would run first, which has
-            // to stay a fair sample)
+        if (G.opt.group_sort) {
+            // group tiers: order the list by window size; the other tiers: by cost, largest first (a shorter tail).
+            // The part a probe would run first stays as it is: it has to be a fair sample.  (The host's count
+            // may be stale - windows the group tiers handed on are appended behind it - which only means that
+            // those few stay unsorted.)
             const uint32_t n_all = h->tmax[t].count;
-            const uint32_t s0 = n_all >= kProbeMin ? kProbe : 0u;
+            const uint32_t s0 = n_all >= kProbeMin / 2 ? kProbe : 0u;
             const uint32_t n = n_all - s0;
             if (n > 256) {
                 uint32_t* list = d_lists + (uint64_t)t * n_win + s0;
                 size_t tmp_bytes = 0;
+                const int by_cost = is_group_tier(t) ? 0 : 1, key_bits = by_cost ? 24 : 14;
                 CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 14, stream));
+                                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, key_bits, stream));
                 const size_t tmp_al = (tmp_bytes + 255) & ~(size_t)255;
                 CUDA_TRY(g.sort.reserve(tmp_al + 3ull * sizeof(uint32_t) * n));
                 uint32_t* k_in = (uint32_t*)((char*)g.sort.p + tmp_al);
                 uint32_t* k_out = k_in + n;
                 uint32_t* v_out = k_out + n;
-                group_key_kernel<<<(n + tb - 1) / tb, tb, 0, stream>>>(d_stats, list, n, k_in);
-                CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.sort.p, tmp_bytes, k_in, k_out, list, v_out, (int)n, 0, 14, stream));
+                group_key_kernel<<<(n + tb - 1) / tb, tb, 0, stream>>>(d_stats, list, n, k_in, by_cost);
+                CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.sort.p, tmp_bytes, k_in, k_out, list, v_out, (int)n, 0, key_bits, stream));
                 CUDA_TRY(cudaMemcpyAsync(list, v_out, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
                 G.launches += 3;
             }
