@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compute-roofline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the two side workloads reported under `extra` (pipeline shape mix, captured window set)")
     ap.add_argument("--mix", default="", choices=["", "pipeline"],
                     help="pipeline: window shapes as the reference CLI produces them (SURVEY.md §6: draft length "
                          "p50 9 / p90 68 / max 100, 10-48 arms, 8 %% of the windows with prefix/suffix arms) "
@@ -192,6 +194,43 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def side_workloads(a):
+    """`extra`: the same metric on the two workloads that look like the reference pipeline's real output - the
+    synthetic pipeline shape mix (1 M windows) and the E. coli-sized window set captured from the reference CLI -
+    so that the driver's own run carries them too.  Host buffers in, host buffers out (hypo_gpu_consensus_batch);
+    `mbp_per_s_kernels` uses the POA kernels' device time (CUDA events inside the library), `mbp_per_s_host_buffers`
+    the wall clock of the call; a strided sample of the result is checked against the CPU oracle."""
+    import argparse as _ap
+    import time as _time
+    from hypo_b200 import native
+    from hypo_b200.batch import split_consensus
+    from tests.oracle_util import oracle_consensus
+    out = {}
+    captured = [os.path.join(ROOT, "data", "captured", f"ecoli5mb_ctg{i}.inspect.gz") for i in (1, 2)]
+    jobs = [("pipeline_mix_1M", dict(mix="pipeline", windows=1_000_000, stream=[]))]
+    if all(os.path.exists(p) for p in captured):
+        jobs.append(("captured_ecoli_sized", dict(mix="", stream=captured, repeat=1)))
+    for name, over in jobs:
+        b = make_batch(_ap.Namespace(**{**vars(a), **over}), a.seed)
+        for _ in range(2):
+            native.consensus_batch_host(b)
+        k_ms, wall = [], []
+        for _ in range(3):
+            t0 = _time.perf_counter()
+            res, off = native.consensus_batch_host(b)
+            wall.append(_time.perf_counter() - t0)
+            k_ms.append(native.last_timing()[0])
+        idx = np.unique(np.linspace(0, b.n_win - 1, 192).astype(np.int64))
+        allc = split_consensus(res, off)
+        want, _ = oracle_consensus(b.select(idx), SCORES)
+        out[name] = {"windows": int(b.n_win), "polished_bp": int(b.polished_bp),
+                     "mbp_per_s_kernels": b.polished_bp / 1e6 / (float(np.mean(k_ms)) / 1e3),
+                     "mbp_per_s_host_buffers": b.polished_bp / 1e6 / float(np.mean(wall)),
+                     "tier_windows": native.last_timing()[2],
+                     "parity_spot_check": bool([allc[i] for i in idx] == want)}
+    return out
 
 
 def measured_peak_gbs():
@@ -523,6 +562,9 @@ def main():
             v0, _, _, desc0 = cpu_reference_time(batch, a.cpu_sample, schedule=0)
             cpu_static = {"value": v0, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": desc0}
 
+    extra = None
+    if rank == 0 and world == 1 and not a.no_extra and not a.stream and not a.mix and not a.option:
+        extra = side_workloads(a)
     meta = None
     if a.stream:
         mp = os.path.join(os.path.dirname(a.stream[0]), os.path.basename(a.stream[0]).split("_ctg")[0] + ".meta.json")
@@ -545,7 +587,7 @@ def main():
                    "tier_windows": tiers, "options": list(a.option), "reference_capture": meta},
         "clocks": clk, "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu, "cpu_baseline_as_shipped": cpu_static,
-        "parity_spot_check": ok, "same_bytes_as_one_gpu": same_as_single,
+        "parity_spot_check": ok, "same_bytes_as_one_gpu": same_as_single, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

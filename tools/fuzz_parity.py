@@ -5,6 +5,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from hypo_b200 import native
+from hypo_b200.batch import concat_batches
 from hypo_b200.hostlib import synth_batch
 from tests.oracle_util import oracle_consensus
 
@@ -32,8 +33,23 @@ while time.time() < t_end:
     cells = n_arms * length * length * (1 + err * n_arms) * (2 if wtype else 1)
     n_win = int(max(8, min(4000, 6e8 / max(cells, 1))))
     b = synth_batch(int(rng.integers(1, 1 << 30)), n_win, length, n_arms, kind, err, wtype=wtype)
+    if rng.random() < 0.6:
+        # ragged: a few more shapes of a similar size class, shuffled together (the windows of a warp of the
+        # group tiers then differ in everything; tier lists get re-ordered by size)
+        parts = [b]
+        for _ in range(int(rng.integers(1, 4))):
+            l2 = int(max(1, min(519, length * float(rng.uniform(0.3, 1.6)))))
+            a2 = int(max(2, min(129, n_arms * float(rng.uniform(0.3, 1.8)))))
+            k2 = str(rng.choice(["internal", "backbone", "prefix", "suffix", "mixed"]))
+            e2 = float(rng.choice([0.0, 0.01, 0.03, 0.08]))
+            c2 = a2 * l2 * l2 * (1 + e2 * a2) * (2 if wtype else 1)
+            parts.append(synth_batch(int(rng.integers(1, 1 << 30)), int(max(4, min(2000, 3e8 / max(c2, 1)))), l2, a2, k2, e2, wtype=wtype))
+        b = concat_batches(parts, {})
+        b = b.select(rng.permutation(b.n_win))
     native.init(scores, 0)
-    native.set_option("first_tier", int(rng.choice([0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7])))   # every tier gets its share
+    native.set_option("first_tier", int(rng.choice([0, 0, 0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9])))   # every tier gets its share
+    native.set_option("group_sort", int(rng.random() < 0.7))
+    native.set_option("teams", int(rng.random() < 0.8))
     try:
         got = native.consensus(b)
     except native.HypoGpuError as e:
