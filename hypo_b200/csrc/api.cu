@@ -164,6 +164,7 @@ struct DevCtrl {
     uint32_t fail[kNumFailReasons];   // why windows were abandoned (diagnostics)
     uint32_t bad;                     // malformed descriptors
     uint32_t pad[3];
+    uint32_t abandoned[16];           // per tier: windows its launches handed on to the successor
     unsigned long long cells;         // DP cells of the completed windows (work counter, GCUPS)
 };
 
@@ -652,6 +653,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.out = d_out; P.out_pos = d_out_pos; P.out_len = d_out_len;
         P.next_list = d_lists + (uint64_t)nx * n_win; P.next_count = &d_ctrl->tmax[nx].count;
         P.fail_hist = d_ctrl->fail;
+        P.abandoned = &d_ctrl->abandoned[t];
         P.cells = &d_ctrl->cells;
         P.need = d_need;
         P.H = (int16_t*)g.H.p; P.h_slot = h_slot;
@@ -754,6 +756,11 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         g.poa_launches += 1;
         g.tier_windows[t] += h->tmax[t].count;
     }
+    // Feedback for the probes: a tier that ran a long list and lost a quarter of it (its probe was skipped, or
+    // the sample was kind) is probed again next time.
+    for (int t = 0; t < kNumTiers; ++t)
+        if (launched[t] && !kTiers[t].from_bounds && h->tmax[t].count >= kProbeMin && h->abandoned[t] * 4ull >= h->tmax[t].count)
+            G.probe_skip[t] = 0;
     for (int k = 0; k < kNumFailReasons; ++k) g.fail_hist[k] += h->fail[k];
     g.cells += h->cells;
     const uint32_t lost = h->tmax[kNumTiers].count;

@@ -894,6 +894,7 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
         if (gl == 0) {
             if (res == -2) {
                 const uint32_t at = atomicAdd(P.next_count, 1u);
+                if (P.abandoned) atomicAdd(P.abandoned, 1u);
                 P.next_list[at] = widx;
             } else {
                 P.out_len[widx] = (uint32_t)res;

@@ -449,8 +449,11 @@ __device__ __noinline__ void team_helper(const GState& st, int role) {
         if (s == last) {
             const long long t0 = clock64();
 #pragma unroll 1
+            unsigned nap = 64;   // (back off: an idle helper must not take issue slots from the owners)
+#pragma unroll 1
             while ((s = ld_volatile_shared(&box->seq)) == last) {
-                __nanosleep(256);
+                __nanosleep(nap);
+                if (nap < 2048) nap *= 2;
                 if (clock64() - t0 > (128ll << 30)) return;   // (a minute: the owner is gone)
             }
         }
@@ -1711,6 +1714,7 @@ poa_kernel(const Params P) {
         if (lane == 0) {
             if (res == -2) {
                 const uint32_t k = atomicAdd(P.next_count, 1u);
+                if (P.abandoned) atomicAdd(P.abandoned, 1u);
                 P.next_list[k] = widx;
                 if constexpr (kProjects<kOneTile, kTier>) {
                     // (run_short / run_long zero it when they start a window; non-zero = abandoned on projection)

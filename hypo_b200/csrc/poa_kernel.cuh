@@ -99,6 +99,7 @@ struct Params {
     uint32_t* out_len;           // consensus length of window w
     uint32_t* next_list;         // windows that exceed this tier are appended to the successor tier's list ...
     uint32_t* next_count;        // ... whose (atomic) length this is; the tier lists never need the host in between
+    uint32_t* abandoned;         // how many windows this tier handed on (feedback for the tier probes; may be null)
     uint32_t* fail_hist;         // [kNumFailReasons] why windows left a tier (diagnostics; may be null)
     unsigned long long* cells;   // sum of the DP cells (rows x columns of every fill) of the windows this
                                  // launch completed: the work counter behind the GCUPS figures (may be null)
