@@ -120,6 +120,11 @@ int hypo_gpu_device_count(void);
  *                      group tiers Tq / Th: windows that do not fit them are routed as from tier 0)
  *   "group_tiers" 0|1  small SHORT windows (<= 63 symbols) start in the group tiers, several windows per
  *                      warp (default 1; only changes where windows run)
+ *   "group_sort" 0|1   tier lists are ordered on the device before they run: by size class for the group tiers
+ *                      (the windows of a warp advance in lock-step), by estimated cost, largest first, for
+ *                      the others (default 1)
+ *   "teams"      0|1   the bound-driven tiers give every window a team of four warps when a launch has few
+ *                      windows (default 1; T1m / T1 always run teams of two / four warps)
  *   "scap"       n     DFS-stack entries of the bound-driven tiers except the last (0 = from bounds)
  *   "probe"      0|1   a shared-memory tier whose list holds >= 16384 windows runs the first 4096 alone and,
  *                      if a quarter of them outgrow the tier, hands the rest of the list to the successor tier
