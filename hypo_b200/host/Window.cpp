@@ -186,23 +186,42 @@ void WindowBatch::run(size_t chunk_windows) {
     // least three: with two calls in flight the per-call costs (copy of a head, compaction, result copy,
     // kernel tails) hide behind the other call's kernels, so chunks may be small enough to keep the two
     // lanes' buffers modest (measured: tools/chunk_sweep.py, profiles/).
-    const size_t ndev = (size_t)std::max(1, hypo_gpu_device_count());
+    // The counts below are for windows of the headline shape (30 reads x 120 bp); a chunk is meant to be a
+    // certain amount of device WORK - per-chunk costs (tier launches and their tails, classification, copies)
+    // are fixed - so for cheaper windows they scale up: `scale` = cost of a headline window / average cost
+    // here, from a strided sample of reads x (length^2 + a per-read constant).
+    double scale = 1.0;
+    {
+        double sum = 0;
+        size_t cnt = 0;
+        for (size_t i = 0; i < n; i += 61, ++cnt) {
+            const Window* w = _windows[i];
+            double arms = 0;
+            for (int k = 0; k < 3; ++k) arms += (double)w->arms(k).size();
+            const double len = (double)w->draft().get_seq_size() + 2.0;
+            sum += arms * (len * len + 300.0) + 300.0;
+        }
+        const double avg = sum / (double)std::max<size_t>(cnt, 1), headline = 30.0 * (122.0 * 122.0 + 300.0);
+        scale = std::min(8.0, std::max(1.0, headline / std::max(avg, 1.0)));
+    }
+    const size_t ndev = (size_t)std::max(1, hypo_gpu_device_count()) * (size_t)1;
+    const size_t unit = (size_t)((double)ndev * scale + 0.5);   // "devices x scale": what the counts are multiplied by
     std::vector<size_t> cut{0};
     if (chunk_windows) {
         while (cut.back() < n) cut.push_back(std::min(n, cut.back() + chunk_windows));
-    } else if (n < 131072 * ndev && !(threads <= 8 && n >= 49152 * ndev)) {
+    } else if (n < 131072 * unit && !(threads <= 8 && n >= 49152 * unit)) {
         cut.push_back(n);
-    } else if (n < 131072 * ndev) {
+    } else if (n < 131072 * unit) {
         // few host threads (several ranks share the host): packing is a visible part of the call, so even a
         // medium batch is cut - a small first chunk, then three equal ones - to overlap it with the device
         const size_t first = std::max<size_t>(8192, n / 8);
         cut.push_back(first);
         for (size_t i = 1; i <= 3; ++i) cut.push_back(first + (n - first) * i / 3);
     } else {
-        const size_t first = 32768 * ndev;
+        const size_t first = 32768 * std::min(unit, 4 * ndev);
         cut.push_back(first);
         const size_t rest = n - first;
-        const size_t k = rest < 196608 * ndev ? 1 : std::max<size_t>(3, (rest + 262144 * ndev - 1) / (262144 * ndev));
+        const size_t k = rest < 196608 * unit ? 1 : std::max<size_t>(3, (rest + 262144 * unit - 1) / (262144 * unit));
         for (size_t i = 1; i <= k; ++i) cut.push_back(first + rest * i / k);
     }
     const size_t n_chunks = cut.size() - 1;

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--check", type=int, default=512, help="windows compared with the CPU oracle per shape (at most)")
     ap.add_argument("--check-cells", type=float, default=2e10, help="DP cells the oracle may spend per shape")
     ap.add_argument("--only-long", action="store_true", help="LONG rows only")
+    ap.add_argument("--long-err", type=float, default=0.01, help="read error of the LONG rows (sub / ins / del each)")
     ap.add_argument("--first-tier", type=int, default=0, help="hypo_gpu_set_option('first_tier'): routing starts there")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="hypo_gpu_set_option knob (A/B runs)")
     a = ap.parse_args()
@@ -59,7 +60,7 @@ def main():
     if a.only_long:
         shapes = []
     if a.long or a.only_long:
-        shapes += [(30, int(l), 0.01, 1) for l in a.lengths.split(",")]
+        shapes += [(30, int(l), a.long_err, 1) for l in a.lengths.split(",")]
     for arms, length, err, wtype in shapes:
         probe = synth_batch(99, 4, length, arms, "internal", err, wtype=wtype)
         st = np.array([oracle_stats(probe, w, SCORES) for w in range(2 if arms * length > 30000 else 4)], dtype=np.float64)
