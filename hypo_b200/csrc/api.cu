@@ -135,19 +135,27 @@ const Tier kTiers[] = {
     {true, true, false, false, 512, 1024, 384, 2048, 127, 5, 2, 486, 6},
     {true, false, true, false, 384, 768, 384, 1536, 255, 6, 2, 364, 4},
     {true, false, true, false, 640, 1152, 512, 2048, 511, 4, 2, 608, 5},
-    {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, 6},
+    {true, false, true, false, 1024, 1920, 1024, 4096, 1023, 5, 1, 972, kTierBig},
     {false, false, true, true, 8192, 16384, 2048, 8192, 4095, 4, 4, 0xffffffffu, 7},
-    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 10},
+    {false, false, true, true, 65534, 65534, 65534, 65534, 0x7ffffff0, 2, 4, 0xffffffffu, 11},   // (11 = the list of windows nothing could hold)
     // Group tiers (poa_group.cu): several small SHORT windows per warp in lock-step.  They run FIRST
     // (kTierOrder) and overflow into Tc; they sit at the end of the table so that tiers 0..7 keep their numbers.
     // Tq: <= 31 symbols, 8 lanes per window, 4 windows per warp;  Th: <= 63 symbols, 16 lanes, 2 per warp.
     {true, true, false, false, 56, 96, 40, 224, 31, 8, 3, 51, 0, 4},
     {true, true, false, false, 120, 192, 80, 448, 63, 8, 3, 110, 0, 2},
+    // T2s: large windows (<= 1023 columns) whose ESTIMATED DAG fits shared memory: capacities in four buckets
+    // (1280 / 1760 / 2680 / 4096 nodes = 4 / 3 / 2 / 1 windows per SM), a team of four warps per window.  The
+    // bound-driven tiers keep such a DAG in global memory, where every phase but the fill pays its latency.
+    {true, false, true, true, 4096, 7680, 4096, 16384, 1023, 5, 1, 0xffffffffu, 6},
 };
 constexpr int kNumTiers = sizeof(kTiers) / sizeof(kTiers[0]);
 constexpr int kLastTier = 7;                  // the bound-driven tier that never refuses a window
-constexpr int kTierOrder[] = {kTierQuad, kTierHalf, 0, 1, 2, 3, 4, 5, 6, 7};   // launch order (a tier's successor comes later)
-static_assert(sizeof(kTierOrder) / sizeof(kTierOrder[0]) == kNumTiers && kNumTiers == 10, "tier order");
+constexpr int kTierOrder[] = {kTierQuad, kTierHalf, 0, 1, 2, 3, 4, 5, kTierBig, 6, 7};   // launch order (a tier's successor comes later)
+static_assert(sizeof(kTierOrder) / sizeof(kTierOrder[0]) == kNumTiers && kNumTiers == 11, "tier order");
+// T2s: estimated nodes of a window / of a list (longest sequence + a share of all bases that covers ~5 % read error)
+__host__ __device__ inline uint64_t big_estimate(uint64_t max_len, uint64_t sum_len, bool is_long) {
+    return max_len + sum_len * (is_long ? 35u : 25u) / 1000u + 64u;
+}
 // Static routing sends only LONG windows to T1: at 5 warps/SM it is slower than T2 at 16 for SHORT windows
 // (30 x 500 bp: 19 vs 36 Mbp/s), while a LONG window's bound-driven capacities in T2 (the round-2 backbone
 // is bounded by the node count) blow up the DP workspace and with it shrink the grid (5.7 vs 2.0 Mbp/s).
@@ -172,6 +180,7 @@ struct RouteCfg {
     uint32_t lcap[kNumTiers], flags[kNumTiers], est_cap[kNumTiers];
     int first_tier;
     int group_mode;   // SHORT windows that fit a group tier start there: 0 = never, 1 = Tq then Th, 2 = Th only
+    int big_mode;     // windows routed to T2 start in T2s if their estimate fits: 0 = never, 1 = yes, 2 = every window that may
 };
 
 struct Options {
@@ -180,6 +189,7 @@ struct Options {
     int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp)
     int group_sort = 1;   // the group tiers' lists are ordered by window size (a warp's windows run in lock-step)
     int teams = 1;        // bound-driven tiers: four warps per window when a launch has few windows
+    int big_tier = 1;     // large windows whose estimated DAG fits shared memory start in T2s, not T2
     int scap = 0;         // > 0: DFS-stack entries of the bound-driven tiers except the last (tests force kFailStack)
     int probe = 1;        // shared-memory tiers probe long lists before running them (see stage_tiers)
     int gather = 0;       // multi-device result gather: 0 = every device copies its bytes to the host itself,
@@ -329,6 +339,11 @@ __global__ void classify_kernel(const WinDesc* __restrict__ win, const ArmDesc* 
                    (max_len > cfg.lcap[t] || (is_long ? !(cfg.flags[t] & 1u) : (cfg.flags[t] & 2u) != 0) ||
                     est > cfg.est_cap[t]))
                 ++t;
+            // (default routing sends only LONG windows there: their two rounds need spoa's exact order, whose serial
+            // walk is what a DAG in global memory makes slow; large SHORT windows are faster at T2's 16 warps / SM)
+            if (cfg.big_mode != 0 && (cfg.big_mode == 2 || (t == 6 && is_long)) && max_len <= cfg.lcap[kTierBig] &&
+                (cfg.big_mode == 2 || big_estimate(max_len, sum_len, is_long) <= cfg.est_cap[kTierBig]))
+                t = kTierBig;
             if (!is_long && cfg.group_mode != 0) {
                 if (cfg.group_mode == 1 && max_len <= cfg.lcap[kTierQuad] && est <= cfg.est_cap[kTierQuad]) t = kTierQuad;
                 else if (max_len <= cfg.lcap[kTierHalf] && est <= cfg.est_cap[kTierHalf]) t = kTierHalf;
@@ -486,6 +501,8 @@ int stage_classify(Ctx& g, const WinDesc* d_win, uint64_t n_win, const ArmDesc* 
     cfg.first_tier = std::min(std::max(G.opt.first_tier, 0), kNumTiers - 1);
     cfg.group_mode = cfg.first_tier == kTierQuad ? 1 : cfg.first_tier == kTierHalf ? 2
                      : (cfg.first_tier == 0 && G.opt.group_tiers) ? 1 : 0;
+    cfg.big_mode = cfg.first_tier == kTierBig ? 2 : (cfg.first_tier < 6 && G.opt.big_tier) ? 1 : 0;
+    cfg.est_cap[kTierBig] = (uint32_t)kTiers[kTierBig].ncap;
     if (cfg.first_tier > kLastTier) cfg.first_tier = 0;
     const int tb = 128;
     classify_kernel<<<(unsigned)((n_win + tb - 1) / tb), tb, 0, stream>>>(d_win, d_arms, n_win, a_lo, a_hi, b_lo, b_hi,
@@ -598,6 +615,14 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
             caps.acap = (int)std::min<uint32_t>(nb, (uint32_t)T.acap);
             caps.scap = (int)std::min<uint32_t>(2 * nb + 64, (uint32_t)T.scap);
             if (G.opt.scap > 0 && t < kLastTier) caps.scap = G.opt.scap;
+            if (t == kTierBig) {
+                // capacities from the estimate, in buckets that fill an SM's shared memory with 4 / 3 / 2 / 1 arenas
+                const uint64_t need = big_estimate(M.max_len, M.sum_len, M.any_long != 0);
+                const int bucket = need <= 1280 ? 1280 : need <= 1760 ? 1760 : need <= 2680 ? 2680 : 4096;
+                caps.lcap = (int)std::min<uint32_t>(lc, (uint32_t)T.lcap);
+                caps.ncap = bucket; caps.ecap = bucket * 15 / 8; caps.acap = bucket; caps.scap = 4 * bucket;
+                caps.alslots = 4;
+            }
         }
         if (M.n_seq > 32000)
             return fail(HYPO_E_CAPACITY, "window with %u sequences exceeds 16-bit edge weights", M.n_seq);
@@ -608,8 +633,8 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         // Teams (four warps fill one window's matrix together): T1 always; a bound-driven tier when its launch
         // has too few windows to fill the device with one warp each - then a window's latency, not the
         // device's throughput, decides how long the launch takes.
-        const bool team = T.from_bounds && G.opt.teams && work_ub <= (uint64_t)g.sms * 10;
-        int wpb = team ? 5 : T.warps_per_block;
+        const bool team = t == kTierBig || (T.from_bounds && G.opt.teams && work_ub <= (uint64_t)g.sms * 10);
+        int wpb = t == kTierBig ? std::max(1, std::min(5, (int)(((size_t)g.smem_optin - 1024) / L.total))) : team ? 5 : T.warps_per_block;
         const int bps = team ? 1 : T.blocks_per_sm;
         size_t smem = 0;
         if (T.smem_graph) {
@@ -661,6 +686,7 @@ int stage_tiers(Ctx& g, int pass, const WinDesc* d_win, uint64_t n_win, const Ar
         P.paths = need_paths ? (uint16_t*)g.paths.p : nullptr; P.p_slot = p_slot;
         P.caps = caps;
         P.packed_end = packed_end;
+        P.long_only = (t == kTierBig && G.opt.first_tier != kTierBig) ? 1u : 0u;
         P.sr_m = G.scores[0]; P.sr_n = G.scores[1]; P.sr_g = G.scores[2];
         P.lr_m = G.scores[3]; P.lr_n = G.scores[4]; P.lr_g = G.scores[5];
         CUDA_TRY(cudaEventRecord(g.tev0[pass][t], stream));
@@ -1228,6 +1254,9 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "group_tiers")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_tiers must be 0 or 1");
         G.opt.group_tiers = (int)value;
+    } else if (!strcmp(name, "big_tier")) {
+        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "big_tier must be 0 or 1");
+        G.opt.big_tier = (int)value;
     } else if (!strcmp(name, "teams")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "teams must be 0 or 1");
         G.opt.teams = (int)value;

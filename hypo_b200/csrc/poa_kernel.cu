@@ -1695,6 +1695,9 @@ poa_kernel(const Params P) {
         } else if (kProjects<kOneTile, kTier> && pass_on) {
             give_up(g, kFailForwarded);
             res = -2;
+        } else if (kTier == -2 && P.long_only && w.wtype == 0 && n >= 2) {
+            give_up(g, kFailForwarded);   // (T2s only takes LONG windows unless it is forced)
+            res = -2;
         } else if (n >= 2) {
             if (w.wtype == 0) res = run_short<kSmem, kOneTile, kTier, kWide>(g, P, caps, H, w, out);
             else if (kLong && paths) res = run_long<kSmem, kOneTile, kTier, kWide>(g, P, caps, H, w, out, paths, P.p_slot);
@@ -1762,7 +1765,10 @@ cudaError_t launch_poa(const Params& P, int tier, bool smem_graph, bool wide, bo
         case 4: k = poa_kernel<true, false, true, 2, 4>; break;    // T1m
         case 5: k = poa_kernel<true, false, true, 2, 5>; break;    // T1
         default:                                                   // bound-driven tiers, DAG in global memory
-            if (smem_graph) return cudaErrorInvalidConfiguration;
+            if (smem_graph) {   // T2s: shared-memory DAG with run-time capacities, always a team
+                if (!team || wide) return cudaErrorInvalidConfiguration;
+                k = poa_kernel<true, false, true, 1, -2, false>;
+            } else
             if (team) k = wide ? poa_kernel<false, false, true, 1, -2, true> : poa_kernel<false, false, true, 1, -2, false>;
             else k = wide ? poa_kernel<false, false, true, 2, -1, true> : poa_kernel<false, false, true, 2, -1, false>;
     }

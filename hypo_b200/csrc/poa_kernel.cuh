@@ -114,6 +114,7 @@ struct Params {
     Caps caps;
     int sr_m, sr_n, sr_g, lr_m, lr_n, lr_g;
     uint64_t packed_end;         // bytes of `packed` that may be read (bulk copies never reach beyond it)
+    uint32_t long_only;          // non-zero: SHORT windows are passed on to the successor tier untried (T2s)
 };
 
 __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -227,6 +228,9 @@ constexpr int kNumFixedTiers = 6;
 // bound-driven tiers in the table so that the tier numbers of round 1 keep their meaning.
 constexpr int kTierQuad = 8;   // Tq: 8 lanes per window, <= 31 symbols
 constexpr int kTierHalf = 9;   // Th: 16 lanes per window, <= 63 symbols
+// T2s: the DAG of a large window in SHARED memory, capacities from an ESTIMATE of its size (not the worst-case
+// bound, which no shared memory holds), teams of four warps; runs between T1 and the bound-driven tiers.
+constexpr int kTierBig = 10;
 __host__ __device__ constexpr bool is_group_tier(int tier) { return tier == kTierQuad || tier == kTierHalf; }
 __host__ __device__ constexpr bool is_fixed_tier(int tier) { return (tier >= 0 && tier < kNumFixedTiers) || is_group_tier(tier); }
 __host__ __device__ constexpr int group_lanes(int tier) { return tier == kTierQuad ? 8 : tier == kTierHalf ? 16 : 32; }

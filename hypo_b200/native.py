@@ -45,8 +45,8 @@ ABI_SYMBOLS = (
 )
 
 
-N_TIERS = 10          # capacity tiers of the library (hypo_gpu_last_tier_windows)
-TIER_QUAD, TIER_HALF = 8, 9
+N_TIERS = 11          # capacity tiers of the library (hypo_gpu_last_tier_windows)
+TIER_QUAD, TIER_HALF, TIER_BIG = 8, 9, 10
 
 
 class HypoGpuError(RuntimeError):

@@ -116,8 +116,11 @@ int hypo_gpu_device_count(void);
 
 /*
  * Knobs for tests and measurements (the defaults are what production uses):
- *   "first_tier" 0..9  routing starts at this capacity tier (7 = the bound-driven last tier; 8 / 9 = the
- *                      group tiers Tq / Th: windows that do not fit them are routed as from tier 0)
+ *   "first_tier" 0..10 routing starts at this capacity tier (7 = the bound-driven last tier; 8 / 9 = the
+ *                      group tiers Tq / Th, 10 = T2s, the estimate-driven shared-memory tier for large windows:
+ *                      windows that do not fit them are routed as from tier 0)
+ *   "big_tier"   0|1   large windows whose estimated DAG fits shared memory start in T2s instead of the
+ *                      bound-driven tier T2 (default 1)
  *   "group_tiers" 0|1  small SHORT windows (<= 63 symbols) start in the group tiers, several windows per
  *                      warp (default 1; only changes where windows run)
  *   "group_sort" 0|1   tier lists are ordered on the device before they run: by size class for the group tiers
@@ -201,7 +204,8 @@ int hypo_gpu_last_timing(float* poa_kernel_ms, uint32_t* poa_launches, uint32_t 
 /*
  * The tier histogram of the most recent batch call for ALL capacity tiers: entries 0..7 as above,
  * 8 = Tq and 9 = Th, the group tiers that run several small SHORT windows per warp (4 x 8 lanes for
- * windows of <= 31 symbols, 2 x 16 lanes for <= 63 symbols); entries beyond the last tier are 0.
+ * windows of <= 31 symbols, 2 x 16 lanes for <= 63 symbols), 10 = T2s (large windows, DAG in shared memory,
+ * capacities from an estimate); entries beyond the last tier are 0.
  */
 int hypo_gpu_last_tier_windows(uint32_t* tier_windows, int n);
 

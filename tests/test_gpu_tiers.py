@@ -270,3 +270,31 @@ def test_probe_reroutes_a_list_its_tier_cannot_hold():
     idx = np.arange(0, b.n_win, 97)
     want, _ = oracle_consensus(b.select(idx))
     assert [probed[i] for i in idx] == want
+
+
+def test_estimate_driven_shared_memory_tier_forced():
+    """T2s (tier 10): the DAG of a large window in shared memory, capacities from an estimate of its size, a team
+    of four warps per window.  Forced: every kind of window starts there; same bytes as the oracle."""
+    native.set_option("first_tier", native.TIER_BIG)
+    for label, b in _mixed_batches():
+        want, _ = oracle_consensus(b)
+        _same(native.consensus(b), want, b, f"T2s/{label}")
+        _, _, tiers = native.last_timing()
+        assert tiers[native.TIER_BIG] > 0 and sum(tiers[:6]) == 0, (label, tiers)
+
+
+def test_noisy_long_windows_run_in_the_estimate_driven_tier():
+    """LONG windows of noisy reads outgrow T1 (1024 nodes) and are re-run in T2s; the noisiest outgrow its
+    estimate as well and end in the bound-driven tiers.  Bytes never change."""
+    for err, n in ((0.03, 40), (0.08, 24)):
+        b = synth_batch(121, n, 420, 24, "internal", err, wtype=WINDOW_LONG)
+        want, _ = oracle_consensus(b)
+        _same(native.consensus(b), want, b, f"LONG err {err}")
+        _, _, tiers = native.last_timing()
+        assert tiers[native.TIER_BIG] > 0, (err, tiers)
+    # large SHORT windows keep going to the bound-driven tier (faster for them at 16 warps / SM)
+    b = synth_batch(122, 24, 480, 60, "mixed", 0.02)
+    want, _ = oracle_consensus(b)
+    _same(native.consensus(b), want, b, "SHORT 60 x 480")
+    _, _, tiers = native.last_timing()
+    assert tiers[native.TIER_BIG] == 0 and tiers[6] == b.n_win, tiers
