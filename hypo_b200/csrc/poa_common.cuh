@@ -60,7 +60,10 @@ struct WarpState {
     uint32_t base;       // nodes | edges << 16 after the second sequence (growth is measured from here)
     uint32_t need;       // projected final nodes | edges << 16 when the window was abandoned on projection
     unsigned long long cells;   // DP cells filled for this window so far: sum of (rows + 1) x (columns + 1)
+    int clean;           // the sequence added last only re-walked existing nodes and edges (and `cur` still holds its
+                         // node path): an identical sequence right after it aligns identically - see repeat_sequence
 };
+static_assert(sizeof(WarpState) <= 48, "the arena reserves 48 bytes for it");
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -852,6 +852,9 @@ __device__ __noinline__ bool seq_step(bool act, uint32_t* fail_hist, int16_t* H,
         __syncwarp();
         build_rows_g<kTier>(changed);
     }
+    // (see repeat_sequence in poa_kernel.cu: a sequence that left the structure untouched can be repeated)
+    if (ok && gl == 0) ws->clean = changed ? 0 : 1;
+    __syncwarp();
     return ok;
 }
 
@@ -879,6 +882,8 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
     int ni = 0, np = 0, ns = 0;
     int k = 0;       // next sequence in the reference's order: -1 = the draft backbone, then the arms
     char* out = nullptr;
+    const uint8_t* memo = nullptr;   // the arm added last: bytes, length, alignment type (decides the markers too)
+    int memo_len = -1, memo_type = -1;
 
     // window `widx` leaves this group: res >= 0 consensus length, -1 copy the draft, -2 hand it to the next tier
     auto finish = [&](int res) {
@@ -943,9 +948,10 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
         if (want && phase != 2) {
             if (res == -3 && !added) res = -1;   // no arm was added: the draft (:150-152)
             if (res == -3) {
-                if (gl == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; }
+                if (gl == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; ws->clean = 0; }
                 phase = 1;
                 k = ni == 0 ? -1 : 0;
+                memo = nullptr;
             } else {
                 finish(res);
             }
@@ -953,28 +959,59 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
         __syncwarp();
         if (!warp_any(phase != 2)) break;
 
-        // ---- the next sequence of every running group
+        // ---- the next sequence of every running group.  A read that repeats the one added last (same bases,
+        // length and kind, and that one left the DAG's structure untouched) aligns identically: its weights are
+        // added along the node path `cur` still holds and the group moves on to its next read, without waiting
+        // for a lock-step trip (repeat_sequence in poa_kernel.cu has the argument).
         const ArmDesc* a = P.arms + first_arm;
         const int n_arms = ni + np + ns;
         GSeq s;
-        s.bytes = nullptr; s.len = 0; s.nb = 2; s.head = false; s.tail = false; s.type = kNW;
-        bool has_seq = false;
-        if (phase == 1) {
+        bool has_seq;
 #pragma unroll 1
-            while (k >= 0 && k < n_arms && a[arm_at(k)].len == 0) ++k;
-            if (k < 0) {   // draft as backbone only without internal arms (:95-101)
-                s.bytes = P.packed + draft_off; s.len = (int)draft_len; s.nb = 4;
-                s.head = true; s.tail = true; s.type = kNW;
-                has_seq = true;
-            } else if (k < n_arms) {
-                const int q = arm_at(k);
-                const ArmDesc d = a[q];
-                s.bytes = P.packed + d.off; s.len = (int)d.len; s.nb = 2;
-                s.head = q < ni + np; s.tail = q < ni || q >= ni + np;
-                s.type = q < ni ? kNW : q < ni + np ? kLOV : kROV;
-                has_seq = true;
+        for (;;) {
+            s.bytes = nullptr; s.len = 0; s.nb = 2; s.head = false; s.tail = false; s.type = kNW;
+            has_seq = false;
+            if (phase == 1) {
+#pragma unroll 1
+                while (k >= 0 && k < n_arms && a[arm_at(k)].len == 0) ++k;
+                if (k < 0) {   // draft as backbone only without internal arms (:95-101)
+                    s.bytes = P.packed + draft_off; s.len = (int)draft_len; s.nb = 4;
+                    s.head = true; s.tail = true; s.type = kNW;
+                    has_seq = true;
+                } else if (k < n_arms) {
+                    const int q = arm_at(k);
+                    const ArmDesc d = a[q];
+                    s.bytes = P.packed + d.off; s.len = (int)d.len; s.nb = 2;
+                    s.head = q < ni + np; s.tail = q < ni || q >= ni + np;
+                    s.type = q < ni ? kNW : q < ni + np ? kLOV : kROV;
+                    has_seq = true;
+                }
             }
+            const bool cand = has_seq && s.nb == 2 && memo != nullptr && ws->clean != 0 && memo_len == s.len && memo_type == s.type;
+            bool diff = false;
+            if (cand) {
+#pragma unroll 1
+                for (int b = gl; b < (s.len + 3) / 4; b += G) diff |= memo[b] != s.bytes[b];
+            }
+            const bool any_diff = Grp<G>::any(diff);   // (a collective: evaluated by every lane, whatever `cand`)
+            const bool rep = cand && !any_diff;
+            if (!warp_any(rep)) break;
+            if (rep) {
+                const Graph v = group_graph<kTier>();
+                const int len = s.len + (s.head ? 1 : 0) + (s.tail ? 1 : 0);
+#pragma unroll 1
+                for (int p = 1 + gl; p < len; p += G) {
+                    const int dst = v.cur[p], src = v.cur[p - 1];
+#pragma unroll 1
+                    for (int e = v.in_head[dst]; e != kNone; e = v.e_next[e])
+                        if (v.e_src[e] == src) { v.e_w[e] = (uint16_t)(v.e_w[e] + 2); break; }
+                }
+                if (gl == 0) ws->n_seq = v.n_seq + 1;
+                ++k;
+            }
+            __syncwarp();
         }
+        if (has_seq && s.nb == 2) { memo = s.bytes; memo_len = s.len; memo_type = s.type; }
         if (warp_any(has_seq)) {
             const bool ok = seq_step<kTier>(has_seq, P.fail_hist, H, s, sc);
             if (has_seq) {

@@ -1371,14 +1371,51 @@ __device__ __noinline__ bool add_sequence(GState& st, const Caps& caps_dyn, int1
     // a read that only re-walks existing nodes and edges leaves the DAG's structure, hence every
     // order, unchanged
     const int nodes_after = ws->n_nodes;
-    if (nodes_after == nodes_before && ws->n_edges == edges_before) return true;
+    if (nodes_after == nodes_before && ws->n_edges == edges_before) {
+        if (lane == 0) ws->clean = 1;
+        __syncwarp();
+        return true;
+    }
     // new nodes must be ranked; new edges alone keep the current order valid (they follow it),
     // but either may change what spoa's DFS would produce
     if (nodes_after != nodes_before) order_update<kSmem, kTier>(st, len, nodes_before);
-    if (lane == 0) ws->exact = 0;
+    if (lane == 0) { ws->exact = 0; ws->clean = 0; }
     __syncwarp();
     build_rows<kSmem, kTier>(st);
     return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Repeated reads.  Most reads of a real window are identical (Illumina reads of a 100 bp window are error-free
+// four times out of five).  If the sequence added last left the DAG's structure untouched (it only re-walked
+// existing nodes and edges: WarpState::clean) and the next sequence has the same bases, length and alignment
+// type, then its DP matrix - a function of the DAG's structure, the order and the sequence - is the same matrix,
+// its traceback the same path and its fusion the same node path, which `cur` still holds: the reference would
+// compute all of that again and arrive at exactly the weight increments below (graph.cpp:99-115,283-288).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool same_packed(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int nbytes) {
+    bool diff = false;
+#pragma unroll 1
+    for (int i = lane_id(); i < nbytes; i += 32) diff |= a[i] != b[i];
+    return !__any_sync(kFull, diff);
+}
+template <bool kSmem, int kTier>
+__device__ __noinline__ void repeat_sequence(const GState& st, int len, uint16_t* path) {
+    const Graph g = make_graph<kSmem, kTier>(st);
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int p = lane; p < len; p += 32) {
+        const int dst = g.cur[p];
+        if (path) path[p] = (uint16_t)dst;
+        if (p >= 1) {
+            const int src = g.cur[p - 1];
+#pragma unroll 1
+            for (int e = g.in_head[dst]; e != kNone; e = g.e_next[e])
+                if (g.e_src[e] == src) { g.e_w[e] = (uint16_t)(g.e_w[e] + 2); break; }
+        }
+    }
+    if (lane == 0) g.ws->n_seq = g.n_seq + 1;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1412,9 +1449,21 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
 
     WarpState* const ws = warp_state<kSmem, kTier>(g);
     if (lane == 0) {
-        ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1;
+        ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; ws->clean = 0;
         if constexpr (kProjects<kOneTile, kTier>) { ws->n_total = n_added + (w.n_internal == 0); ws->base = 0; ws->need = 0; }
     }
+    // the arm added last (repeat_sequence): its bytes, length and kind (0 internal, 1 prefix, 2 suffix)
+    const uint8_t* memo = nullptr;
+    int memo_len = -1, memo_kind = -1;
+    auto repeated = [&](const SeqSrc& q, int kind) -> bool {
+        const bool cand = memo != nullptr && ws->clean != 0 && memo_kind == kind && memo_len == q.len;
+        if (cand && same_packed(memo, q.bytes, (q.len + 3) / 4)) {
+            repeat_sequence<kSmem, kTier>(g, q.len + (q.head ? 1 : 0) + (q.tail ? 1 : 0), nullptr);
+            return true;
+        }
+        memo = q.bytes; memo_len = q.len; memo_kind = kind;
+        return false;
+    };
     __syncwarp();
     SeqSrc s;
     s.ascii = nullptr;
@@ -1458,6 +1507,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     for (uint32_t k = 0; k < w.n_internal; ++k) {   // :102-110
         if (a[k].len == 0) continue;
         s.bytes = P.packed + a[k].off; s.len = a[k].len; s.head = true; s.tail = true; s.type = kNW;
+        if (repeated(s, 0)) continue;
         if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* pre = a + w.n_internal;
@@ -1465,6 +1515,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     for (int k = (int)w.n_pre - 1; k >= 0; --k) {   // :112-121, reverse order, kLOV
         if (pre[k].len == 0) continue;
         s.bytes = P.packed + pre[k].off; s.len = pre[k].len; s.head = true; s.tail = false; s.type = kLOV;
+        if (repeated(s, 1)) continue;
         if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
     const ArmDesc* suf = pre + w.n_pre;
@@ -1472,6 +1523,7 @@ __device__ __forceinline__ int run_short(GState& g, const Params& P, const Caps&
     for (uint32_t k = 0; k < w.n_suf; ++k) {   // :123-132, kROV
         if (suf[k].len == 0) continue;
         s.bytes = P.packed + suf[k].off; s.len = suf[k].len; s.head = false; s.tail = true; s.type = kROV;
+        if (repeated(s, 2)) continue;
         if (!add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, s, sc, nullptr)) return -2;
     }
 #endif
@@ -1525,9 +1577,11 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         WarpState* const ws = warp_state<kSmem, kTier>(g);
         __syncwarp();
         if (lane == 0) {
-            ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1;
+            ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; ws->clean = 0;
             ws->n_total = n_added + 1; ws->base = 0; ws->need = 0;
         }
+        const uint8_t* memo = nullptr;   // the arm added last (repeat_sequence)
+        int memo_len = -1;
         __syncwarp();
         uint32_t used = 0;
         SeqSrc s;
@@ -1539,7 +1593,15 @@ __device__ __forceinline__ int run_long(GState& g, const Params& P, const Caps& 
         auto add = [&](const SeqSrc& q) -> bool {
             if (used + (uint32_t)q.len > pcap) return give_up(g, kFailPaths);
             if (lane == 0) pstart[ws->n_seq] = used;
-            const bool ok = add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, q, sc, pnodes + used);
+            bool ok = true;
+            const bool cand = q.nb == 2 && memo != nullptr && ws->clean != 0 && memo_len == q.len;
+            if (cand && same_packed(memo, q.bytes, (q.len + 3) / 4)) {
+                repeat_sequence<kSmem, kTier>(g, q.len, pnodes + used);
+            } else {
+                memo = q.nb == 2 ? q.bytes : nullptr;
+                memo_len = q.len;
+                ok = add_sequence<kSmem, kOneTile, kTier, kWide>(g, caps, H, q, sc, pnodes + used);
+            }
             used += q.len;
             return ok;
         };

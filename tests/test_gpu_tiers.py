@@ -286,7 +286,7 @@ def test_estimate_driven_shared_memory_tier_forced():
 def test_noisy_long_windows_run_in_the_estimate_driven_tier():
     """LONG windows of noisy reads outgrow T1 (1024 nodes) and are re-run in T2s; the noisiest outgrow its
     estimate as well and end in the bound-driven tiers.  Bytes never change."""
-    for err, n in ((0.03, 40), (0.08, 24)):
+    for err, n in ((0.05, 40), (0.10, 24)):
         b = synth_batch(121, n, 420, 24, "internal", err, wtype=WINDOW_LONG)
         want, _ = oracle_consensus(b)
         _same(native.consensus(b), want, b, f"LONG err {err}")
