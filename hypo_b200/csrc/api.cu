@@ -186,7 +186,8 @@ struct RouteCfg {
 struct Options {
     int first_tier = 0;   // routing starts here (tests / measurements force the later tiers with it; 8 / 9 = the
                           // group tiers: windows that do not fit them are routed as from tier 0)
-    int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp)
+    int group_tiers = 1;  // small SHORT windows start in the group tiers (several windows per warp): 0 never, 1 in
+                          // batches of at least kGroupMinWindows windows, 2 always
     int group_sort = 1;   // the group tiers' lists are ordered by window size (a warp's windows run in lock-step)
     int teams = 1;        // bound-driven tiers: four warps per window when a launch has few windows
     int big_tier = 1;     // large windows whose estimated DAG fits shared memory start in T2s, not T2
@@ -197,6 +198,7 @@ struct Options {
 };
 
 constexpr int kPasses = 2;   // head and tail of the pipelined host-buffer path
+constexpr uint64_t kGroupMinWindows = 131072;   // batches (passes) below this size do not use the group tiers
 constexpr uint32_t kProbe = 4096;            // windows of a tier's list that run first, alone ...
 constexpr uint32_t kProbeMin = 4 * kProbe;   // ... when the list holds at least this many
 
@@ -482,8 +484,11 @@ inline uint64_t* host_words(Ctx& g) { return (uint64_t*)((char*)g.pinned_ctrl + 
 
 // Stage 1 of a pass: classify + route `n_win` windows.  Nothing is synchronised here; the caller copies
 // the control block back (fetch_ctrl) together with whatever else it needs and synchronises ONCE.
+// `n_call`: windows of the whole call this pass belongs to (the head / tail passes of one batch decide alike).
 int stage_classify(Ctx& g, const WinDesc* d_win, uint64_t n_win, const ArmDesc* d_arms, uint64_t a_lo, uint64_t a_hi,
-                   uint64_t b_lo, uint64_t b_hi, WinStat* d_stats, uint64_t* d_bound, cudaStream_t stream) {
+                   uint64_t b_lo, uint64_t b_hi, WinStat* d_stats, uint64_t* d_bound, cudaStream_t stream,
+                   uint64_t n_call = 0) {
+    if (n_call < n_win) n_call = n_win;
     if (n_win > 0xfffffff0ull) return fail(HYPO_E_ARG, "too many windows in one batch");
     CUDA_TRY(g.ctrl.reserve(sizeof(DevCtrl)));
     // tier lists, the list of windows no tier could hold, and the per-window size projections
@@ -499,8 +504,10 @@ int stage_classify(Ctx& g, const WinDesc* d_win, uint64_t n_win, const ArmDesc* 
         cfg.est_cap[t] = kTiers[t].est_cap;
     }
     cfg.first_tier = std::min(std::max(G.opt.first_tier, 0), kNumTiers - 1);
+    // (a small batch is better off in ONE launch of the compact tier than in three launches with their tails:
+    // measured on the captured 88 613-window set, 698 vs 610 Mbp/s; from ~250 K windows on the group tiers win)
     cfg.group_mode = cfg.first_tier == kTierQuad ? 1 : cfg.first_tier == kTierHalf ? 2
-                     : (cfg.first_tier == 0 && G.opt.group_tiers) ? 1 : 0;
+                     : (cfg.first_tier == 0 && (G.opt.group_tiers == 2 || (G.opt.group_tiers == 1 && n_call >= kGroupMinWindows))) ? 1 : 0;
     cfg.big_mode = cfg.first_tier == kTierBig ? 2 : (cfg.first_tier < 6 && G.opt.big_tier) ? 1 : 0;
     cfg.est_cap[kTierBig] = (uint32_t)kTiers[kTierBig].ncap;
     if (cfg.first_tier > kLastTier) cfg.first_tier = 0;
@@ -890,7 +897,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
         CUDA_TRY(cudaStreamWaitEvent(s, g.ev_head, 0));
         CUDA_TRY(cudaMemsetAsync(g.out_len.p, 0, sizeof(uint32_t) * n_win, s));
         // head descriptors must only reference what has arrived: limits a_s / b_s
-        if (int rc = stage_classify(g, d_win, w_s, d_arms, sh.a0, a_s, sh.b0, b_s, d_stats, d_bound, s)) return rc;
+        if (int rc = stage_classify(g, d_win, w_s, d_arms, sh.a0, a_s, sh.b0, b_s, d_stats, d_bound, s, n_win)) return rc;
         CUDA_TRY(cudaMemsetAsync(d_bound + w_s, 0, sizeof(uint64_t), s));
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp.p, tmp_bytes, d_bound, d_pos, w_s + 1, s));
         ++G.launches;
@@ -914,7 +921,7 @@ int shard_compute(Ctx& g, const WinDesc* win, const ArmDesc* arms, const uint8_t
         CUDA_TRY(cudaStreamWaitEvent(s, g.ev_tail, 0));
         const uint64_t n_tail = n_win - w_s;
         if (int rc = stage_classify(g, d_win + w_s, n_tail, d_arms, sh.a0, sh.a1, sh.b0, sh.b1, d_stats + w_s,
-                                    d_bound + w_s, s))
+                                    d_bound + w_s, s, n_win))
             return rc;
         CUDA_TRY(cudaMemsetAsync(d_bound + n_win, 0, sizeof(uint64_t), s));
         CUDA_TRY(cub::DeviceScan::ExclusiveScan(g.cub_tmp.p, tmp_bytes, d_bound + w_s, d_pos + w_s, cuda::std::plus<>{},
@@ -1252,7 +1259,7 @@ int hypo_gpu_set_option(const char* name, int64_t value) {
         if (value < 0 || value >= kNumTiers) return fail(HYPO_E_ARG, "first_tier must be 0..%d", kNumTiers - 1);
         G.opt.first_tier = (int)value;
     } else if (!strcmp(name, "group_tiers")) {
-        if (value != 0 && value != 1) return fail(HYPO_E_ARG, "group_tiers must be 0 or 1");
+        if (value < 0 || value > 2) return fail(HYPO_E_ARG, "group_tiers must be 0, 1 or 2");
         G.opt.group_tiers = (int)value;
     } else if (!strcmp(name, "big_tier")) {
         if (value != 0 && value != 1) return fail(HYPO_E_ARG, "big_tier must be 0 or 1");

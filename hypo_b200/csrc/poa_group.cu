@@ -882,7 +882,8 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
     int ni = 0, np = 0, ns = 0;
     int k = 0;       // next sequence in the reference's order: -1 = the draft backbone, then the arms
     char* out = nullptr;
-    const uint8_t* memo = nullptr;   // the arm added last: bytes, length, alignment type (decides the markers too)
+    // the arm added last: its packed byte `gl`, length, alignment type (decides the markers too)
+    uint32_t memo_byte = 0xffffffffu;
     int memo_len = -1, memo_type = -1;
 
     // window `widx` leaves this group: res >= 0 consensus length, -1 copy the draft, -2 hand it to the next tier
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
                 if (gl == 0) { ws->n_nodes = 0; ws->n_edges = 0; ws->n_al = 0; ws->n_seq = 0; ws->exact = 1; ws->clean = 0; }
                 phase = 1;
                 k = ni == 0 ? -1 : 0;
-                memo = nullptr;
+                memo_len = -1;
             } else {
                 finish(res);
             }
@@ -967,6 +968,7 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
         const int n_arms = ni + np + ns;
         GSeq s;
         bool has_seq;
+        uint32_t my_byte = 0xffffffffu;
 #pragma unroll 1
         for (;;) {
             s.bytes = nullptr; s.len = 0; s.nb = 2; s.head = false; s.tail = false; s.type = kNW;
@@ -987,13 +989,13 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
                     has_seq = true;
                 }
             }
-            const bool cand = has_seq && s.nb == 2 && memo != nullptr && ws->clean != 0 && memo_len == s.len && memo_type == s.type;
-            bool diff = false;
-            if (cand) {
-#pragma unroll 1
-                for (int b = gl; b < (s.len + 3) / 4; b += G) diff |= memo[b] != s.bytes[b];
-            }
-            const bool any_diff = Grp<G>::any(diff);   // (a collective: evaluated by every lane, whatever `cand`)
+            // (lane b of the group keeps packed byte b of the read added last in a register: a group's reads have
+            // at most 4 G symbols = G bytes, so the comparison costs one byte load per lane - of the bytes the
+            // decode is about to read anyway)
+            my_byte = 0xffffffffu;
+            if (has_seq && s.nb == 2 && gl < (s.len + 3) / 4) my_byte = s.bytes[gl];
+            const bool cand = has_seq && s.nb == 2 && memo_len == s.len && memo_type == s.type && s.len <= 4 * G && ws->clean != 0;
+            const bool any_diff = Grp<G>::any(my_byte != memo_byte);   // (a collective: evaluated by every lane, whatever `cand`)
             const bool rep = cand && !any_diff;
             if (!warp_any(rep)) break;
             if (rep) {
@@ -1006,12 +1008,18 @@ __global__ void __launch_bounds__(256, 3) poa_group_kernel(const Params P) {
                     for (int e = v.in_head[dst]; e != kNone; e = v.e_next[e])
                         if (v.e_src[e] == src) { v.e_w[e] = (uint16_t)(v.e_w[e] + 2); break; }
                 }
-                if (gl == 0) ws->n_seq = v.n_seq + 1;
                 ++k;
             }
+            __syncwarp();   // (every lane has taken its snapshot of the counts)
+            if (rep && gl == 0) ws->n_seq += 1;
             __syncwarp();
         }
-        if (has_seq && s.nb == 2) { memo = s.bytes; memo_len = s.len; memo_type = s.type; }
+        // the read that goes through the DP now is the one a later read may repeat
+        memo_len = -1;
+        if (has_seq && s.nb == 2) {
+            memo_len = s.len; memo_type = s.type;
+            memo_byte = my_byte;
+        }
         if (warp_any(has_seq)) {
             const bool ok = seq_step<kTier>(has_seq, P.fail_hist, H, s, sc);
             if (has_seq) {

@@ -1414,6 +1414,7 @@ __device__ __noinline__ void repeat_sequence(const GState& st, int len, uint16_t
                 if (g.e_src[e] == src) { g.e_w[e] = (uint16_t)(g.e_w[e] + 2); break; }
         }
     }
+    __syncwarp();   // (every lane has taken its snapshot of the counts)
     if (lane == 0) g.ws->n_seq = g.n_seq + 1;
     __syncwarp();
 }

@@ -121,8 +121,9 @@ int hypo_gpu_device_count(void);
  *                      windows that do not fit them are routed as from tier 0)
  *   "big_tier"   0|1   large windows whose estimated DAG fits shared memory start in T2s instead of the
  *                      bound-driven tier T2 (default 1)
- *   "group_tiers" 0|1  small SHORT windows (<= 63 symbols) start in the group tiers, several windows per
- *                      warp (default 1; only changes where windows run)
+ *   "group_tiers" 0|1|2  small SHORT windows (<= 63 symbols) start in the group tiers, several windows per
+ *                      warp: 0 never, 1 in batches of at least 131072 windows (default: a small batch is better
+ *                      off in one launch of the compact tier), 2 always; only changes where windows run
  *   "group_sort" 0|1   tier lists are ordered on the device before they run: by size class for the group tiers
  *                      (the windows of a warp advance in lock-step), by estimated cost, largest first, for
  *                      the others (default 1)

@@ -22,7 +22,7 @@ KINDS = ("internal", "backbone", "prefix", "suffix", "mixed")
 def _init():
     native.init(DEFAULT_SCORES, 0)
     native.set_option("first_tier", 0)
-    native.set_option("group_tiers", 1)
+    native.set_option("group_tiers", 2)   # (the default, 1, only uses them for batches of >= 131072 windows)
     yield
     native.set_option("first_tier", 0)
     native.set_option("group_tiers", 1)

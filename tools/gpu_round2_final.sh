@@ -10,6 +10,7 @@ python bench.py --mix pipeline --windows 4000000 2>/dev/null | tail -1 > gpurun_
 python bench.py --mix pipeline --windows 4000000 --no-cpu-baseline --no-e2e --option group_tiers=0 2>/dev/null | tail -1 > gpurun_out/${R}_bench_pipeline_mix_one_warp_tiers_only.json
 python bench.py --stream data/captured/ecoli5mb_ctg1.inspect.gz data/captured/ecoli5mb_ctg2.inspect.gz 2>/dev/null | tail -1 > gpurun_out/${R}_bench_ecoli5mb.json
 python bench.py --stream data/captured/ecoli5mb_ctg1.inspect.gz data/captured/ecoli5mb_ctg2.inspect.gz --repeat 12 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/${R}_bench_capture_x12.json
+python bench.py --stream data/captured/ecoli5mb_ctg1.inspect.gz data/captured/ecoli5mb_ctg2.inspect.gz --no-cpu-baseline --no-e2e --option group_tiers=2 2>/dev/null | tail -1 > gpurun_out/${R}_bench_ecoli5mb_group_tiers_forced.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${R}_launches_pipeline_mix.csv \
     python bench.py --mix pipeline --windows 1000000 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-compute-roofline > gpurun_out/${R}_launches_mix.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:poa_group_kernel -s 1 -c 1 -o gpurun_out/${R}_gprof -f \
@@ -20,7 +21,8 @@ python bench.py --impl reference 2>/dev/null | tail -1 > gpurun_out/${R}_bench_r
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log
 HYPO_SANITIZE_NO_TEAMS=1 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_run.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log
 timeout 600 compute-sanitizer --tool racecheck --print-limit 6 python tools/sanitize_run.py > gpurun_out/sanitizer_racecheck_teams.log 2>&1; echo "racecheck (teams) exit $?" >> gpurun_out/sanitizer_racecheck_teams.log
-tail -3 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_racecheck_teams.log
+for f in gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_racecheck_teams.log; do tail -n 3 $f; done
+timeout 400 python tools/fuzz_parity.py 240 31337 2>&1 | tail -3 | tee gpurun_out/${R}_fuzz.txt
 for f in gpurun_out/${R}_bench_*.json; do echo "== $f"; python - "$f" <<'PY'
 import json, sys
 try:

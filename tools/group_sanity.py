@@ -16,6 +16,7 @@ for i in range(n):
                                err=float(rng.choice([0.0, 0.02, 0.08]))))
 b = build_batch(specs)
 native.init(DEFAULT_SCORES, 0)
+native.set_option("group_tiers", 2)   # always (by default only batches of >= 131072 windows use the group tiers)
 got = native.consensus(b)
 _, _, tiers = native.last_timing()
 want, _ = oracle_consensus(b)

@@ -28,6 +28,7 @@ for i in range(60):
                                kind=("internal", "backbone", "prefix", "suffix", "mixed")[i % 5], err=float(rng.choice([0.0, 0.02, 0.08]))))
 b = build_batch(specs)
 native.init(DEFAULT_SCORES, 0)
+native.set_option("group_tiers", 2)   # always (by default only batches of >= 131072 windows use the group tiers)
 if NO_TEAMS:
     native.set_option("teams", 0)
 got = native.consensus(b)
