@@ -202,7 +202,7 @@ void WindowBatch::run(size_t chunk_windows) {
             sum += arms * (len * len + 300.0) + 300.0;
         }
         const double avg = sum / (double)std::max<size_t>(cnt, 1), headline = 30.0 * (122.0 * 122.0 + 300.0);
-        scale = std::min(8.0, std::max(1.0, headline / std::max(avg, 1.0)));
+        scale = std::min(4.0, std::max(1.0, headline / std::max(avg, 1.0)));
     }
     const size_t ndev = (size_t)std::max(1, hypo_gpu_device_count()) * (size_t)1;
     const size_t unit = (size_t)((double)ndev * scale + 0.5);   // "devices x scale": what the counts are multiplied by
