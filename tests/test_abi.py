@@ -94,3 +94,33 @@ def test_no_cpu_fallback_without_device():
     b = build_batch([WindowSpec("ACGT", ["ACGT", "ACGT"], [], [], 0, 0)])
     with pytest.raises(native.HypoGpuError):
         native.consensus(b)
+
+
+def test_options_are_validated_without_a_device():
+    """hypo_gpu_set_option is host state: every documented knob accepts its documented range and rejects the rest
+    (the execution shapes - group tiers, list ordering, teams, the estimate-driven tier - only change where windows
+    run, never a result byte, so they are plain integers)."""
+    ok = {"first_tier": (0, 10), "group_tiers": (0, 2), "group_sort": (0, 1), "teams": (0, 1), "big_tier": (0, 1),
+          "probe": (0, 1), "scap": (0, 65534)}
+    defaults = {"first_tier": 0, "group_tiers": 1, "group_sort": 1, "teams": 1, "big_tier": 1, "probe": 1, "scap": 0}
+    try:
+        for name, (lo, hi) in ok.items():
+            native.set_option(name, lo)
+            native.set_option(name, hi)
+            for bad in (lo - 1, hi + 1):
+                with pytest.raises(native.HypoGpuError):
+                    native.set_option(name, bad)
+        with pytest.raises(native.HypoGpuError):
+            native.set_option("no_such_option", 1)
+    finally:
+        for name, v in defaults.items():
+            native.set_option(name, v)
+
+
+def test_tier_histogram_call_checks_its_arguments():
+    lib = native.lib()
+    buf = (ctypes.c_uint32 * 16)(*([7] * 16))
+    assert lib.hypo_gpu_last_tier_windows(buf, 16) == 0
+    assert list(buf) == [0] * 16          # nothing has run; entries beyond the last tier are zero as documented
+    assert lib.hypo_gpu_last_tier_windows(None, 4) != 0
+    assert native.N_TIERS == 11 and (native.TIER_QUAD, native.TIER_HALF, native.TIER_BIG) == (8, 9, 10)
