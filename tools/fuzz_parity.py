@@ -47,7 +47,7 @@ while time.time() < t_end:
         b = concat_batches(parts, {})
         b = b.select(rng.permutation(b.n_win))
     native.init(scores, 0)
-    native.set_option("first_tier", int(rng.choice([0, 0, 0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9])))   # every tier gets its share
+    native.set_option("first_tier", int(rng.choice([0, 0, 0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 10])))   # every tier gets its share
     native.set_option("group_tiers", int(rng.choice([0, 2, 2, 2])))   # (the default, 1, keeps small batches out of the group tiers)
     native.set_option("group_sort", int(rng.random() < 0.7))
     native.set_option("teams", int(rng.random() < 0.8))
