@@ -200,8 +200,9 @@ def side_workloads(a):
     """`extra`: the same metric on the two workloads that look like the reference pipeline's real output - the
     synthetic pipeline shape mix (1 M windows) and the E. coli-sized window set captured from the reference CLI -
     so that the driver's own run carries them too.  Host buffers in, host buffers out (hypo_gpu_consensus_batch);
-    `mbp_per_s_kernels` uses the POA kernels' device time (CUDA events inside the library), `mbp_per_s_host_buffers`
-    the wall clock of the call; a strided sample of the result is checked against the CPU oracle."""
+    `mbp_per_s_kernels` uses the POA kernels' device time (CUDA events inside the library),
+    `mbp_per_s_call_from_pageable_buffers` the wall clock of the call on ordinary (not page-locked) numpy arrays - a
+    lower bound: the e2e figures of `--mix pipeline` / `--stream` runs use the page-locked, chunked `Window` path; a strided sample of the result is checked against the CPU oracle."""
     import argparse as _ap
     import time as _time
     from hypo_b200 import native
@@ -227,7 +228,7 @@ def side_workloads(a):
         want, _ = oracle_consensus(b.select(idx), SCORES)
         out[name] = {"windows": int(b.n_win), "polished_bp": int(b.polished_bp),
                      "mbp_per_s_kernels": b.polished_bp / 1e6 / (float(np.mean(k_ms)) / 1e3),
-                     "mbp_per_s_host_buffers": b.polished_bp / 1e6 / float(np.mean(wall)),
+                     "mbp_per_s_call_from_pageable_buffers": b.polished_bp / 1e6 / float(np.mean(wall)),
                      "tier_windows": native.last_timing()[2],
                      "parity_spot_check": bool([allc[i] for i in idx] == want)}
     return out
