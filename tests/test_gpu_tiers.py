@@ -298,3 +298,43 @@ def test_noisy_long_windows_run_in_the_estimate_driven_tier():
     _same(native.consensus(b), want, b, "SHORT 60 x 480")
     _, _, tiers = native.last_timing()
     assert tiers[native.TIER_BIG] == 0 and tiers[6] == b.n_win, tiers
+
+
+def test_repeated_reads_are_not_aligned_twice():
+    """A read identical to the one added last - when that one left the DAG's structure untouched - is not
+    aligned again: its weights go along the stored node path (repeat_sequence).  Windows made of repeats only
+    (error-free reads), windows where repeats and erroneous reads alternate, prefix / suffix arms, LONG windows
+    (whose per-sequence node paths the repeats must still record): same bytes as the oracle, and the device's
+    DP-cell counter shows that most fills were skipped."""
+    rng = np.random.default_rng(131)
+    specs = []
+    for i in range(300):
+        truth = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=int(rng.integers(20, 110))))
+        bad = truth[: len(truth) // 2] + "A" + truth[len(truth) // 2 + 1:]
+        arms = [truth] * 6 + [bad] + [truth] * 5 + [bad, bad] + [truth] * 8
+        if i % 3 == 0:
+            specs.append(WindowSpec(truth, arms, [], [], 0, 0))
+        elif i % 3 == 1:
+            cut = len(truth) // 2
+            specs.append(WindowSpec(truth, arms[:9], [truth[:cut + 3]] * 5 + [truth[:cut]] * 3, [truth[cut:]] * 6, 0, 0))
+        else:
+            specs.append(WindowSpec(truth, [], [truth[: len(truth) - 2]] * 7, [truth[2:]] * 7, 0, 0))
+    b = build_batch(specs)
+    want, _ = oracle_consensus(b)
+    for first_tier, group_tiers in ((0, 1), (0, 2), (3, 1), (6, 1)):
+        native.set_option("first_tier", first_tier)
+        native.set_option("group_tiers", group_tiers)
+        try:
+            _same(native.consensus(b), want, b, f"repeats tier {first_tier} groups {group_tiers}")
+        finally:
+            native.set_option("group_tiers", 1)
+    native.set_option("first_tier", 0)
+    clean = build_batch([WindowSpec("ACGTTGCAAGGCTTAACCGGTTAA" * 4, ["ACGTTGCAAGGCTTAACCGGTTAA" * 4] * 30, [], [], 0, 0)] * 64)
+    native.consensus(clean)
+    cells_all = 64 * 30 * 99 * 99   # what 30 fills per window would count at the very least
+    assert 0 < native.last_cells() < cells_all // 5, (native.last_cells(), cells_all)
+    # LONG windows: both rounds, node paths recorded for repeated arms too
+    lb = build_batch([WindowSpec(s.draft, list(s.internal) + list(s.internal[:4]), [], [], 0, WINDOW_LONG)
+                      for s in (b.spec(i) for i in range(0, 300, 3))])
+    want, _ = oracle_consensus(lb)
+    _same(native.consensus(lb), want, lb, "LONG repeats")
